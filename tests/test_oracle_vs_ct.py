@@ -1,0 +1,61 @@
+"""CPU: cross-check the C oracle against LIVE compressed_tensors calls (skipped when the package is absent).
+Complements the committed golden vectors with fresh seeds / shapes each format."""
+import pytest
+import torch
+
+from oracle import ct_live as L
+from oracle import oracle as O
+from tests.util import FORMATS, assert_bits_equal, geom_of, synth_weight
+
+pytestmark = pytest.mark.skipif(not L.available(), reason="compressed_tensors not importable")
+
+
+@pytest.mark.parametrize("name", list(FORMATS))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_compress_live(name, dtype):
+    fmt, args = L.format_args(name)
+    _, qtype, nb, sym, *_ = FORMATS[name]
+    for R, C, seed in ((16, 128, 1), (72, 640, 2), (200, 384, 3)):
+        w = synth_weight(R, C, dtype, seed)
+        ref = L.compress(w, fmt, args)
+        got = O.compress(w, fmt, geom_of(name), nb, sym)
+        assert set(ref) == set(got)
+        for k in ref:
+            assert_bits_equal(got[k], ref[k], f"{name}/{dtype}/{R}x{C}:{k}")
+
+
+def test_nvfp4_supplied_global_scale_live():
+    """fused q/k/v (gate/up) layers share min(global_scale): the compressor gets it from the state dict."""
+    fmt, args = L.format_args("nvfp4")
+    w = synth_weight(32, 256, torch.bfloat16, 7)
+    gs = torch.tensor([L.global_scale(w).item() * 0.37])
+    ref = L.compress(w, fmt, args, gs)
+    got = O.compress(w, fmt, geom_of("nvfp4"), 4, True, gs)
+    for k in ref:
+        assert_bits_equal(got[k], ref[k], k)
+
+
+def test_dequantize_roundtrip_live():
+    from compressed_tensors.compressors.base import BaseCompressor
+    from compressed_tensors.quantization import QuantizationScheme
+
+    for name in ("int4_g128_asym", "int4_g32_sym", "fp8_block", "fp8_channel", "nvfp4"):
+        fmt, args = L.format_args(name)
+        _, qtype, nb, sym, *_ = FORMATS[name]
+        w = synth_weight(128, 256, torch.bfloat16, 11)
+        sd = L.compress(w, fmt, args)
+        ref = BaseCompressor.get_value_from_registry(fmt).decompress(sd, QuantizationScheme(targets=["Linear"], weights=args))
+        geom = geom_of(name)
+        if fmt == "pack-quantized":
+            q = O.unpack_from_int32(sd["weight_packed"], nb, w.shape)
+            zp = None
+            if not sym:
+                zp = O.unpack_from_int32(sd["weight_zero_point"], nb, sd["weight_scale"].shape, 0)
+            got = O.dequantize(q, sd["weight_scale"], zp, geom, qtype)
+        elif fmt == "float-quantized":
+            got = O.dequantize(sd["weight"], sd["weight_scale"], None, geom, qtype)
+        else:
+            vals = O.unpack_fp4_from_uint8(sd["weight_packed"], *w.shape)
+            got = O.dequantize(vals, sd["weight_scale"].to(torch.bfloat16), None, geom, qtype, sd["weight_global_scale"],
+                               out_dtype=torch.bfloat16)
+        assert_bits_equal(got, ref["weight"], name)
