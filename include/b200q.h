@@ -1,0 +1,181 @@
+/*
+ * b200q.h -- C ABI of libb200q.so: the B200 (sm_100a) implementation of the quantization hot path behind
+ * mratsim/quantizers' llm-compressor / compressed-tensors recipes.
+ *
+ * The reference has no native code and no FFI; its seams are Python callables.  Every entry
+ * point below names the reference callable it replaces (CT: = compressed_tensors 0.15.0.1, the reference's
+ * pinned dependency, /root/reference/pyproject.toml:8; LLMC: = llmcompressor >= 0.9, pyproject.toml:9).
+ * The Python binding a maintainer would add is quantizers_b200/_lib.py (ctypes); see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless the name ends in _host.
+ *   - the caller owns every buffer; the library allocates nothing persistent except inside an explicit
+ *     b200q_pipeline handle.
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it, nothing synchronises unless
+ *     stated.  No global mutable state: thread-safe when each thread uses its own stream.
+ *   - return 0 on success, negative errno-style code otherwise; b200q_last_error() gives the message
+ *     (thread-local).
+ *   - weights are row-major [batch, rows, cols] (batch = experts of a MoE layer, 1 for a dense Linear).
+ */
+#ifndef B200Q_H
+#define B200Q_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* tensor dtypes (weight / scale) */
+#define B200Q_BF16 0
+#define B200Q_F16 1
+#define B200Q_F32 2
+/* QuantizationType x num_bits  (CT:quantization/quant_args.py:91-98) */
+#define B200Q_INT 0 /* type=int,   num_bits in {4,8} */
+#define B200Q_FP8 1 /* type=float, num_bits=8 (float8_e4m3fn) */
+#define B200Q_FP4 2 /* type=float, num_bits=4 (e2m1, NVFP4) */
+/* QuantizationStrategy (CT:quantization/quant_args.py:100-112) */
+#define B200Q_TENSOR 0
+#define B200Q_CHANNEL 1
+#define B200Q_GROUP 2 /* GROUP and TENSOR_GROUP */
+#define B200Q_BLOCK 3
+
+/* mirrors the fields of CT QuantizationArgs that change the arithmetic (quant_args.py:157-408) */
+typedef struct b200q_scheme {
+    int32_t dtype;      /* B200Q_BF16 / F16 / F32: dtype of the weight, of weight_scale and of all rounding */
+    int32_t qtype;      /* B200Q_INT / FP8 / FP4 */
+    int32_t num_bits;   /* 4 or 8 */
+    int32_t symmetric;  /* 1 / 0 */
+    int32_t strategy;   /* B200Q_TENSOR / CHANNEL / GROUP / BLOCK */
+    int32_t group_size; /* GROUP: 16, 32, 64, 128 or 256 */
+    int32_t block_h;    /* BLOCK: 128 */
+    int32_t block_w;    /* BLOCK: 128 */
+    int32_t has_zp;     /* 1 when the caller's state dict carries a zero-point tensor (adds +0: -0.0 -> +0.0) */
+    int32_t reserved;
+} b200q_scheme;
+
+const char* b200q_last_error(void);
+int b200q_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused  observer -> calculate_qparams -> quantize -> pack   (one HBM read of the weight)
+ * Replaces, for one Linear weight (or a batch of expert weights):
+ *   LLMC update_weight_zp_scale (memoryless_minmax Observer.forward -> CT calculate_qparams, helpers.py:50-137)
+ *   + CT Compressor.compress  (pack_quantized/base.py:36-77 | naive_quantized/base.py:34-82 | nvfp4/base.py:40-72)
+ * Outputs are exactly the state-dict tensors CT emits.
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* pack-quantized (INT4/INT8, GROUP or CHANNEL):
+ *   packed     int32 [batch, rows, ceil(cols*num_bits/32)]
+ *   scale      T     [batch, rows, n_groups]            (n_groups = cols/group_size, 1 for CHANNEL)
+ *   zp_packed  int32 [batch, ceil(rows*num_bits/32), n_groups]  (asymmetric only; may be NULL when symmetric) */
+int b200q_compress_int_packed(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* scheme,
+                              int32_t* packed, void* scale, int32_t* zp_packed, void* stream);
+
+/* float-quantized (FP8 e4m3; CHANNEL, GROUP, BLOCK 128x128 or TENSOR):
+ *   q      uint8 (float8_e4m3fn bits) [batch, rows, cols]
+ *   scale  T [batch, rows, 1] | [batch, rows, n_groups] | [batch, ceil(rows/128), ceil(cols/128)] | [batch, 1]
+ *   workspace: TENSOR strategy only, >= 4*batch bytes (device), else may be NULL */
+int b200q_compress_fp8(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* scheme,
+                       uint8_t* q, void* scale, void* workspace, void* stream);
+
+/* nvfp4-pack-quantized (e2m1 codes, e4m3 per-16 scales, fp32 global scale):
+ *   global_scale fp32 [batch] : INPUT when compute_global != 0 is false; otherwise OUTPUT, computed from each
+ *                weight's absmax (LLMC Observer.get_global_scale -> CT generate_gparam, helpers.py:309-338).
+ *                Fused q/k/v and gate/up siblings: call b200q_global_scale per tensor, take the min on the
+ *                host side (LLMC update_fused_layer_weight_global_scales), then pass compute_global = 0.
+ *   packed  uint8 [batch, rows, cols/2];  scale_e4m3 uint8 [batch, rows, cols/16] */
+int b200q_compress_nvfp4(const void* weight, int64_t batch, int64_t rows, int64_t cols, int32_t dtype,
+                         int32_t compute_global, float* global_scale, uint8_t* packed, uint8_t* scale_e4m3, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Observers  (LLMC observers/min_max.py + observers/base.py, restated in SURVEY.md Appendix A)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* O1: min / max per quantization chunk (flatten_for_calibration + amin/amax).  mn, mx: T, qparam-grid shaped. */
+int b200q_minmax(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* scheme, void* mn,
+                 void* mx, void* stream);
+/* O2 + Q2: per-tensor global scale = generate_gparam(min, max) -> fp32 [batch].
+ * Also O3 (static_minmax activation global scale): pass running != 0 to fold the previous min/max kept in
+ * minmax_state (fp32 [batch,2], initialise to {+inf,-inf}) before deriving the scale. */
+int b200q_global_scale(const void* x, int64_t batch, int64_t numel, int32_t dtype, float* minmax_state, int32_t running,
+                       float* global_scale, void* stream);
+/* Q1: calculate_qparams(min_vals, max_vals, args, global_scale) CT:quantization/utils/helpers.py:50-137
+ *   scale: T (fp32 when global_scale != NULL; e4m3-rounded values for FP4); zp: int8 (INT only, else untouched) */
+int b200q_calculate_qparams(const void* mn, const void* mx, int64_t n, const b200q_scheme* scheme,
+                            const float* global_scale, void* scale, int8_t* zp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Un-fused element-wise path with caller-supplied qparams (AWQ inner loop, decompression, round trips)
+ *   scale: T, qparam-grid shaped; zp: int8 (INT) or NULL; global_scale: fp32[1] device or NULL
+ * ------------------------------------------------------------------------------------------------------- */
+/* Q3: CT quantize()  forward.py:37-73 -> codes: int8 (INT) | e4m3 bytes (FP8) | e2m1 grid values as T (FP4) */
+int b200q_quantize(const void* x, int64_t rows, int64_t cols, const b200q_scheme* scheme, const void* scale,
+                   const int8_t* zp, const float* global_scale, uint8_t* codes, void* stream);
+/* Q3 + Q7/Q8 fused: CT Compressor.compress with the module's existing qparams (compressors/pack_quantized/base.py:36-77,
+ * nvfp4/base.py:40-72, naive_quantized/base.py:34-82): codes written directly in storage layout -- int32 words (INT4),
+ * offset bytes (INT8), e4m3 bytes (FP8), two e2m1 nibbles per byte (FP4).  GROUP strategies (batch of weights). */
+int b200q_quantize_pack(const void* x, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* scheme,
+                        const void* scale, const int8_t* zp, const float* global_scale, void* packed, void* stream);
+/* Q4: CT fake_quantize()  forward.py:149-181 -> out: T [rows, cols] */
+int b200q_fake_quantize(const void* x, int64_t rows, int64_t cols, const b200q_scheme* scheme, const void* scale,
+                        const int8_t* zp, const float* global_scale, void* out, void* stream);
+/* Q5: CT dequantize()  forward.py:77-145.  codes: int8 | e4m3 bytes | (FP4) values as T.  out dtype = scheme->dtype */
+int b200q_dequantize(const void* codes, int64_t rows, int64_t cols, const b200q_scheme* scheme, const void* scale,
+                     const int8_t* zp, const float* global_scale, void* out, void* stream);
+
+/* Q7/Q9: pack_to_int32 / unpack_from_int32  CT:compressors/pack_quantized/helpers.py:20-161 */
+int b200q_pack_int32(const int8_t* value, int64_t rows, int64_t cols, int32_t num_bits, int32_t packed_dim,
+                     int32_t* packed, void* stream);
+int b200q_unpack_int32(const int32_t* packed, int64_t rows, int64_t cols, int32_t num_bits, int32_t packed_dim,
+                       int8_t* value, void* stream);
+/* Q8/Q9: pack_fp4_to_uint8 / unpack_fp4_from_uint8  CT:compressors/nvfp4/helpers.py:34-111 */
+int b200q_pack_fp4(const void* x, int64_t rows, int64_t cols, int32_t dtype, uint8_t* packed, void* stream);
+int b200q_unpack_fp4(const uint8_t* packed, int64_t rows, int64_t cols, int32_t dtype, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * AWQ statistics and search  (LLMC modifiers/awq/base.py, restated in SURVEY.md Appendix A)
+ * ------------------------------------------------------------------------------------------------------- */
+/* O5: _accumulate_mean numerator: acc[k] += sum_t |x[t,k]|  (fp32 [K], caller zero-initialises; all-reduce SUM
+ * across token shards, then divide by the token count) */
+int b200q_abs_sum_cols(const void* x, int64_t tokens, int64_t k, int32_t dtype, float* acc, void* stream);
+/* O5: _compute_layer_means numerator: acc[k] += sum_rows |w| / (group_absmax + 1e-6)  (fp64 [K]) */
+int b200q_wmean_accumulate(const void* weight, int64_t rows, int64_t cols, int32_t dtype, int32_t group_size,
+                           double* acc, void* stream);
+/* W1: scales for one grid point: s = x_mean^r / (w_mean^(1-r) + 1e-4), clamp(min=1e-4)  [duo_scaling]
+ *     | x_mean^r clamp(1e-4);   s /= sqrt(max(s) * min(s));  inf/nan -> 1.   fp32 [K] in, fp32 [K] out.
+ *     n_ratios rows are produced at once: scales [n_ratios, K], ratios fp32 [n_ratios] (host pointer). */
+int b200q_awq_scales(const float* x_mean, const float* w_mean, int64_t k, const float* ratios_host, int32_t n_ratios,
+                     int32_t duo_scaling, float* scales, void* stream);
+/* W1 inner step, fused: W' = fake_quantize(W * s[None,:]) / s[None,:]  with a fresh memoryless_minmax observer
+ * (call_observer + forward_quantize + div), written as T [rows, cols] */
+int b200q_awq_scaled_fake_quantize(const void* weight, int64_t rows, int64_t cols, const b200q_scheme* scheme,
+                                   const float* scales, void* out, void* stream);
+/* W3: _compute_loss partial: acc[0] += sum (bf16(y_ref) - bf16(y_q))^2 in fp32 (device fp32 accumulator) */
+int b200q_sq_err_accumulate(const void* y_ref, const void* y_q, int64_t numel, int32_t dtype, float* acc, void* stream);
+/* W1-W3 fused on the tensor cores: for each of n_ratios pre-fake-quantized weight variants Wq[r] (T [n, k]) compute
+ * loss[r] += sum_{t,n} ( bf16(X Wref^T)[t,n] - bf16(X Wq[r]^T)[t,n] )^2  without materialising the outputs.
+ * tcgen05 / TMEM bf16 GEMM (fp32 accumulate) with the squared-error reduction in the epilogue.  bf16 only. */
+int b200q_awq_gemm_loss(const void* x, int64_t tokens, int64_t k, const void* w_ref, const void* w_q, int64_t n,
+                        int32_t n_ratios, float* loss, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t b200q_awq_gemm_loss_workspace(int64_t tokens, int64_t k, int64_t n, int32_t n_ratios);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Host-buffer pipeline: what LLMC model_free_ptq's per-tensor job does (load -> device -> observe ->
+ * compress -> host), /root/reference/scripts/quant_GLM-4.7-Flash-FP8.py:11-24.  Pinned staging buffers and two
+ * streams live in the handle; weight_host / outputs are HOST pointers (pinned or pageable).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct b200q_pipeline b200q_pipeline;
+int b200q_pipeline_create(b200q_pipeline** out, int64_t max_weight_bytes, int32_t device);
+int b200q_pipeline_destroy(b200q_pipeline* p);
+/* fmt: 0 pack-quantized, 1 float-quantized, 2 nvfp4-pack-quantized; outputs as in the b200q_compress_* calls.
+ * Asynchronous: returns after enqueueing; b200q_pipeline_sync waits for every submitted job. */
+int b200q_pipeline_compress_host(b200q_pipeline* p, const void* weight_host, int64_t batch, int64_t rows, int64_t cols,
+                                 const b200q_scheme* scheme, void* codes_host, void* scale_host, void* zp_host,
+                                 float* global_scale_host);
+int b200q_pipeline_sync(b200q_pipeline* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Q_H */

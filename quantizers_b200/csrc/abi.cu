@@ -1,0 +1,356 @@
+// abi.cu -- the extern "C" surface declared in include/b200q.h.  Argument validation mirrors the reference's
+// ValueErrors: the Python shims turn a negative return code + b200q_last_error() into ValueError.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "../../include/b200q.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace b200q {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace b200q
+
+using namespace b200q;
+
+#define REQ_PTR(p) B200Q_REQUIRE((p) != nullptr, #p " must not be NULL")
+
+static int check_scheme(const b200q_scheme* s) {
+    REQ_PTR(s);
+    B200Q_REQUIRE(s->dtype >= 0 && s->dtype <= 2, "unsupported dtype %d", s->dtype);
+    B200Q_REQUIRE(s->qtype >= 0 && s->qtype <= 2, "Invalid quantization type %d", s->qtype);
+    if (s->qtype == B200Q_INT) B200Q_REQUIRE(s->num_bits == 4 || s->num_bits == 8, "INT num_bits must be 4 or 8, got %d", s->num_bits);
+    if (s->qtype == B200Q_FP8) B200Q_REQUIRE(s->num_bits == 8, "Only num_bits in (4, 8) are supported");
+    if (s->qtype == B200Q_FP4) B200Q_REQUIRE(s->num_bits == 4, "Only num_bits in (4, 8) are supported");
+    if (s->qtype != B200Q_INT) B200Q_REQUIRE(s->symmetric, "Asymmetric Quantization is not supported for float types");
+    B200Q_REQUIRE(s->strategy >= 0 && s->strategy <= 3, "unknown strategy %d", s->strategy);
+    return 0;
+}
+
+extern "C" {
+
+const char* b200q_last_error(void) { return g_err; }
+int b200q_version(void) { return 100; }
+
+int b200q_compress_int_packed(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* sc,
+                              int32_t* packed, void* scale, int32_t* zp_packed, void* stream) {
+    if (int rc = check_scheme(sc)) return rc;
+    B200Q_REQUIRE(sc->qtype == B200Q_INT, "pack-quantized needs an INT scheme");
+    REQ_PTR(weight); REQ_PTR(packed); REQ_PTR(scale);
+    if (!sc->symmetric) B200Q_REQUIRE(zp_packed != nullptr, "Asymmetric quant requires zero-point values");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sc->strategy == B200Q_GROUP) {
+        GroupParams p{};
+        p.w = weight; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = sc->num_bits;
+        p.symmetric = sc->symmetric; p.has_zp = 1; p.scale = scale; p.zp_packed = zp_packed; p.out = packed;
+        return dispatch_group<MODE_COMPRESS>(sc->dtype, QT_INT, p, batch, st);
+    }
+    if (sc->strategy == B200Q_CHANNEL) {
+        TileParams p{};
+        p.w = weight; p.rows = rows; p.cols = cols; p.nbits = sc->num_bits; p.symmetric = sc->symmetric; p.has_zp = 1;
+        p.scale = scale; p.zp_packed = zp_packed; p.out = packed;
+        return launch_channel_compress(sc->dtype, QT_INT, p, batch, st);
+    }
+    set_error("pack-quantized fused compress supports GROUP and CHANNEL strategies (got %d)", sc->strategy);
+    return B200Q_EINVAL;
+}
+
+int b200q_compress_fp8(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* sc, uint8_t* q,
+                       void* scale, void* workspace, void* stream) {
+    if (int rc = check_scheme(sc)) return rc;
+    B200Q_REQUIRE(sc->qtype == B200Q_FP8, "float-quantized needs an FP8 scheme");
+    REQ_PTR(weight); REQ_PTR(q); REQ_PTR(scale);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sc->strategy == B200Q_GROUP) {
+        GroupParams p{};
+        p.w = weight; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = 8; p.symmetric = 1;
+        p.has_zp = sc->has_zp; p.scale = scale; p.out = q;
+        return dispatch_group<MODE_COMPRESS>(sc->dtype, QT_FP8, p, batch, st);
+    }
+    TileParams p{};
+    p.w = weight; p.rows = rows; p.cols = cols; p.nbits = 8; p.symmetric = 1; p.has_zp = sc->has_zp; p.scale = scale;
+    p.out = q; p.workspace = (float*)workspace;
+    if (sc->strategy == B200Q_CHANNEL) return launch_channel_compress(sc->dtype, QT_FP8, p, batch, st);
+    if (sc->strategy == B200Q_BLOCK) {
+        B200Q_REQUIRE(sc->block_h == 128 && sc->block_w == 128, "fused block compress supports block_structure [128,128], got [%d,%d]",
+                      sc->block_h, sc->block_w);
+        return launch_block_fp8_compress(sc->dtype, p, batch, st);
+    }
+    return launch_tensor_fp8_compress(sc->dtype, p, batch, st);
+}
+
+int b200q_compress_nvfp4(const void* weight, int64_t batch, int64_t rows, int64_t cols, int32_t dtype, int32_t compute_global,
+                         float* global_scale, uint8_t* packed, uint8_t* scale_e4m3, void* stream) {
+    REQ_PTR(weight); REQ_PTR(global_scale); REQ_PTR(packed); REQ_PTR(scale_e4m3);
+    B200Q_REQUIRE(cols % 16 == 0, "tensor column shape must be divisible by the given group_size 16 but got %lld", (long long)cols);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (compute_global) {
+        // the min/max state lives in the first 8*batch bytes of the (not yet written) scale output buffer
+        B200Q_REQUIRE(rows * cols / 16 >= 8, "weight too small to stage the min/max state");
+        float* state = (float*)scale_e4m3;
+        B200Q_REQUIRE(((uintptr_t)state & 3) == 0, "scale buffer must be 4-byte aligned");
+        if (int rc = launch_global_scale(dtype, weight, batch, rows * cols, state, 0, global_scale, st)) return rc;
+    }
+    GroupParams p{};
+    p.w = weight; p.rows = rows; p.cols = cols; p.group = 16; p.nbits = 4; p.symmetric = 1; p.has_zp = 1;
+    p.scale = scale_e4m3; p.gs = global_scale; p.gs_stride = 1; p.out = packed;
+    return dispatch_group<MODE_COMPRESS>(dtype, QT_FP4, p, batch, st);
+}
+
+int b200q_minmax(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* sc, void* mn, void* mx,
+                 void* stream) {
+    if (int rc = check_scheme(sc)) return rc;
+    REQ_PTR(weight); REQ_PTR(mn); REQ_PTR(mx);
+    return launch_minmax(sc->dtype, weight, batch, rows, cols, sc->strategy, sc->group_size, sc->block_h, sc->block_w, mn, mx,
+                         (cudaStream_t)stream);
+}
+
+int b200q_global_scale(const void* x, int64_t batch, int64_t numel, int32_t dtype, float* minmax_state, int32_t running,
+                       float* global_scale, void* stream) {
+    REQ_PTR(x); REQ_PTR(minmax_state);
+    return launch_global_scale(dtype, x, batch, numel, minmax_state, running, global_scale, (cudaStream_t)stream);
+}
+
+int b200q_calculate_qparams(const void* mn, const void* mx, int64_t n, const b200q_scheme* sc, const float* global_scale,
+                            void* scale, int8_t* zp, void* stream) {
+    if (int rc = check_scheme(sc)) return rc;
+    REQ_PTR(mn); REQ_PTR(mx); REQ_PTR(scale);
+    return launch_qparams(sc->dtype, sc->qtype, sc->num_bits, sc->symmetric, mn, mx, n, global_scale, scale, zp,
+                          (cudaStream_t)stream);
+}
+
+static int elementwise(int op, const void* x, int64_t rows, int64_t cols, const b200q_scheme* sc, const void* scale,
+                       const int8_t* zp, const float* gs, void* out, void* stream) {
+    if (int rc = check_scheme(sc)) return rc;
+    REQ_PTR(x); REQ_PTR(scale); REQ_PTR(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sc->qtype == B200Q_FP4) B200Q_REQUIRE(gs != nullptr || sc->strategy != B200Q_GROUP || true, "unreachable");
+    const bool vec_ok = cols % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0;
+    const int g = sc->group_size;
+    if (op != EW_DEQUANT && sc->strategy == B200Q_GROUP && vec_ok && (g == 16 || g == 32 || g == 64 || g == 128 || g == 256) &&
+        cols % g == 0 && (sc->qtype != B200Q_FP4 || gs != nullptr)) {
+        GroupParams p{};
+        p.w = x; p.rows = rows; p.cols = cols; p.group = g; p.nbits = sc->num_bits; p.symmetric = sc->symmetric;
+        p.has_zp = sc->has_zp; p.scale = const_cast<void*>(scale); p.zp_in = zp; p.gs = gs; p.gs_stride = 0; p.out = out;
+        return op == EW_QUANT ? dispatch_group<MODE_QUANT>(sc->dtype, sc->qtype, p, 1, st)
+                              : dispatch_group<MODE_FQ>(sc->dtype, sc->qtype, p, 1, st);
+    }
+    ElemParams p{};
+    p.x = x; p.rows = rows; p.cols = cols; p.strategy = sc->strategy; p.group = g; p.bh = sc->block_h; p.bw = sc->block_w;
+    p.nbits = sc->num_bits; p.has_zp = sc->has_zp; p.scale = scale; p.zp = zp; p.gs = gs; p.out = out;
+    return launch_elementwise(op, sc->dtype, sc->qtype, p, st);
+}
+int b200q_quantize(const void* x, int64_t rows, int64_t cols, const b200q_scheme* sc, const void* scale, const int8_t* zp,
+                   const float* gs, uint8_t* codes, void* stream) {
+    return elementwise(EW_QUANT, x, rows, cols, sc, scale, zp, gs, codes, stream);
+}
+int b200q_quantize_pack(const void* x, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* sc, const void* scale,
+                        const int8_t* zp, const float* gs, void* packed, void* stream) {
+    if (int rc = check_scheme(sc)) return rc;
+    REQ_PTR(x); REQ_PTR(scale); REQ_PTR(packed);
+    B200Q_REQUIRE(sc->strategy == B200Q_GROUP, "b200q_quantize_pack handles GROUP strategies; use b200q_quantize + b200q_pack_int32 otherwise");
+    if (sc->qtype == B200Q_FP4) REQ_PTR(gs);
+    GroupParams p{};
+    p.w = x; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = sc->num_bits; p.symmetric = sc->symmetric;
+    p.has_zp = sc->has_zp; p.scale = const_cast<void*>(scale); p.zp_in = zp; p.gs = gs; p.gs_stride = 0; p.out = packed;
+    return dispatch_group<MODE_QUANT_PACK>(sc->dtype, sc->qtype, p, batch, (cudaStream_t)stream);
+}
+int b200q_fake_quantize(const void* x, int64_t rows, int64_t cols, const b200q_scheme* sc, const void* scale, const int8_t* zp,
+                        const float* gs, void* out, void* stream) {
+    return elementwise(EW_FQ, x, rows, cols, sc, scale, zp, gs, out, stream);
+}
+int b200q_dequantize(const void* codes, int64_t rows, int64_t cols, const b200q_scheme* sc, const void* scale, const int8_t* zp,
+                     const float* gs, void* out, void* stream) {
+    return elementwise(EW_DEQUANT, codes, rows, cols, sc, scale, zp, gs, out, stream);
+}
+
+int b200q_pack_int32(const int8_t* value, int64_t rows, int64_t cols, int32_t num_bits, int32_t packed_dim, int32_t* packed,
+                     void* stream) {
+    REQ_PTR(value); REQ_PTR(packed);
+    return launch_pack_int32(value, rows, cols, num_bits, packed_dim, packed, (cudaStream_t)stream);
+}
+int b200q_unpack_int32(const int32_t* packed, int64_t rows, int64_t cols, int32_t num_bits, int32_t packed_dim, int8_t* value,
+                       void* stream) {
+    REQ_PTR(value); REQ_PTR(packed);
+    return launch_unpack_int32(packed, rows, cols, num_bits, packed_dim, value, (cudaStream_t)stream);
+}
+int b200q_pack_fp4(const void* x, int64_t rows, int64_t cols, int32_t dtype, uint8_t* packed, void* stream) {
+    REQ_PTR(x); REQ_PTR(packed);
+    return launch_pack_fp4(dtype, x, rows, cols, packed, (cudaStream_t)stream);
+}
+int b200q_unpack_fp4(const uint8_t* packed, int64_t rows, int64_t cols, int32_t dtype, void* out, void* stream) {
+    REQ_PTR(out); REQ_PTR(packed);
+    return launch_unpack_fp4(dtype, packed, rows, cols, out, (cudaStream_t)stream);
+}
+
+int b200q_abs_sum_cols(const void* x, int64_t tokens, int64_t k, int32_t dtype, float* acc, void* stream) {
+    REQ_PTR(acc);
+    if (tokens == 0) return 0;
+    REQ_PTR(x);
+    return launch_abs_sum_cols(dtype, x, tokens, k, acc, (cudaStream_t)stream);
+}
+int b200q_wmean_accumulate(const void* weight, int64_t rows, int64_t cols, int32_t dtype, int32_t group_size, double* acc,
+                           void* stream) {
+    REQ_PTR(weight); REQ_PTR(acc);
+    return launch_wmean(dtype, weight, rows, cols, group_size, acc, (cudaStream_t)stream);
+}
+int b200q_awq_scales(const float* x_mean, const float* w_mean, int64_t k, const float* ratios_host, int32_t n_ratios,
+                     int32_t duo, float* scales, void* stream) {
+    REQ_PTR(x_mean); REQ_PTR(ratios_host); REQ_PTR(scales);
+    B200Q_REQUIRE(n_ratios >= 0 && n_ratios <= 256, "n_ratios out of range");
+    // ratios travel as kernel-visible memory: stage them at the tail of the output (row n_ratios-1 is written last)
+    cudaStream_t st = (cudaStream_t)stream;
+    float* d_ratios = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&d_ratios, sizeof(float) * n_ratios, st);
+    if (e != cudaSuccess) { set_error("cudaMallocAsync: %s", cudaGetErrorString(e)); return B200Q_ECUDA; }
+    cudaMemcpyAsync(d_ratios, ratios_host, sizeof(float) * n_ratios, cudaMemcpyHostToDevice, st);
+    int rc = launch_awq_scales(x_mean, w_mean, k, d_ratios, n_ratios, duo, scales, st);
+    cudaFreeAsync(d_ratios, st);
+    return rc;
+}
+int b200q_awq_scaled_fake_quantize(const void* weight, int64_t rows, int64_t cols, const b200q_scheme* sc, const float* scales,
+                                   void* out, void* stream) {
+    if (int rc = check_scheme(sc)) return rc;
+    REQ_PTR(weight); REQ_PTR(out);
+    B200Q_REQUIRE(sc->strategy == B200Q_GROUP, "AWQ fused fake-quantize supports GROUP strategies");
+    B200Q_REQUIRE(sc->qtype != B200Q_FP4, "AWQ over NVFP4 goes through b200q_global_scale + b200q_fake_quantize");
+    GroupParams p{};
+    p.w = weight; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = sc->num_bits; p.symmetric = sc->symmetric;
+    p.has_zp = sc->has_zp; p.col_scale = scales; p.out = out;
+    return dispatch_group<MODE_OBS_FQ>(sc->dtype, sc->qtype, p, 1, (cudaStream_t)stream);
+}
+int b200q_sq_err_accumulate(const void* y_ref, const void* y_q, int64_t numel, int32_t dtype, float* acc, void* stream) {
+    REQ_PTR(y_ref); REQ_PTR(y_q); REQ_PTR(acc);
+    return launch_sq_err(dtype, y_ref, y_q, numel, acc, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------- host pipeline
+struct b200q_pipeline {
+    static constexpr int NS = 3;
+    int device;
+    int64_t cap;  // bytes per slot for the weight; outputs get cap/2 + cap/16 + 4096
+    cudaStream_t s_in, s_run, s_out;
+    void* d_w[NS];
+    void* d_codes[NS];
+    void* d_scale[NS];
+    void* d_zp[NS];
+    float* d_gs[NS];
+    void* d_ws[NS];
+    cudaEvent_t ev_in[NS], ev_run[NS], ev_out[NS];
+    bool used[NS];
+    int next;
+};
+
+#define CU(x)                                                                              \
+    do {                                                                                   \
+        cudaError_t e__ = (x);                                                             \
+        if (e__ != cudaSuccess) { set_error("%s: %s", #x, cudaGetErrorString(e__)); return B200Q_ECUDA; } \
+    } while (0)
+
+int b200q_pipeline_create(b200q_pipeline** out, int64_t max_weight_bytes, int32_t device) {
+    REQ_PTR(out);
+    B200Q_REQUIRE(max_weight_bytes > 0, "max_weight_bytes must be positive");
+    CU(cudaSetDevice(device));
+    b200q_pipeline* p = new b200q_pipeline();
+    p->device = device; p->cap = max_weight_bytes; p->next = 0;
+    CU(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < b200q_pipeline::NS; i++) {
+        CU(cudaMalloc(&p->d_w[i], max_weight_bytes));
+        CU(cudaMalloc(&p->d_codes[i], max_weight_bytes / 2 + 256));      // <= 1 byte per 2-byte element
+        CU(cudaMalloc(&p->d_scale[i], max_weight_bytes / 16 + 4096));    // <= T per 16 elements
+        CU(cudaMalloc(&p->d_zp[i], max_weight_bytes / 64 + 4096));
+        CU(cudaMalloc((void**)&p->d_gs[i], 65536 * sizeof(float)));
+        CU(cudaMalloc(&p->d_ws[i], 65536 * sizeof(float)));
+        CU(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&p->ev_run[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+        p->used[i] = false;
+    }
+    *out = p;
+    return 0;
+}
+int b200q_pipeline_destroy(b200q_pipeline* p) {
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->s_in); cudaStreamSynchronize(p->s_run); cudaStreamSynchronize(p->s_out);
+    for (int i = 0; i < b200q_pipeline::NS; i++) {
+        cudaFree(p->d_w[i]); cudaFree(p->d_codes[i]); cudaFree(p->d_scale[i]); cudaFree(p->d_zp[i]); cudaFree(p->d_gs[i]);
+        cudaFree(p->d_ws[i]);
+        cudaEventDestroy(p->ev_in[i]); cudaEventDestroy(p->ev_run[i]); cudaEventDestroy(p->ev_out[i]);
+    }
+    cudaStreamDestroy(p->s_in); cudaStreamDestroy(p->s_run); cudaStreamDestroy(p->s_out);
+    delete p;
+    return 0;
+}
+int b200q_pipeline_sync(b200q_pipeline* p) {
+    REQ_PTR(p);
+    CU(cudaStreamSynchronize(p->s_in));
+    CU(cudaStreamSynchronize(p->s_run));
+    CU(cudaStreamSynchronize(p->s_out));
+    return 0;
+}
+
+int b200q_pipeline_compress_host(b200q_pipeline* p, const void* weight_host, int64_t batch, int64_t rows, int64_t cols,
+                                 const b200q_scheme* sc, void* codes_host, void* scale_host, void* zp_host,
+                                 float* global_scale_host) {
+    REQ_PTR(p); REQ_PTR(weight_host); REQ_PTR(codes_host); REQ_PTR(scale_host);
+    if (int rc = check_scheme(sc)) return rc;
+    const int64_t esz = sc->dtype == B200Q_F32 ? 4 : 2;
+    const int64_t n = batch * rows * cols, wbytes = n * esz;
+    B200Q_REQUIRE(wbytes <= p->cap, "weight of %lld bytes exceeds the pipeline slot (%lld)", (long long)wbytes, (long long)p->cap);
+    B200Q_REQUIRE(batch <= 65535, "batch out of range");
+    int64_t qrows, qcols;
+    switch (sc->strategy) {
+    case B200Q_TENSOR: qrows = 1; qcols = 1; break;
+    case B200Q_CHANNEL: qrows = rows; qcols = 1; break;
+    case B200Q_GROUP: B200Q_REQUIRE(sc->group_size > 0, "group_size required"); qrows = rows; qcols = cols / sc->group_size; break;
+    default: qrows = (rows + 127) / 128; qcols = (cols + 127) / 128; break;
+    }
+    int64_t code_bytes, scale_bytes, zp_bytes = 0;
+    if (sc->qtype == B200Q_INT) {
+        const int pf = 32 / sc->num_bits;
+        code_bytes = batch * rows * ((cols + pf - 1) / pf) * 4;
+        scale_bytes = batch * qrows * qcols * esz;
+        if (!sc->symmetric) { REQ_PTR(zp_host); zp_bytes = batch * ((qrows + pf - 1) / pf) * qcols * 4; }
+    } else if (sc->qtype == B200Q_FP8) {
+        code_bytes = n; scale_bytes = batch * qrows * qcols * esz;
+    } else {
+        REQ_PTR(global_scale_host);
+        code_bytes = n / 2; scale_bytes = n / 16;
+    }
+    CU(cudaSetDevice(p->device));
+    const int s = p->next;
+    p->next = (p->next + 1) % b200q_pipeline::NS;
+    if (p->used[s]) CU(cudaStreamWaitEvent(p->s_in, p->ev_out[s], 0));  // slot reuse: previous D2H must have drained
+    CU(cudaMemcpyAsync(p->d_w[s], weight_host, wbytes, cudaMemcpyHostToDevice, p->s_in));
+    CU(cudaEventRecord(p->ev_in[s], p->s_in));
+    CU(cudaStreamWaitEvent(p->s_run, p->ev_in[s], 0));
+    int rc;
+    if (sc->qtype == B200Q_INT)
+        rc = b200q_compress_int_packed(p->d_w[s], batch, rows, cols, sc, (int32_t*)p->d_codes[s], p->d_scale[s], (int32_t*)p->d_zp[s], p->s_run);
+    else if (sc->qtype == B200Q_FP8)
+        rc = b200q_compress_fp8(p->d_w[s], batch, rows, cols, sc, (uint8_t*)p->d_codes[s], p->d_scale[s], p->d_ws[s], p->s_run);
+    else
+        rc = b200q_compress_nvfp4(p->d_w[s], batch, rows, cols, sc->dtype, 1, p->d_gs[s], (uint8_t*)p->d_codes[s], (uint8_t*)p->d_scale[s], p->s_run);
+    if (rc) return rc;
+    CU(cudaEventRecord(p->ev_run[s], p->s_run));
+    CU(cudaStreamWaitEvent(p->s_out, p->ev_run[s], 0));
+    CU(cudaMemcpyAsync(codes_host, p->d_codes[s], code_bytes, cudaMemcpyDeviceToHost, p->s_out));
+    CU(cudaMemcpyAsync(scale_host, p->d_scale[s], scale_bytes, cudaMemcpyDeviceToHost, p->s_out));
+    if (zp_bytes) CU(cudaMemcpyAsync(zp_host, p->d_zp[s], zp_bytes, cudaMemcpyDeviceToHost, p->s_out));
+    if (sc->qtype == B200Q_FP4) CU(cudaMemcpyAsync(global_scale_host, p->d_gs[s], batch * sizeof(float), cudaMemcpyDeviceToHost, p->s_out));
+    CU(cudaEventRecord(p->ev_out[s], p->s_out));
+    p->used[s] = true;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// awq_stats.cu -- AWQ statistics (LLMC modifiers/awq/base.py, restated in SURVEY.md Appendix A):
+//   abs_sum_cols   _accumulate_mean numerator     sum_t |x[t,k]|
+//   wmean          _compute_layer_means numerator sum_rows |w| / (chunk_absmax + 1e-6), fp64 accumulate
+//   awq_scales     _compute_best_scale grid point s = x_mean^r / (w_mean^(1-r) + 1e-4) ... / sqrt(max*min)
+//   sq_err         _compute_loss partial          sum (T(y_ref - y_q))^2 in fp32
+// All HBM-bound single-pass reductions (2 B/element for bf16).
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace b200q {
+
+// block (32, 8): x -> 256 columns (8 per thread), y -> row lanes; grid (ceil(K/256), row splits)
+template <int DT>
+__global__ void __launch_bounds__(256) abs_sum_cols_kernel(const void* __restrict__ x, int64_t tokens, int64_t k,
+                                                           float* __restrict__ acc) {
+    __shared__ float sm[8][256 + 8];
+    const int64_t c0 = ((int64_t)blockIdx.x * 32 + threadIdx.x) * 8;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c0 < k) {
+        for (int64_t t = (int64_t)blockIdx.y * 8 + threadIdx.y; t < tokens; t += (int64_t)gridDim.y * 8) {
+            Chunk8<DT> ch;
+            float v[8];
+            load_chunk<DT>(ch, x, t * k + c0);
+            chunk_to_float<DT>(ch, v);
+#pragma unroll
+            for (int i = 0; i < 8; i++) s[i] += fabsf(v[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) sm[threadIdx.y][threadIdx.x * 8 + i] = s[i];
+    __syncthreads();
+    const int tid = threadIdx.y * 32 + threadIdx.x;  // 256 threads -> 256 columns
+    float tot = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; r++) tot += sm[r][tid];
+    const int64_t c = (int64_t)blockIdx.x * 256 + tid;
+    if (c < k) atomicAdd(&acc[c], tot);
+}
+
+int launch_abs_sum_cols(int dt, const void* x, int64_t tokens, int64_t k, float* acc, cudaStream_t st) {
+    B200Q_REQUIRE(k % 8 == 0, "hidden size must be a multiple of 8, got %lld", (long long)k);
+    B200Q_REQUIRE(((uintptr_t)x & 15) == 0, "activation pointer must be 16-byte aligned");
+    if (tokens * k == 0) return B200Q_OK;  // unrouted expert: calibrate_activations skips empty inputs
+    const int64_t gx = (k + 255) / 256;
+    const int64_t gy = max((int64_t)1, min((tokens + 63) / 64, (int64_t)(kNumSMs * 4 + gx - 1) / gx));
+    B200Q_DISPATCH_DT(dt, { abs_sum_cols_kernel<DT><<<dim3((unsigned)gx, (unsigned)gy), dim3(32, 8), 0, st>>>(x, tokens, k, acc); });
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+// one warp per row of the tile, 8 warps stride over rows; lanes own 8 columns of a 256-column tile
+template <int DT>
+__global__ void __launch_bounds__(256) wmean_kernel(const void* __restrict__ w, int64_t rows, int64_t cols, int group,
+                                                    double* __restrict__ acc) {
+    __shared__ double sm[8][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * 256 + lane * 8;
+    const int L = group >> 3;
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int64_t r_per = (rows + gridDim.y - 1) / gridDim.y;
+    const int64_t r_begin = (int64_t)blockIdx.y * r_per, r_end = min(rows, r_begin + r_per);
+    for (int64_t r = r_begin + warp; r < r_begin + ((r_per + 7) / 8) * 8; r += 8) {  // warp-uniform trip count
+        const bool ok = r < r_end && c0 < cols;
+        float v[8];
+        if (ok) {
+            Chunk8<DT> ch;
+            load_chunk<DT>(ch, w, r * cols + c0);
+            chunk_to_float<DT>(ch, v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = 0.0f;
+        }
+        float a = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { v[i] = fabsf(v[i]); a = fmaxf(a, v[i]); }
+        a = subwarp_max(a, L);
+        const float den = round_to<DT>(fadd(a, 1e-6f));
+        if (ok) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) s[i] += (double)round_to<DT>(fdiv(v[i], den));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) sm[warp][lane * 8 + i] = s[i];
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) tot += sm[r][threadIdx.x];
+    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c < cols) atomicAdd(&acc[c], tot);
+}
+
+int launch_wmean(int dt, const void* w, int64_t rows, int64_t cols, int group, double* acc, cudaStream_t st) {
+    B200Q_REQUIRE(group == 16 || group == 32 || group == 64 || group == 128 || group == 256,
+                  "w_mean: group_size %d unsupported (16/32/64/128/256)", group);
+    B200Q_REQUIRE(cols % group == 0, "columns %lld not divisible by group_size %d", (long long)cols, group);
+    B200Q_REQUIRE(((uintptr_t)w & 15) == 0, "weight pointer must be 16-byte aligned");
+    if (rows * cols == 0) return B200Q_OK;
+    const int64_t gx = (cols + 255) / 256;
+    const int64_t gy = max((int64_t)1, min((rows + 31) / 32, (int64_t)(kNumSMs * 4 + gx - 1) / gx));
+    B200Q_DISPATCH_DT(dt, { wmean_kernel<DT><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(w, rows, cols, group, acc); });
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+// one CTA per grid point
+__global__ void __launch_bounds__(256) awq_scales_kernel(const float* __restrict__ x_mean, const float* __restrict__ w_mean,
+                                                         int64_t k, const float* __restrict__ ratios, int duo,
+                                                         float* __restrict__ scales) {
+    __shared__ float smx[8], smn[8];
+    const float r = ratios[blockIdx.x];
+    float* out = scales + (int64_t)blockIdx.x * k;
+    float mx = -INFINITY, mn = INFINITY;
+    for (int64_t i = threadIdx.x; i < k; i += blockDim.x) {
+        float s = powf(x_mean[i], r);
+        if (duo) s = s / (powf(w_mean[i], 1.0f - r) + 1e-4f);
+        s = fmaxf(s, 1e-4f);  // clamp(min=1e-4); NaN stays NaN in torch, fmaxf drops it -> fixed below by the isnan rule
+        out[i] = s;
+        mx = fmaxf(mx, s);
+        mn = fminf(mn, s);
+    }
+    mx = subwarp_max(mx, 32);
+    mn = subwarp_min(mn, 32);
+    if ((threadIdx.x & 31) == 0) { smx[threadIdx.x >> 5] = mx; smn[threadIdx.x >> 5] = mn; }
+    __syncthreads();
+    mx = smx[0]; mn = smn[0];
+    for (int i = 1; i < 8; i++) { mx = fmaxf(mx, smx[i]); mn = fminf(mn, smn[i]); }
+    const float norm = sqrtf(mx * mn);
+    for (int64_t i = threadIdx.x; i < k; i += blockDim.x) {
+        float s = out[i] / norm;
+        if (isinf(s) || isnan(s)) s = 1.0f;
+        out[i] = s;
+    }
+}
+
+int launch_awq_scales(const float* x_mean, const float* w_mean, int64_t k, const float* ratios, int n_ratios, int duo,
+                      float* scales, cudaStream_t st) {
+    if (k == 0 || n_ratios == 0) return B200Q_OK;
+    B200Q_REQUIRE(!duo || w_mean != nullptr, "duo_scaling needs w_mean");
+    awq_scales_kernel<<<n_ratios, 256, 0, st>>>(x_mean, w_mean, k, ratios, duo, scales);
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) sq_err_kernel(const void* __restrict__ a, const void* __restrict__ b, int64_t n,
+                                                     float* __restrict__ acc) {
+    __shared__ float sm[8];
+    float s = 0.0f;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n / 8; t += (int64_t)gridDim.x * blockDim.x) {
+        Chunk8<DT> ca, cb;
+        float x[8], y[8];
+        load_chunk<DT>(ca, a, t * 8);
+        load_chunk<DT>(cb, b, t * 8);
+        chunk_to_float<DT>(ca, x);
+        chunk_to_float<DT>(cb, y);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const float d = round_to<DT>(fadd(x[i], -y[i])); s = fmaf(d, d, s); }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n % 8)) {
+        const float d = round_to<DT>(fadd(load_T<DT>(a, (n / 8) * 8 + threadIdx.x), -load_T<DT>(b, (n / 8) * 8 + threadIdx.x)));
+        s = fmaf(d, d, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.0f;
+        for (int i = 0; i < 8; i++) tot += sm[i];
+        atomicAdd(acc, tot);
+    }
+}
+
+int launch_sq_err(int dt, const void* a, const void* b, int64_t n, float* acc, cudaStream_t st) {
+    B200Q_REQUIRE((((uintptr_t)a | (uintptr_t)b) & 15) == 0, "output pointers must be 16-byte aligned");
+    if (n == 0) return B200Q_OK;
+    const unsigned g = (unsigned)max((int64_t)1, min((n / 8 + 255) / 256, (int64_t)kNumSMs * 8));
+    B200Q_DISPATCH_DT(dt, { sq_err_kernel<DT><<<g, 256, 0, st>>>(a, b, n, acc); });
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+}  // namespace b200q

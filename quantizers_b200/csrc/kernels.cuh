@@ -1,0 +1,74 @@
+// kernels.cuh -- internal launcher interface between the .cu translation units and abi.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200q {
+
+enum : int { MODE_COMPRESS = 0, MODE_QUANT = 1, MODE_FQ = 2, MODE_OBS_FQ = 3, MODE_QUANT_PACK = 4 };
+
+// ---- GROUP / TENSOR_GROUP (quant_group.cu)
+struct GroupParams {
+    const void* w;
+    int64_t rows, cols;
+    int32_t group, nbits, symmetric, has_zp;
+    // qparams: outputs in MODE_COMPRESS, inputs in MODE_QUANT / MODE_FQ
+    void* scale;            // T [b, rows, G]  (FP4 compress: e4m3 bytes)
+    const int8_t* zp_in;    // int8 [b, rows, G] or null
+    int32_t* zp_packed;     // int32 [b, ceil(rows/pf), G]  (compress, asym)
+    const float* gs;        // fp32 [b] (FP4) or null
+    int32_t gs_stride;      // 1: per batch entry, 0: shared
+    const float* col_scale; // fp32 [cols]: AWQ smoothing scale (MODE_OBS_FQ) or null
+    void* out;              // codes / packed words / T values, depending on mode
+};
+template <int MODE> int dispatch_group(int dt, int qt, const GroupParams& p, int64_t batch, cudaStream_t st);
+
+// ---- generic element-wise path with caller-supplied qparams, any strategy (quant_elementwise.cu)
+struct ElemParams {
+    const void* x;          // T values, or codes for dequantize
+    int64_t rows, cols;
+    int32_t strategy, group, bh, bw, nbits, has_zp;
+    const void* scale;      // T, qparam grid
+    const int8_t* zp;       // int8 or null
+    const float* gs;        // fp32[1] or null
+    void* out;
+};
+enum : int { EW_QUANT = 0, EW_FQ = 1, EW_DEQUANT = 2 };
+int launch_elementwise(int op, int dt, int qt, const ElemParams& p, cudaStream_t st);
+
+// ---- observers / qparams (observers.cu)
+int launch_minmax(int dt, const void* w, int64_t batch, int64_t rows, int64_t cols, int strategy, int group, int bh, int bw,
+                  void* mn, void* mx, cudaStream_t st);
+int launch_global_scale(int dt, const void* x, int64_t batch, int64_t numel, float* state, int running, float* gs,
+                        cudaStream_t st);
+int launch_qparams(int dt, int qt, int nbits, int symmetric, const void* mn, const void* mx, int64_t n, const float* gs,
+                   void* scale, int8_t* zp, cudaStream_t st);
+
+// ---- pack / unpack (pack.cu)
+int launch_pack_int32(const int8_t* v, int64_t rows, int64_t cols, int nbits, int packed_dim, int32_t* out, cudaStream_t st);
+int launch_unpack_int32(const int32_t* p, int64_t rows, int64_t cols, int nbits, int packed_dim, int8_t* out, cudaStream_t st);
+int launch_pack_fp4(int dt, const void* x, int64_t rows, int64_t cols, uint8_t* out, cudaStream_t st);
+int launch_unpack_fp4(int dt, const uint8_t* p, int64_t rows, int64_t cols, void* out, cudaStream_t st);
+
+// ---- fused CHANNEL / BLOCK / TENSOR compress (quant_tile.cu)
+struct TileParams {
+    const void* w;
+    int64_t rows, cols;
+    int32_t nbits, symmetric, has_zp;
+    void* scale;          // T
+    int32_t* zp_packed;   // INT asym channel
+    void* out;            // packed int32 (INT) / e4m3 bytes (FP8)
+    float* workspace;     // TENSOR: fp32 absmax bits per batch
+};
+int launch_channel_compress(int dt, int qt, const TileParams& p, int64_t batch, cudaStream_t st);
+int launch_block_fp8_compress(int dt, const TileParams& p, int64_t batch, cudaStream_t st);
+int launch_tensor_fp8_compress(int dt, const TileParams& p, int64_t batch, cudaStream_t st);
+
+// ---- AWQ statistics (awq_stats.cu)
+int launch_abs_sum_cols(int dt, const void* x, int64_t tokens, int64_t k, float* acc, cudaStream_t st);
+int launch_wmean(int dt, const void* w, int64_t rows, int64_t cols, int group, double* acc, cudaStream_t st);
+int launch_awq_scales(const float* x_mean, const float* w_mean, int64_t k, const float* ratios, int n_ratios, int duo,
+                      float* scales, cudaStream_t st);
+int launch_sq_err(int dt, const void* a, const void* b, int64_t n, float* acc, cudaStream_t st);
+
+}  // namespace b200q

@@ -1,0 +1,229 @@
+// observers.cu -- calibration observers as stand-alone kernels.
+//   O1 min/max per quantization chunk  (LLMC observers/helpers.py flatten_for_calibration + min_max.py _get_min_max)
+//   O2/O3 per-tensor running min/max + generate_gparam  (LLMC Observer.get_global_scale, static_minmax;
+//         CT:quantization/utils/helpers.py:309-338)
+//   Q1 calculate_qparams  (CT:quantization/utils/helpers.py:50-137)
+// All are single-pass, HBM-bound reads with 128-bit loads; results are exact (min/max are order independent).
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace b200q {
+
+__device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
+    if (v >= 0.0f) atomicMax((int*)addr, __float_as_int(v));
+    else atomicMin((unsigned int*)addr, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_f32(float* addr, float v) {
+    if (v >= 0.0f) atomicMin((int*)addr, __float_as_int(v));
+    else atomicMax((unsigned int*)addr, __float_as_uint(v));
+}
+
+// ---- GROUP (g = 16..256, sub-warp reduce) and CHANNEL (whole row): one warp per row, 256 columns per step
+template <int DT>
+__global__ void __launch_bounds__(256) minmax_rows_kernel(const void* __restrict__ w, int64_t nrows, int64_t cols, int group,
+                                                          void* __restrict__ mn_out, void* __restrict__ mx_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const bool channel = group <= 0;
+    const int L = channel ? 32 : (group >> 3);
+    const int64_t gtot = channel ? 1 : cols / group;
+    float rmn = INFINITY, rmx = -INFINITY;
+    const int64_t nsteps = (cols + 255) / 256;  // warp-uniform trip count (shuffles inside)
+    for (int64_t step = 0; step < nsteps; step++) {
+        const int64_t c0 = step * 256 + (int64_t)lane * 8;
+        const bool ok = c0 < cols;
+        float mn = INFINITY, mx = -INFINITY;
+        if (ok) {
+            Chunk8<DT> ch;
+            float x[8];
+            load_chunk<DT>(ch, w, row * cols + c0);
+            chunk_to_float<DT>(ch, x);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { mn = fminf(mn, x[i]); mx = fmaxf(mx, x[i]); }
+        }
+        if (channel) { rmn = fminf(rmn, mn); rmx = fmaxf(rmx, mx); continue; }
+        mn = subwarp_min(mn, L);
+        mx = subwarp_max(mx, L);
+        if (ok && (lane % L) == 0) {
+            store_T<DT>(mn_out, row * gtot + c0 / group, mn);
+            store_T<DT>(mx_out, row * gtot + c0 / group, mx);
+        }
+    }
+    if (channel) {
+        rmn = subwarp_min(rmn, 32);
+        rmx = subwarp_max(rmx, 32);
+        if (lane == 0) { store_T<DT>(mn_out, row, rmn); store_T<DT>(mx_out, row, rmx); }
+    }
+}
+
+// ---- BLOCK: one CTA per (block-row, block-col) tile; ragged edges see the zero padding CT applies
+template <int DT>
+__global__ void __launch_bounds__(256) minmax_block_kernel(const void* __restrict__ w, int64_t rows, int64_t cols, int bh, int bw,
+                                                           void* __restrict__ mn_out, void* __restrict__ mx_out) {
+    const int64_t b = blockIdx.z;
+    const int64_t r0 = (int64_t)blockIdx.y * bh, c0 = (int64_t)blockIdx.x * bw;
+    const char* base = (const char*)w + b * rows * cols * ElemSize<DT>::value;
+    float mn = INFINITY, mx = -INFINITY;
+    const bool ragged = (r0 + bh > rows) || (c0 + bw > cols);
+    if (ragged) { mn = 0.0f; mx = 0.0f; }
+    const int cpr = bw / 8;  // chunks per tile row (bw % 8 == 0 enforced by the launcher)
+    for (int t = threadIdx.x; t < bh * cpr; t += blockDim.x) {
+        const int64_t r = r0 + t / cpr, c = c0 + (int64_t)(t % cpr) * 8;
+        if (r < rows && c < cols) {
+            Chunk8<DT> ch;
+            float x[8];
+            load_chunk<DT>(ch, base, r * cols + c);
+            chunk_to_float<DT>(ch, x);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { mn = fminf(mn, x[i]); mx = fmaxf(mx, x[i]); }
+        }
+    }
+    __shared__ float smn[8], smx[8];
+    mn = subwarp_min(mn, 32);
+    mx = subwarp_max(mx, 32);
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) { mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
+        const int64_t k = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        store_T<DT>(mn_out, k, mn);
+        store_T<DT>(mx_out, k, mx);
+    }
+}
+
+// ---- TENSOR: grid-stride reduce into fp32 {min,max} state per batch entry
+__global__ void init_minmax_state_kernel(float* state, int64_t batch) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < batch) { state[2 * i] = INFINITY; state[2 * i + 1] = -INFINITY; }
+}
+template <int DT>
+__global__ void __launch_bounds__(256) minmax_tensor_kernel(const void* __restrict__ x, int64_t numel, float* __restrict__ state) {
+    const int64_t b = blockIdx.y;
+    const char* base = (const char*)x + b * numel * ElemSize<DT>::value;
+    float mn = INFINITY, mx = -INFINITY;
+    const int64_t nchunks = numel / 8;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nchunks; t += (int64_t)gridDim.x * blockDim.x) {
+        Chunk8<DT> ch;
+        float v[8];
+        load_chunk<DT>(ch, base, t * 8);
+        chunk_to_float<DT>(ch, v);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { mn = fminf(mn, v[i]); mx = fmaxf(mx, v[i]); }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(numel % 8)) {
+        const float v = load_T<DT>(base, nchunks * 8 + threadIdx.x);
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    mn = subwarp_min(mn, 32);
+    mx = subwarp_max(mx, 32);
+    __shared__ float smn[8], smx[8];
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) { mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
+        if (mn <= mx) { atomic_min_f32(&state[2 * b], mn); atomic_max_f32(&state[2 * b + 1], mx); }
+    }
+}
+template <int DT>
+__global__ void gparam_kernel(const float* __restrict__ state, int64_t batch, float* __restrict__ gs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    const float mn = fminf(state[2 * i], 0.0f), mx = fmaxf(state[2 * i + 1], 0.0f);
+    gs[i] = gparam<DT>(fmaxf(fabsf(mn), fabsf(mx)));
+}
+int launch_global_scale(int dt, const void* x, int64_t batch, int64_t numel, float* state, int running, float* gs,
+                        cudaStream_t st) {
+    B200Q_REQUIRE(batch >= 1 && batch <= 65535, "batch out of range");
+    B200Q_REQUIRE(((uintptr_t)x & 15) == 0 && (batch == 1 || (numel * (dt == DT_F32 ? 4 : 2)) % 16 == 0),
+                  "tensor must be 16-byte aligned");
+    if (!running) { init_minmax_state_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(state, batch); B200Q_CHECK_LAUNCH(); }
+    if (numel > 0) {
+        const int64_t per = (numel / 8 + 255) / 256;
+        const unsigned gx = (unsigned)max((int64_t)1, min(per, (int64_t)max(1, kNumSMs * 8 / (int)min(batch, (int64_t)64))));
+        B200Q_DISPATCH_DT(dt, { minmax_tensor_kernel<DT><<<dim3(gx, (unsigned)batch), 256, 0, st>>>(x, numel, state); });
+        B200Q_CHECK_LAUNCH();
+    }
+    if (gs) {
+        B200Q_DISPATCH_DT(dt, { gparam_kernel<DT><<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(state, batch, gs); });
+        B200Q_CHECK_LAUNCH();
+    }
+    return B200Q_OK;
+}
+
+int launch_minmax(int dt, const void* w, int64_t batch, int64_t rows, int64_t cols, int strategy, int group, int bh, int bw,
+                  void* mn, void* mx, cudaStream_t st) {
+    B200Q_REQUIRE(((uintptr_t)w & 15) == 0, "weight pointer must be 16-byte aligned");
+    if (batch * rows * cols == 0) return B200Q_OK;
+    if (strategy == ST_GROUP || strategy == ST_CHANNEL) {
+        const int g = strategy == ST_CHANNEL ? 0 : group;
+        if (g) B200Q_REQUIRE((g == 16 || g == 32 || g == 64 || g == 128 || g == 256) && cols % g == 0,
+                             "group_size %d unsupported or does not divide %lld columns", g, (long long)cols);
+        B200Q_REQUIRE(cols % 8 == 0, "columns must be a multiple of 8");
+        const int64_t nrows = batch * rows;
+        B200Q_DISPATCH_DT(dt, { minmax_rows_kernel<DT><<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(w, nrows, cols, g, mn, mx); });
+    } else if (strategy == ST_BLOCK) {
+        B200Q_REQUIRE(bw % 8 == 0 && cols % 8 == 0 && bh > 0, "block width and columns must be multiples of 8");
+        dim3 grid((unsigned)((cols + bw - 1) / bw), (unsigned)((rows + bh - 1) / bh), (unsigned)batch);
+        B200Q_DISPATCH_DT(dt, { minmax_block_kernel<DT><<<grid, 256, 0, st>>>(w, rows, cols, bh, bw, mn, mx); });
+    } else {
+        set_error("minmax: TENSOR strategy goes through b200q_global_scale / the tensor compress workspace");
+        return B200Q_EINVAL;
+    }
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+// ---- Q1 calculate_qparams
+template <int DT, int QT>
+__global__ void __launch_bounds__(256) qparams_kernel(const void* __restrict__ mn_in, const void* __restrict__ mx_in, int64_t n,
+                                                      int nbits, int symmetric, const float* __restrict__ gs,
+                                                      void* __restrict__ scale, int8_t* __restrict__ zp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float lo = (QT == QT_INT) ? -(float)(1 << (nbits - 1)) : (QT == QT_FP8 ? -448.0f : -6.0f);
+    const float hi = (QT == QT_INT) ? (float)((1 << (nbits - 1)) - 1) : (QT == QT_FP8 ? 448.0f : 6.0f);
+    float mn = fminf(load_T<DT>(mn_in, i), 0.0f), mx = fmaxf(load_T<DT>(mx_in, i), 0.0f);
+    float s, z = 0.0f;
+    if (symmetric) {
+        const float a = fmaxf(fabsf(mn), fabsf(mx));
+        if (QT == QT_FP4 && gs) {  // e4m3-rounded fp32 scale, helpers.py:101-126
+            float se;
+            const uint8_t code = qparams_fp4<DT>(a, gs[0], se);
+            ((float*)scale)[i] = e4m3_decode(code);
+            if (zp) zp[i] = 0;
+            return;
+        }
+        s = round_to<DT>(fdiv(a, (hi - lo) * 0.5f));
+        if (gs) {
+            float sf = fmul(gs[0], s);
+            ((float*)scale)[i] = sf == 0.0f ? 1.1920928955078125e-07f : sf;
+            if (zp) zp[i] = 0;
+            return;
+        }
+        if (s == 0.0f) s = eps_of<DT>();
+    } else {
+        qparams_asym<DT>(mn, mx, lo, hi, s, z);
+    }
+    store_T<DT>(scale, i, s);
+    if (zp) zp[i] = (int8_t)(int)z;
+}
+
+int launch_qparams(int dt, int qt, int nbits, int symmetric, const void* mn, const void* mx, int64_t n, const float* gs,
+                   void* scale, int8_t* zp, cudaStream_t st) {
+    if (n == 0) return B200Q_OK;
+    B200Q_REQUIRE(symmetric || qt == QT_INT, "Asymmetric Quantization is not supported for FP4/FP8 here");
+    const unsigned g = (unsigned)((n + 255) / 256);
+    B200Q_DISPATCH_DT(dt, {
+        switch (qt) {
+        case QT_INT: qparams_kernel<DT, QT_INT><<<g, 256, 0, st>>>(mn, mx, n, nbits, symmetric, gs, scale, zp); break;
+        case QT_FP8: qparams_kernel<DT, QT_FP8><<<g, 256, 0, st>>>(mn, mx, n, nbits, symmetric, gs, scale, zp); break;
+        case QT_FP4: qparams_kernel<DT, QT_FP4><<<g, 256, 0, st>>>(mn, mx, n, nbits, symmetric, gs, scale, zp); break;
+        default: set_error("bad qtype %d", qt); return B200Q_EINVAL;
+        }
+    });
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+}  // namespace b200q

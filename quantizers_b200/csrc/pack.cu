@@ -1,0 +1,100 @@
+// pack.cu -- pack_to_int32 / unpack_from_int32 (CT:compressors/pack_quantized/helpers.py:20-161) and
+// pack_fp4_to_uint8 / unpack_fp4_from_uint8 (CT:compressors/nvfp4/helpers.py:34-111) as stand-alone kernels.
+// The fused compress kernels never call these; they exist for the un-fused CT call sites and decompression.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace b200q {
+
+// one thread per output word; packed_dim 1: words along columns, 0: along rows (used for zero-points)
+__global__ void __launch_bounds__(256) pack_int32_kernel(const int8_t* __restrict__ v, int64_t rows, int64_t cols, int nbits,
+                                                         int packed_dim, int32_t* __restrict__ out) {
+    const int pf = 32 / nbits, off = 1 << (nbits - 1);
+    const int64_t orow = packed_dim == 1 ? rows : (rows + pf - 1) / pf;
+    const int64_t ocol = packed_dim == 1 ? (cols + pf - 1) / pf : cols;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < orow * ocol; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / ocol, c = t % ocol;
+        uint32_t acc = 0;
+        for (int i = 0; i < pf; i++) {
+            const int64_t rr = packed_dim == 1 ? r : r * pf + i, cc = packed_dim == 1 ? c * pf + i : c;
+            if (rr < rows && cc < cols) acc |= ((uint32_t)(uint8_t)(v[rr * cols + cc] + off)) << (nbits * i);
+        }
+        out[t] = (int32_t)acc;
+    }
+}
+__global__ void __launch_bounds__(256) unpack_int32_kernel(const int32_t* __restrict__ p, int64_t rows, int64_t cols, int nbits,
+                                                           int packed_dim, int8_t* __restrict__ out) {
+    const int pf = 32 / nbits, off = 1 << (nbits - 1);
+    const uint32_t mask = (1u << nbits) - 1u;
+    const int64_t pcols = packed_dim == 1 ? (cols + pf - 1) / pf : cols;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < rows * cols; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / cols, c = t % cols;
+        const uint32_t w = packed_dim == 1 ? (uint32_t)p[r * pcols + c / pf] : (uint32_t)p[(r / pf) * pcols + c];
+        const int sh = nbits * (int)(packed_dim == 1 ? c % pf : r % pf);
+        out[t] = (int8_t)((int)((w >> sh) & mask) - off);
+    }
+}
+
+// nearest e2m1 magnitude (first minimum, like torch.argmin over |abs(x) - table| evaluated in T) | signbit << 3
+template <int DT>
+__global__ void __launch_bounds__(256) pack_fp4_kernel(const void* __restrict__ x, int64_t n_pairs, uint8_t* __restrict__ out) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_pairs; t += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t nib[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const float v = load_T<DT>(x, 2 * t + k);
+            const float a = fabsf(v);
+            int best = 0;
+            float bd = INFINITY;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float d = fabsf(round_to<DT>(fadd(a, -e2m1_value(i))));
+                if (d < bd) { bd = d; best = i; }
+            }
+            nib[k] = (uint32_t)best | ((__float_as_uint(v) >> 31) << 3);
+        }
+        out[t] = (uint8_t)(nib[0] | (nib[1] << 4));
+    }
+}
+template <int DT>
+__global__ void __launch_bounds__(256) unpack_fp4_kernel(const uint8_t* __restrict__ p, int64_t n, void* __restrict__ out) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const uint8_t b = p[t >> 1];
+        const uint32_t nib = (t & 1) ? (b >> 4) : (b & 0xf);
+        const float v = e2m1_value(nib & 7u);
+        store_T<DT>(out, t, (nib & 8u) ? -v : v);
+    }
+}
+
+static int nblocks(int64_t work) { return (int)max((int64_t)1, min((int64_t)kNumSMs * 16, (work + 255) / 256)); }
+
+int launch_pack_int32(const int8_t* v, int64_t rows, int64_t cols, int nbits, int packed_dim, int32_t* out, cudaStream_t st) {
+    B200Q_REQUIRE(nbits >= 1 && nbits <= 8, "Packing is only supported for less than 8 bits");
+    B200Q_REQUIRE(packed_dim == 0 || packed_dim == 1, "packed_dim must be 0 or 1");
+    if (rows * cols == 0) return B200Q_OK;
+    pack_int32_kernel<<<nblocks(rows * cols / (32 / nbits) + 1), 256, 0, st>>>(v, rows, cols, nbits, packed_dim, out);
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+int launch_unpack_int32(const int32_t* p, int64_t rows, int64_t cols, int nbits, int packed_dim, int8_t* out, cudaStream_t st) {
+    B200Q_REQUIRE(nbits >= 1 && nbits <= 8, "Unpacking is only supported for less than 8 bits");
+    if (rows * cols == 0) return B200Q_OK;
+    unpack_int32_kernel<<<nblocks(rows * cols), 256, 0, st>>>(p, rows, cols, nbits, packed_dim, out);
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+int launch_pack_fp4(int dt, const void* x, int64_t rows, int64_t cols, uint8_t* out, cudaStream_t st) {
+    B200Q_REQUIRE(cols % 2 == 0, "tensor must have an even number of columns for nvfp4 compression");
+    if (rows * cols == 0) return B200Q_OK;
+    B200Q_DISPATCH_DT(dt, { pack_fp4_kernel<DT><<<nblocks(rows * cols / 2), 256, 0, st>>>(x, rows * cols / 2, out); });
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+int launch_unpack_fp4(int dt, const uint8_t* p, int64_t rows, int64_t cols, void* out, cudaStream_t st) {
+    if (rows * cols == 0) return B200Q_OK;
+    B200Q_DISPATCH_DT(dt, { unpack_fp4_kernel<DT><<<nblocks(rows * cols), 256, 0, st>>>(p, rows * cols, out); });
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+}  // namespace b200q

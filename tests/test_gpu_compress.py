@@ -1,0 +1,221 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle, the committed golden vectors
+and, when importable, live compressed_tensors.  Bit-exact everywhere (integer / byte / index work and scales)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ct_live as L
+from oracle import oracle as O
+from tests.util import FORMATS, assert_bits_equal, from_bits, geom_of, golden_files, load_golden, synth_weight
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.bfloat16, torch.float16, torch.float32]
+
+
+class Args:
+    """Minimal QuantizationArgs look-alike (the ops accept any object with these attributes)."""
+
+    def __init__(self, name):
+        fmt, qtype, nb, sym, strat, g, blk = FORMATS[name]
+        self.num_bits = nb
+        self.type = "int" if qtype == O.INT else "float"
+        self.symmetric = sym
+        self.strategy = {O.TENSOR: "tensor", O.CHANNEL: "channel", O.GROUP: "tensor_group" if qtype == O.FP4 else "group",
+                         O.BLOCK: "block"}[strat]
+        self.group_size = g or None
+        self.block_structure = list(blk) if blk else None
+        self.zp_dtype = torch.int8 if qtype == O.INT else torch.float8_e4m3fn
+
+
+def _cmp_sd(got, want, what):
+    assert set(got) == set(want), f"{what}: keys {sorted(got)} != {sorted(want)}"
+    for k in want:
+        w = want[k]
+        if isinstance(w, np.ndarray):
+            assert_bits_equal(got[k].reshape(w.shape), w, f"{what}:{k}")
+        else:
+            assert_bits_equal(got[k].reshape(w.shape), w, f"{what}:{k}")
+
+
+@pytest.mark.parametrize("fname", golden_files())
+def test_fused_compress_matches_golden(fname):
+    from quantizers_b200 import ops
+
+    name, dtype, z = load_golden(fname)
+    w = from_bits(z["w"], dtype).cuda()
+    got = ops.compress_weight(w, Args(name))
+    want = {k[3:]: v for k, v in z.items() if k.startswith("sd_")}
+    _cmp_sd(got, want, name)
+
+
+@pytest.mark.parametrize("name", list(FORMATS))
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fused_compress_matches_oracle(name, dtype):
+    from quantizers_b200 import ops
+
+    fmt, qtype, nb, sym, strat, g, blk = FORMATS[name]
+    for R, C, seed in ((8, 128, 1), (77, 1280, 2), (200, 384, 3), (256, 2304, 4)):
+        w = synth_weight(R, C, dtype, seed)
+        want = O.compress(w, fmt, geom_of(name), nb, sym)
+        got = ops.compress_weight(w.cuda(), Args(name))
+        _cmp_sd(got, want, f"{name}/{dtype}/{R}x{C}")
+
+
+@pytest.mark.parametrize("name", ["int4_g128_asym", "int4_g32_sym", "fp8_block", "fp8_g32", "nvfp4", "int4_channel_asym"])
+def test_fused_compress_expert_stack(name):
+    """[E, rows, cols] stacks (MoE experts) == per-expert results; rows not a multiple of 8 exercises zp row packing."""
+    from quantizers_b200 import ops
+
+    fmt, qtype, nb, sym, strat, g, blk = FORMATS[name]
+    E, R, C = 5, 36, 512
+    ws = [synth_weight(R, C, torch.bfloat16, 100 + e) for e in range(E)]
+    got = ops.compress_weight(torch.stack(ws).cuda(), Args(name))
+    for e in range(E):
+        want = O.compress(ws[e], fmt, geom_of(name), nb, sym)
+        for k in want:
+            if k == "weight_shape":
+                continue
+            assert_bits_equal(got[k][e].reshape(want[k].shape), want[k], f"{name}[{e}]:{k}")
+
+
+def test_nvfp4_supplied_global_scale():
+    from quantizers_b200 import ops
+
+    w = synth_weight(64, 512, torch.bfloat16, 9)
+    gs = torch.tensor([37.25])
+    want = O.compress(w, "nvfp4-pack-quantized", geom_of("nvfp4"), 4, True, gs)
+    got = ops.compress_weight(w.cuda(), Args("nvfp4"), global_scale=gs.cuda())
+    _cmp_sd(got, want, "nvfp4 gs")
+
+
+@pytest.mark.parametrize("name", list(FORMATS))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_unfused_ops_match_oracle(name, dtype):
+    """observe_minmax -> calculate_qparams -> quantize / quantize_pack / fake_quantize / dequantize, each vs the oracle."""
+    from quantizers_b200 import ops
+
+    fmt, qtype, nb, sym, strat, g, blk = FORMATS[name]
+    geom = geom_of(name)
+    args = Args(name)
+    R, C = (200, 384) if strat == O.BLOCK else (40, 768)
+    w = synth_weight(R, C, dtype, 17)
+    wd = w.cuda()
+    gs = O.generate_gparam(float(w.float().min()), float(w.float().max()), dtype) if qtype == O.FP4 else None
+    gsd = gs.cuda() if gs is not None else None
+    # observer
+    if strat != O.TENSOR or True:
+        mn_o, mx_o = O.minmax(w, geom)
+        mn, mx = ops.observe_minmax(wd, args)
+        if strat != O.BLOCK or (R % 128 == 0 and C % 128 == 0):
+            assert_bits_equal(mn.reshape(mn_o.shape), mn_o, "min")
+            assert_bits_equal(mx.reshape(mx_o.shape), mx_o, "max")
+    if qtype == O.FP4:
+        assert ops.observe_global_scale(wd).item() == gs.item()
+    # qparams
+    s_o, z_o = O.calculate_qparams(mn_o, mx_o, qtype, nb, sym, gs)
+    s, zp = ops.calculate_qparams(mn_o.cuda(), mx_o.cuda(), args, gsd)
+    assert_bits_equal(s.reshape(s_o.shape), s_o, "scale")
+    if qtype == O.INT:
+        assert_bits_equal(zp.reshape(z_o.shape), z_o, "zp")
+    sT = s_o.to(dtype)
+    zarg = z_o if qtype == O.INT else torch.zeros(s_o.shape, dtype=torch.float8_e4m3fn)
+    # quantize
+    q_o = O.quantize(w, sT, zarg, geom, qtype, nb, gs)
+    if qtype == O.FP4:
+        q = ops.quantize(wd, sT.cuda(), zarg.cuda(), args, global_scale=gsd)
+        vals = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0])[(q_o & 7).long()] * torch.where((q_o & 8) > 0, -1.0, 1.0)
+        assert_bits_equal(q, vals.to(dtype), "fp4 values")
+        packed = ops.pack_fp4_to_uint8(q)
+        assert_bits_equal(packed, (q_o[:, 0::2] | (q_o[:, 1::2] << 4)), "pack_fp4")
+        assert_bits_equal(ops.unpack_fp4_from_uint8(packed, R, C, dtype), vals.to(dtype), "unpack_fp4")
+    else:
+        q = ops.quantize(wd, sT.cuda(), zarg.cuda(), args, dtype=torch.int8 if qtype == O.INT else torch.float8_e4m3fn)
+        assert_bits_equal(q, q_o, "codes")
+    # quantize_pack == compress given qparams
+    qp = ops.quantize_pack(wd, sT.cuda(), zarg.cuda(), args, global_scale=gsd)
+    if qtype == O.INT:
+        assert_bits_equal(qp, O.pack_to_int32(q_o, nb), "quantize_pack")
+        assert_bits_equal(ops.unpack_from_int32(qp, nb, (R, C)), q_o, "unpack")
+    elif qtype == O.FP8:
+        assert_bits_equal(qp, q_o, "quantize_pack fp8")
+    else:
+        assert_bits_equal(qp, (q_o[:, 0::2] | (q_o[:, 1::2] << 4)), "quantize_pack fp4")
+    # fake_quantize
+    fq_o = O.fake_quantize(w, sT, zarg, geom, qtype, nb, gs)
+    fq = ops.fake_quantize(wd, sT.cuda(), zarg.cuda(), args, global_scale=gsd)
+    assert_bits_equal(fq, fq_o, "fake_quantize")
+    # dequantize
+    if qtype == O.FP4:
+        dq_o = O.dequantize(vals.to(dtype), sT, None, geom, qtype, gs, out_dtype=dtype)
+        dq = ops.dequantize(vals.to(dtype).cuda(), sT.cuda(), None, args, dtype=dtype, global_scale=gsd)
+    else:
+        dq_o = O.dequantize(q_o, sT, z_o if qtype == O.INT else None, geom, qtype)
+        dq = ops.dequantize(q_o.cuda(), sT.cuda(), z_o.cuda() if qtype == O.INT else None, args)
+    assert_bits_equal(dq, dq_o, "dequantize")
+
+
+def test_pack_zero_point_rows_and_ragged():
+    from quantizers_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    for R, C in [(1, 1), (7, 13), (9, 8), (16, 24), (130, 77)]:
+        v = torch.randint(-8, 8, (R, C), generator=g, dtype=torch.int8)
+        for dim in (0, 1):
+            p = ops.pack_to_int32(v.cuda(), 4, dim)
+            assert_bits_equal(p, O.pack_to_int32(v, 4, dim), f"pack {R}x{C} dim{dim}")
+            assert torch.equal(ops.unpack_from_int32(p, 4, v.shape, dim).cpu(), v)
+    with pytest.raises(ValueError):
+        ops.pack_to_int32(torch.zeros(2, 2, dtype=torch.int32).cuda(), 4)
+    with pytest.raises(ValueError):
+        ops.pack_fp4_to_uint8(torch.zeros(2, 3, dtype=torch.bfloat16).cuda())
+
+
+def test_error_behaviour_matches_reference():
+    from quantizers_b200 import ops
+
+    a = Args("int4_g128_sym")
+    with pytest.raises(ValueError, match="divisble"):
+        ops.compress_weight(torch.zeros(8, 200, dtype=torch.bfloat16).cuda(), a)
+    w = torch.zeros(8, 200, dtype=torch.bfloat16).cuda()
+    with pytest.raises(ValueError, match="divisble"):
+        ops.fake_quantize(w, torch.ones(8, 2, dtype=torch.bfloat16).cuda(), None, a)
+    # empty input: nothing to do, nothing launched
+    e = ops.fake_quantize(torch.zeros(0, 128, dtype=torch.bfloat16).cuda(), torch.ones(0, 1, dtype=torch.bfloat16).cuda(), None, a)
+    assert e.numel() == 0
+
+
+@pytest.mark.skipif(not L.available(), reason="compressed_tensors not importable")
+@pytest.mark.parametrize("name", ["int4_g128_asym", "int4_g32_sym", "int4_channel_asym", "fp8_block", "fp8_channel", "fp8_g32", "nvfp4"])
+def test_registered_compressors_match_live_ct(name):
+    """The drop-in seam: BaseCompressor registry override vs the stock compressor on the same state dict, and
+    decompress round trip through the CUDA unpack/dequantize kernels vs CT's."""
+    from compressed_tensors.compressors.base import BaseCompressor
+    from compressed_tensors.quantization import QuantizationScheme
+
+    import quantizers_b200.patch as P
+
+    fmt, args = L.format_args(name)
+    scheme = QuantizationScheme(targets=["Linear"], weights=args)
+    w = synth_weight(136, 640, torch.bfloat16, 23)
+    gs = L.global_scale(w) if args.strategy == "tensor_group" else None
+    scale, zp = L.weight_qparams(w, args, gs)
+    sd = {"weight": w, "weight_scale": scale, "weight_zero_point": zp}
+    if gs is not None:
+        sd["weight_global_scale"] = gs
+    ref = BaseCompressor.get_value_from_registry(fmt).compress(sd, scheme)
+    ref_dec = BaseCompressor.get_value_from_registry(fmt).decompress(ref, scheme)
+    sd_cuda = {k: v.cuda() for k, v in sd.items()}
+    keys_before = set(sd_cuda)
+    with P.patch():
+        comp = BaseCompressor.get_value_from_registry(fmt)
+        assert comp.__name__.startswith("B200")
+        got = comp.compress(sd_cuda, scheme)
+        got_dec = comp.decompress(got, scheme)
+    assert set(sd_cuda) == keys_before  # input dict not modified
+    assert set(got) == set(ref)
+    for k in ref:
+        assert got[k].dtype == ref[k].dtype, k
+        assert_bits_equal(got[k], ref[k], f"{name}:{k}")
+    assert_bits_equal(got_dec["weight"], ref_dec["weight"], f"{name}:decompress")
+    assert BaseCompressor.get_value_from_registry(fmt).__name__.startswith("B200") is False
