@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the quantization hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1]): Qwen3-4B (random-init, synthetic) mixed FP8 128x128 block (attention
+q/k/v/o) + INT4 W4A16 group-128 asymmetric (MLP gate/up/down), RTN quantize+pack of all 36 decoder layers
+= 252 matrices = 7.27 GB of bf16 weights per step.  One step = one pass of the fused
+observer -> qparams -> quantize -> pack path over the whole model.
+
+  value   : bf16 weight GB/s quantized+packed, weights already resident in HBM (device-timed, CUDA events)
+  e2e     : same metric through the C-ABI host pipeline (b200q_pipeline_compress_host): pinned HOST weights in,
+            packed HOST tensors out, host<->device copies inside the timed region
+  roofline: dominant kernel (INT4 group kernel) algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
+  N > 1   : weak scaling -- every rank quantizes its own 36-layer shard (layers are independent units; no
+            data-path collective), value = N * bytes / max-over-ranks time
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "bf16_weight_GBps_quantized_packed"
+UNIT = "GB/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.samples = []
+        self.marks = {}
+        self.proc = None
+        self.index = index
+        self._t = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def rd():
+            for line in self.proc.stdout:
+                self.samples.append((time.time(), line.strip()))
+
+        self._t = threading.Thread(target=rd, daemon=True)
+        self._t.start()
+
+    def mark(self, name):
+        self.marks[name] = time.time()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        t0, t1 = self.marks.get("t0", 0), self.marks.get("t1", float("inf"))
+        rows = [s for s in self.samples if t0 <= s[0] <= t1] or [s for s in self.samples if s[0] >= self.marks.get("w0", 0)]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for _, line in rows:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference / CPU baseline
+def cpu_layer(layer_idx: int):
+    """One Qwen3-4B decoder layer (7 matrices, 201.9 MB bf16) on the CPU, SURVEY.md §8d seeds."""
+    shapes = [("q_proj", 4096, 2560, "fp8_block"), ("k_proj", 1024, 2560, "fp8_block"), ("v_proj", 1024, 2560, "fp8_block"),
+              ("o_proj", 2560, 4096, "fp8_block"), ("gate_proj", 9728, 2560, "int4_g128_asym"),
+              ("up_proj", 9728, 2560, "int4_g128_asym"), ("down_proj", 2560, 9728, "int4_g128_asym")]
+    out = []
+    for mi, (name, r, c, fmt) in enumerate(shapes):
+        g = torch.Generator().manual_seed(1234 + layer_idx * 1000 + mi)
+        out.append((name, fmt, (torch.randn(r, c, generator=g) * 0.02).to(torch.bfloat16)))
+    return out
+
+
+def cpu_quantize_layer(layer, kind: str):
+    """The reference CPU path for one layer: live compressed_tensors (kind 'reference') or the C oracle ('port')."""
+    nbytes = 0
+    if kind == "reference":
+        from oracle import ct_live as L
+
+        for _, fmt_name, w in layer:
+            fmt, args = L.format_args(fmt_name)
+            L.compress(w, fmt, args)
+            nbytes += w.numel() * 2
+    else:
+        from oracle import oracle as O
+
+        for _, fmt_name, w in layer:
+            if fmt_name == "fp8_block":
+                O.compress(w, "float-quantized", O.Geom(O.BLOCK, 0, 128, 128), 8, True)
+            else:
+                O.compress(w, "pack-quantized", O.Geom(O.GROUP, 128), 4, False)
+            nbytes += w.numel() * 2
+    return nbytes
+
+
+def cpu_kind():
+    from oracle import ct_live as L
+
+    return "reference" if L.available() else "port"
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation (live compressed_tensors when importable, else the
+    oracle port) on the host cores; each step = one decoder layer of the same workload (bounded sample)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind = cpu_kind()
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads() if kind == "reference" else 1
+    layers = [cpu_layer(i % 2) for i in range(2)]
+    for i in range(max(args.warmup, 1) if args.warmup else 0):
+        cpu_quantize_layer(layers[i % 2], kind)
+    t0 = time.perf_counter()
+    nbytes = 0
+    for i in range(args.steps):
+        nbytes += cpu_quantize_layer(layers[i % 2], kind)
+    dt = time.perf_counter() - t0
+    v = nbytes / dt / 1e9
+    sample = "one Qwen3-4B decoder layer (7 matrices, 201.9 MB bf16) per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16->int4/fp8", "data": "synthetic",
+        "config": {"workload": "qwen3-4b mixed FP8_BLOCK(attn)+INT4 g128 asym(MLP) RTN quantize+pack", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ----------------------------------------------------------------------------- e2e through the host pipeline
+def run_e2e(spec, arena, steps, warmup, device_index):
+    """Pinned host weights -> b200q_pipeline_compress_host -> pinned host outputs, per matrix (252 jobs / step)."""
+    import ctypes
+
+    from quantizers_b200 import _lib as L
+    from quantizers_b200 import ops
+    from quantizers_b200.scheduler import PRESETS
+
+    lib = L.lib()
+    jobs = []
+    h2d = d2h = 0
+    max_bytes = 0
+    for m in spec.matrices:
+        w = arena[m.name]
+        a = PRESETS[m.preset]
+        hw = torch.empty(w.shape, dtype=w.dtype, pin_memory=True)
+        hw.copy_(w)
+        n_mat, rows, cols = w.shape
+        max_bytes = max(max_bytes, rows * cols * 2)
+        sc = ops.scheme_from_args(a, w.dtype, True)
+        if a.type == "int":
+            codes = torch.empty((n_mat, rows, cols // 8), dtype=torch.int32, pin_memory=True)
+            scale = torch.empty((n_mat, rows, cols // a.group_size), dtype=w.dtype, pin_memory=True)
+            zp = None if a.symmetric else torch.empty((n_mat, -(-rows // 8), cols // a.group_size), dtype=torch.int32, pin_memory=True)
+        else:
+            codes = torch.empty((n_mat, rows, cols), dtype=torch.uint8, pin_memory=True)
+            scale = torch.empty((n_mat, -(-rows // 128), -(-cols // 128)), dtype=w.dtype, pin_memory=True)
+            zp = None
+        for i in range(n_mat):
+            jobs.append((hw[i], rows, cols, sc, codes[i], scale[i], None if zp is None else zp[i]))
+            h2d += hw[i].numel() * 2
+            d2h += codes[i].numel() * codes.element_size() + scale[i].numel() * 2 + (0 if zp is None else zp[i].numel() * 4)
+    handle = ctypes.c_void_p()
+    L.check(lib.b200q_pipeline_create(ctypes.byref(handle), max_bytes, device_index))
+
+    def step():
+        for hw, rows, cols, sc, codes, scale, zp in jobs:
+            L.check(lib.b200q_pipeline_compress_host(handle, L.ptr(hw), 1, rows, cols, ctypes.byref(sc), L.ptr(codes), L.ptr(scale),
+                                                     L.ptr(zp), None))
+        L.check(lib.b200q_pipeline_sync(handle))
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    lib.b200q_pipeline_destroy(handle)
+    return h2d * steps / dt / 1e9, h2d, d2h, dt
+
+
+# ----------------------------------------------------------------------------- main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layers", type=int, default=36, help="decoder layers per rank (36 = full Qwen3-4B)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the quantization hot path has no CPU fallback")
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+
+    from quantizers_b200 import scheduler as S
+
+    spec = S.qwen3_4b(layers=args.layers)
+    units = list(range(rank * spec.units, (rank + 1) * spec.units))  # weak scaling: a distinct 36-layer shard per rank
+    arena = S.build_arena(spec, units, dev)
+    step_bytes = spec.units * spec.unit_bytes()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sampler.mark("w0")
+    for _ in range(warmup):
+        S.quantize_arena(spec, arena)
+    barrier()
+    torch.cuda.synchronize()
+    timings = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark("t0")
+    e0.record()
+    for _ in range(args.steps):
+        out = S.quantize_arena(spec, arena, timings)
+    e1.record()
+    torch.cuda.synchronize()
+    sampler.mark("t1")
+    barrier()
+    ms = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    sampler.stop()
+    value = world * step_bytes * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- per-kernel-class times (CUDA events on the launching stream, inside the timed region)
+    per = {}
+    for name, preset, elems, a, b in timings:
+        d = per.setdefault(preset, {"ms": 0.0, "elems": 0, "n": 0})
+        d["ms"] += a.elapsed_time(b)
+        d["elems"] += elems
+        d["n"] += 1
+    dom = max(per, key=lambda k: per[k]["ms"])
+    dargs = S.PRESETS[dom]
+    alg_bytes = dargs.bytes_per_element() * per[dom]["elems"]
+    achieved = alg_bytes / (per[dom]["ms"] * 1e-3) / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": f"group_kernel<bf16,{dom}> (fused observe+qparams+quantize+pack)",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
+                "alg_bytes_per_element": dargs.bytes_per_element(), "avg_launch_ms": per[dom]["ms"] / per[dom]["n"],
+                "per_class": {k: {"GBps_bf16_in": v["elems"] * 2 / (v["ms"] * 1e-3) / 1e9,
+                                  "GBps_algorithmic": S.PRESETS[k].bytes_per_element() * v["elems"] / (v["ms"] * 1e-3) / 1e9,
+                                  "share_of_step": v["ms"] / sum(x["ms"] for x in per.values())} for k, v in per.items()}}
+    traffic_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(dom)
+        except Exception:
+            pass
+    del out
+
+    # ---- e2e through the host pipeline (same metric, host buffers, copies in the timed region)
+    e2e_v, h2d, d2h, _ = run_e2e(spec, arena, args.e2e_steps, 1, local)
+    ev = torch.tensor([e2e_v], device=dev)
+    if world > 1:
+        dist.all_reduce(ev, op=dist.ReduceOp.MIN)  # slowest rank bounds the job
+        e2e_v = float(ev.item()) * world
+    barrier()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16->int4/fp8", "data": "synthetic",
+        "config": {"workload": "qwen3-4b mixed FP8_BLOCK(attn)+INT4 g128 asym(MLP) RTN quantize+pack",
+                   "layers_per_gpu": spec.units, "matrices_per_step": 7 * spec.units, "bytes_per_step_per_gpu": step_bytes,
+                   "l2": "inputs (7.27 GB/step) far larger than the 126 MB L2; no flush needed", "parallelism": f"layer-sharded x{world}"},
+        "roofline": roofline,
+        "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
+        "gpu_launches": S.launches_per_step(spec) * args.steps,
+        "clocks": sampler.summary() if rank == 0 else None,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            kind = cpu_kind()
+            torch.set_num_threads(os.cpu_count() or 1)
+            layer = cpu_layer(0)
+            t0 = time.perf_counter()
+            nb = cpu_quantize_layer(layer, kind)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": nb / dt / 1e9, "unit": UNIT, "cores": torch.get_num_threads() if kind == "reference" else 1,
+                                    "kind": kind, "sample": "one Qwen3-4B decoder layer (7 matrices, 201.9 MB bf16), single cold pass"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

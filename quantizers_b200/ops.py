@@ -479,3 +479,16 @@ def quantize_pack(weight: torch.Tensor, scale, zero_point, args, global_scale=No
         L.check(L.lib().b200q_quantize_pack(L.ptr(w), batch, rows, cols, ctypes.byref(sc), L.ptr(scale_t),
                                             L.ptr(_zp_int8(zero_point, qt)), L.ptr(gs), L.ptr(out), L.stream_ptr(w.device)))
     return out.view(_FP8) if qt == L.FP8 else out
+
+
+@torch.no_grad()
+def weight_global_scales(weights: torch.Tensor) -> torch.Tensor:
+    """Batched Observer.get_global_scale over a stack ``[units, rows, cols]`` -> fp32 ``[units]``."""
+    L.require_cuda(weights)
+    w = weights.contiguous()
+    batch = 1 if w.ndim == 2 else w.shape[0]
+    state = torch.empty(2 * batch, dtype=torch.float32, device=w.device)
+    gs = torch.empty(batch, dtype=torch.float32, device=w.device)
+    L.check(L.lib().b200q_global_scale(L.ptr(w), batch, w.numel() // batch, L.DTYPE_CODE[w.dtype], L.ptr(state), 0, L.ptr(gs),
+                                       L.stream_ptr(w.device)))
+    return gs
