@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include "../../include/b200q.h"
 #include "common.cuh"
@@ -15,6 +16,10 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+bool fast_paths_enabled() {  // B200Q_DISABLE_FAST=1 forces the generic kernels (A/B parity tests)
+    const char* e = getenv("B200Q_DISABLE_FAST");
+    return !(e && e[0] == '1');
 }
 }  // namespace b200q
 
@@ -50,6 +55,10 @@ int b200q_compress_int_packed(const void* weight, int64_t batch, int64_t rows, i
         GroupParams p{};
         p.w = weight; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = sc->num_bits;
         p.symmetric = sc->symmetric; p.has_zp = 1; p.scale = scale; p.zp_packed = zp_packed; p.out = packed;
+        if (sc->dtype == B200Q_BF16 && fast_paths_enabled()) {
+            const int rc = launch_int4_group_fast(p, batch, st);
+            if (rc != B200Q_ENOSYS) return rc;
+        }
         return dispatch_group<MODE_COMPRESS>(sc->dtype, QT_INT, p, batch, st);
     }
     if (sc->strategy == B200Q_CHANNEL) {

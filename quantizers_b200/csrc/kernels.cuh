@@ -22,6 +22,9 @@ struct GroupParams {
     void* out;              // codes / packed words / T values, depending on mode
 };
 template <int MODE> int dispatch_group(int dt, int qt, const GroupParams& p, int64_t batch, cudaStream_t st);
+// bf16 fast paths (issue-budget tuned); return B200Q_ENOSYS when the scheme/shape is not covered
+int launch_int4_group_fast(const GroupParams& p, int64_t batch, cudaStream_t st);
+bool fast_paths_enabled();
 
 // ---- generic element-wise path with caller-supplied qparams, any strategy (quant_elementwise.cu)
 struct ElemParams {

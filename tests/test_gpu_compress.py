@@ -219,3 +219,39 @@ def test_registered_compressors_match_live_ct(name):
         assert_bits_equal(got[k], ref[k], f"{name}:{k}")
     assert_bits_equal(got_dec["weight"], ref_dec["weight"], f"{name}:decompress")
     assert BaseCompressor.get_value_from_registry(fmt).__name__.startswith("B200") is False
+
+
+@pytest.mark.parametrize("name", ["int4_g128_asym", "int4_g128_sym", "int4_g32_sym", "int4_g32_asym", "fp8_block", "fp8_g32",
+                                  "fp8_channel", "nvfp4"])
+def test_generic_kernels_still_match_oracle_bf16(name, monkeypatch):
+    """bf16 normally takes the issue-tuned fast kernels; B200Q_DISABLE_FAST=1 forces the generic templates."""
+    from quantizers_b200 import ops
+
+    monkeypatch.setenv("B200Q_DISABLE_FAST", "1")
+    fmt, qtype, nb, sym, strat, g, blk = FORMATS[name]
+    w = synth_weight(72, 1280, torch.bfloat16, 31)
+    want = O.compress(w, fmt, geom_of(name), nb, sym)
+    got = ops.compress_weight(w.cuda(), Args(name))
+    _cmp_sd(got, want, name)
+
+
+def test_fast_int4_boundary_cases():
+    """Adversarial inputs for the reciprocal-multiply fast path: quotients that land on / next to bf16 rounding
+    boundaries, huge / tiny scales (exact-path fallback), exact zeros, and a dense sweep of all bf16 magnitudes."""
+    from quantizers_b200 import ops
+
+    rows = []
+    # every finite positive bf16 bit pattern (and negatives) as data, in groups whose absmax is set by column 0
+    allv = torch.arange(0x0001, 0x7F80, dtype=torch.int32).to(torch.int16).view(torch.bfloat16).float()
+    for scale_max in (1.0, 0.0371, 7.5, 3.0e-3, 1.0e30, 1.0e-30, 448.0):
+        v = allv[(allv <= scale_max)][-(127 * 64):]
+        blk = v.reshape(-1, 127)
+        blk = torch.cat([torch.full((blk.shape[0], 1), scale_max), blk * torch.where(torch.arange(127) % 2 == 0, 1.0, -1.0)], dim=1)
+        rows.append(blk)
+    w = torch.cat(rows).to(torch.bfloat16)
+    w = w[: (w.shape[0] // 8) * 8]
+    for name in ("int4_g128_asym", "int4_g128_sym", "int4_g32_sym", "int4_g32_asym"):
+        fmt, qtype, nb, sym, strat, g, blk = FORMATS[name]
+        want = O.compress(w, fmt, geom_of(name), nb, sym)
+        got = ops.compress_weight(w.cuda(), Args(name))
+        _cmp_sd(got, want, name)
