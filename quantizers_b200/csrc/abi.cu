@@ -56,7 +56,7 @@ int b200q_compress_int_packed(const void* weight, int64_t batch, int64_t rows, i
         p.w = weight; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = sc->num_bits;
         p.symmetric = sc->symmetric; p.has_zp = 1; p.scale = scale; p.zp_packed = zp_packed; p.out = packed;
         if (sc->dtype == B200Q_BF16 && fast_paths_enabled()) {
-            const int rc = launch_int4_group_fast(p, batch, st);
+            const int rc = launch_group_fast(QT_INT, p, batch, st);
             if (rc != B200Q_ENOSYS) return rc;
         }
         return dispatch_group<MODE_COMPRESS>(sc->dtype, QT_INT, p, batch, st);
@@ -81,6 +81,10 @@ int b200q_compress_fp8(const void* weight, int64_t batch, int64_t rows, int64_t 
         GroupParams p{};
         p.w = weight; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = 8; p.symmetric = 1;
         p.has_zp = sc->has_zp; p.scale = scale; p.out = q;
+        if (sc->dtype == B200Q_BF16 && fast_paths_enabled()) {
+            const int rc = launch_group_fast(QT_FP8, p, batch, st);
+            if (rc != B200Q_ENOSYS) return rc;
+        }
         return dispatch_group<MODE_COMPRESS>(sc->dtype, QT_FP8, p, batch, st);
     }
     TileParams p{};
@@ -90,6 +94,10 @@ int b200q_compress_fp8(const void* weight, int64_t batch, int64_t rows, int64_t 
     if (sc->strategy == B200Q_BLOCK) {
         B200Q_REQUIRE(sc->block_h == 128 && sc->block_w == 128, "fused block compress supports block_structure [128,128], got [%d,%d]",
                       sc->block_h, sc->block_w);
+        if (sc->dtype == B200Q_BF16 && fast_paths_enabled()) {
+            const int rc = launch_block_fp8_fast(p, batch, st);
+            if (rc != B200Q_ENOSYS) return rc;
+        }
         return launch_block_fp8_compress(sc->dtype, p, batch, st);
     }
     return launch_tensor_fp8_compress(sc->dtype, p, batch, st);
@@ -110,6 +118,10 @@ int b200q_compress_nvfp4(const void* weight, int64_t batch, int64_t rows, int64_
     GroupParams p{};
     p.w = weight; p.rows = rows; p.cols = cols; p.group = 16; p.nbits = 4; p.symmetric = 1; p.has_zp = 1;
     p.scale = scale_e4m3; p.gs = global_scale; p.gs_stride = 1; p.out = packed;
+    if (dtype == B200Q_BF16 && fast_paths_enabled()) {
+        const int rc = launch_nvfp4_fast(p, batch, st);
+        if (rc != B200Q_ENOSYS) return rc;
+    }
     return dispatch_group<MODE_COMPRESS>(dtype, QT_FP4, p, batch, st);
 }
 

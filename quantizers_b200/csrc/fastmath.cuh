@@ -1,0 +1,52 @@
+// fastmath.cuh -- sm_100a packed-math building blocks of the issue-tuned bf16 kernels.
+//
+// Exact T(x / s) without an IEEE division per element ("bracketed reciprocal"):
+//   r = rcp.approx(s) (<= 1 ulp), r_lo = r(1 - 2^-21), r_hi = r(1 + 2^-21)  =>  x*r_lo <= x/s <= x*r_hi in magnitude,
+//   with >= 2^-22 relative slack on both sides after every rounding involved.  Rounding is monotone, so if the
+//   two bracket ends round to the same low-precision value (bf16 / e2m1 code), the reference's
+//   round(fp32(x/s)) rounds to it too.  When they differ (p ~ 1.5e-5 .. 2.5e-4 per element) the element is
+//   recomputed with the IEEE chain from qmath.cuh.  Packed FMUL2/FFMA2 + F2FP keep this at 2.5 issue slots per
+//   element instead of ~9 for div.rn.
+#pragma once
+#include "common.cuh"
+
+namespace b200q {
+namespace fast {
+
+__device__ __forceinline__ uint32_t hmax2(uint32_t a, uint32_t b) { uint32_t r; asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t hmin2(uint32_t a, uint32_t b) { uint32_t r; asm("min.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t hmaxabs2(uint32_t a, uint32_t b) { uint32_t r; asm("max.xorsign.abs.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) { uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+
+struct f32x2 { uint64_t v; };
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+// a*b + 0.0: kills -0.0 exactly like the reference's "+ zero_point(0)" (x = -0.0 -> +0.0), same issue cost as mul2
+__device__ __forceinline__ f32x2 mul2_plus0(f32x2 a, f32x2 b) {
+    f32x2 r;
+    const uint64_t z = 0;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(z));
+    return r;
+}
+// the two bf16 halves of a 32-bit word as an fp32 pair (lo element first)
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t w) { return pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+
+struct Bracket {
+    f32x2 lo, hi;  // (r_lo, r_lo), (r_hi, r_hi)
+    __device__ __forceinline__ void init(float s) {
+        const float r = rcp_approx(s);
+        const float a = __fmul_rn(r, 0.99999952316284179688f);  // 1 - 2^-21
+        const float b = __fmul_rn(r, 1.00000047683715820312f);  // 1 + 2^-21
+        lo = pack2(a, a);
+        hi = pack2(b, b);
+    }
+};
+// 2^-100 <= s <= 1: reciprocal normal, quotients of in-group data neither overflow nor lose their sign
+__device__ __forceinline__ bool scale_is_safe(uint32_t s_bits) { return (s_bits - 0x0d800000u) <= (0x3f800000u - 0x0d800000u); }
+
+}  // namespace fast
+}  // namespace b200q

@@ -5,6 +5,8 @@
 
 namespace b200q {
 
+struct TileParams;
+
 enum : int { MODE_COMPRESS = 0, MODE_QUANT = 1, MODE_FQ = 2, MODE_OBS_FQ = 3, MODE_QUANT_PACK = 4 };
 
 // ---- GROUP / TENSOR_GROUP (quant_group.cu)
@@ -23,7 +25,9 @@ struct GroupParams {
 };
 template <int MODE> int dispatch_group(int dt, int qt, const GroupParams& p, int64_t batch, cudaStream_t st);
 // bf16 fast paths (issue-budget tuned); return B200Q_ENOSYS when the scheme/shape is not covered
-int launch_int4_group_fast(const GroupParams& p, int64_t batch, cudaStream_t st);
+int launch_group_fast(int qt, const GroupParams& p, int64_t batch, cudaStream_t st);
+int launch_block_fp8_fast(const TileParams& p, int64_t batch, cudaStream_t st);
+int launch_nvfp4_fast(const GroupParams& p, int64_t batch, cudaStream_t st);
 bool fast_paths_enabled();
 
 // ---- generic element-wise path with caller-supplied qparams, any strategy (quant_elementwise.cu)

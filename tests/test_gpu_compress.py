@@ -245,13 +245,26 @@ def test_fast_int4_boundary_cases():
     allv = torch.arange(0x0001, 0x7F80, dtype=torch.int32).to(torch.int16).view(torch.bfloat16).float()
     for scale_max in (1.0, 0.0371, 7.5, 3.0e-3, 1.0e30, 1.0e-30, 448.0):
         v = allv[(allv <= scale_max)][-(127 * 64):]
+        v = v[: (v.numel() // 127) * 127]
         blk = v.reshape(-1, 127)
         blk = torch.cat([torch.full((blk.shape[0], 1), scale_max), blk * torch.where(torch.arange(127) % 2 == 0, 1.0, -1.0)], dim=1)
         rows.append(blk)
     w = torch.cat(rows).to(torch.bfloat16)
     w = w[: (w.shape[0] // 8) * 8]
-    for name in ("int4_g128_asym", "int4_g128_sym", "int4_g32_sym", "int4_g32_asym"):
+    for name in ("int4_g128_asym", "int4_g128_sym", "int4_g32_sym", "int4_g32_asym", "fp8_g32", "fp8_g128", "fp8_block", "nvfp4"):
         fmt, qtype, nb, sym, strat, g, blk = FORMATS[name]
         want = O.compress(w, fmt, geom_of(name), nb, sym)
         got = ops.compress_weight(w.cuda(), Args(name))
         _cmp_sd(got, want, name)
+    # NVFP4 thresholds: quotients exactly on / one ulp around the e2m1 rounding points, scale fixed by column 0 = 6.0
+    th = torch.tensor([0.25, 0.75, 1.25, 1.75, 2.5, 3.5, 5.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0, 0.0])
+    th_bits = th.to(torch.bfloat16).view(torch.int16).int()
+    cols = [torch.full((15,), 6.0)]
+    for d in (-1, 0, 1):
+        v = (th_bits + d).clamp(min=0).to(torch.int16).view(torch.bfloat16).float()
+        cols += [v, -v]
+    blk16 = torch.stack(cols + [torch.zeros(15)] * (16 - len(cols)), dim=1)  # [15, 16]
+    w2 = blk16.repeat(8, 8).to(torch.bfloat16)  # [120, 128]
+    want = O.compress(w2, "nvfp4-pack-quantized", geom_of("nvfp4"), 4, True)
+    got = ops.compress_weight(w2.cuda(), Args("nvfp4"))
+    _cmp_sd(got, want, "nvfp4 thresholds")
