@@ -17,6 +17,10 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+bool tma_paths_enabled() {  // B200Q_DISABLE_TMA=1 selects the register-tile fast kernels instead
+    const char* e = getenv("B200Q_DISABLE_TMA");
+    return !(e && e[0] == '1');
+}
 bool fast_paths_enabled() {  // B200Q_DISABLE_FAST=1 forces the generic kernels (A/B parity tests)
     const char* e = getenv("B200Q_DISABLE_FAST");
     return !(e && e[0] == '1');
@@ -56,7 +60,8 @@ int b200q_compress_int_packed(const void* weight, int64_t batch, int64_t rows, i
         p.w = weight; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = sc->num_bits;
         p.symmetric = sc->symmetric; p.has_zp = 1; p.scale = scale; p.zp_packed = zp_packed; p.out = packed;
         if (sc->dtype == B200Q_BF16 && fast_paths_enabled()) {
-            const int rc = launch_group_fast(QT_INT, p, batch, st);
+            int rc = tma_paths_enabled() ? launch_group_tma(QT_INT, p, batch, st) : B200Q_ENOSYS;
+            if (rc == B200Q_ENOSYS) rc = launch_group_fast(QT_INT, p, batch, st);
             if (rc != B200Q_ENOSYS) return rc;
         }
         return dispatch_group<MODE_COMPRESS>(sc->dtype, QT_INT, p, batch, st);
@@ -82,7 +87,8 @@ int b200q_compress_fp8(const void* weight, int64_t batch, int64_t rows, int64_t 
         p.w = weight; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = 8; p.symmetric = 1;
         p.has_zp = sc->has_zp; p.scale = scale; p.out = q;
         if (sc->dtype == B200Q_BF16 && fast_paths_enabled()) {
-            const int rc = launch_group_fast(QT_FP8, p, batch, st);
+            int rc = tma_paths_enabled() ? launch_group_tma(QT_FP8, p, batch, st) : B200Q_ENOSYS;
+            if (rc == B200Q_ENOSYS) rc = launch_group_fast(QT_FP8, p, batch, st);
             if (rc != B200Q_ENOSYS) return rc;
         }
         return dispatch_group<MODE_COMPRESS>(sc->dtype, QT_FP8, p, batch, st);
@@ -119,7 +125,8 @@ int b200q_compress_nvfp4(const void* weight, int64_t batch, int64_t rows, int64_
     p.w = weight; p.rows = rows; p.cols = cols; p.group = 16; p.nbits = 4; p.symmetric = 1; p.has_zp = 1;
     p.scale = scale_e4m3; p.gs = global_scale; p.gs_stride = 1; p.out = packed;
     if (dtype == B200Q_BF16 && fast_paths_enabled()) {
-        const int rc = launch_nvfp4_fast(p, batch, st);
+        int rc = tma_paths_enabled() ? launch_group_tma(QT_FP4, p, batch, st) : B200Q_ENOSYS;
+        if (rc == B200Q_ENOSYS) rc = launch_nvfp4_fast(p, batch, st);
         if (rc != B200Q_ENOSYS) return rc;
     }
     return dispatch_group<MODE_COMPRESS>(dtype, QT_FP4, p, batch, st);

@@ -1,0 +1,377 @@
+// quant_group_tma.cu -- bf16 GROUP / TENSOR_GROUP fused compress, TMA-staged "lane owns a group" design.
+//
+// Why: with a warp spread across a group (quant_group_fast.cu) the group statistics need a shuffle butterfly, the
+// qparams have to be transposed to owner lanes and broadcast back, and every lane re-derives reciprocals per
+// chunk; ncu shows ~21 issued instructions per weight against a budget of ~13 at HBM speed.  Here shared memory is
+// the transposer:
+//   * the weight is a flat array of groups ([batch, rows, cols] is contiguous and groups never straddle rows), a
+//     warp tile is 4096 consecutive elements (8 KB) = 16 x 16-byte chunks per lane;
+//   * tiles are brought in by the TMA engine (1-D cp.async.bulk + mbarrier, 3 stages per warp, issued by lane 0),
+//     so loads are fully asynchronous and independent of occupancy; packed codes leave through a bulk store;
+//   * lane l owns groups {l, l+32, ...} of the tile and walks its chunks in a rotated order that is bank-conflict
+//     free (LDS.128): statistics are a straight max/min chain (no shuffles), qparams are computed once per group by
+//     the lane that uses them, the reciprocal bracket (fastmath.cuh) is set up once per group.
+// Arithmetic is the same bit-exact chain as the other kernels (qmath.cuh); elements whose reciprocal bracket is
+// ambiguous are recomputed with the IEEE path.  Zero-points of asymmetric INT4 are OR-ed into the row-packed int32
+// layout with one atomic per group (the buffer is zeroed by the launcher).
+#include "common.cuh"
+#include "fastmath.cuh"
+#include "kernels.cuh"
+
+namespace b200q {
+namespace {
+using namespace fast;
+
+constexpr int kWarps = 8;
+constexpr int kStages = 3;
+constexpr int kTileElems = 4096;
+constexpr int kTileBytes = kTileElems * 2;
+
+// ---- mbarrier / bulk-copy PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v)); }
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(v.x), "r"(v.y)); }
+
+__device__ __forceinline__ uint32_t cvt_e4m3x2(float hi, float lo) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t cvt_e2m1x2(float hi, float lo) {
+    uint16_t r;
+    asm("{ .reg .b8 t; cvt.rn.satfinite.e2m1x2.f32 t, %1, %2; cvt.u16.u8 %0, t; }" : "=h"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ bool fp4_scale_is_safe(float s_eff) { return s_eff >= 7.8886090522101181e-31f && s_eff <= 65536.0f; }
+
+struct TmaParams {
+    const uint16_t* w;        // flat bf16
+    int64_t n_groups;         // batch * rows * cols / g
+    int64_t groups_per_mat;   // rows * cols / g
+    int64_t groups_per_row;   // cols / g
+    int64_t rows;
+    uint8_t* out;             // packed codes, flat
+    void* scale;              // bf16 (INT/FP8) or e4m3 bytes (FP4), flat [n_groups]
+    int32_t* zp_packed;       // asym INT4
+    const float* gs;          // FP4: fp32 [batch] (stride 1) or [1] (stride 0)
+    int32_t gs_stride;
+    int32_t has_zp;
+};
+
+// ---- exact per-element repair of one chunk (rare): returns the repaired packed representation
+template <int QT, bool SYM>
+__device__ __noinline__ uint2 repair_chunk(const uint4 raw, float s, float z, bool add_zp, bool all, uint2 packed) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    Bracket br;
+    br.init(s);
+    float rl, rh, dummy;
+    unpack2(br.lo, rl, dummy);
+    unpack2(br.hi, rh, dummy);
+    uint32_t o[2] = {packed.x, packed.y};
+#pragma unroll 1
+    for (int e = 0; e < 8; e++) {
+        const uint32_t half = (e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16);
+        const float x = __uint_as_float(half);
+        bool differ;
+        if (QT == QT_FP4) differ = cvt_e2m1x2(0.0f, __fmaf_rn(x, rl, 0.0f)) != cvt_e2m1x2(0.0f, __fmaf_rn(x, rh, 0.0f));
+        else differ = __float2bfloat16_rn(__fmul_rn(x, rl)) != __float2bfloat16_rn(__fmul_rn(x, rh));
+        if (all || differ) {
+            if (QT == QT_INT) {
+                const uint32_t c = (uint32_t)(quant_int<DT_BF16>(x, s, z, !SYM, -8.0f, 7.0f) + 8) & 0xfu;
+                o[0] = (o[0] & ~(0xfu << (4 * e))) | (c << (4 * e));
+            } else if (QT == QT_FP8) {
+                const uint32_t c = quant_fp8<DT_BF16>(x, s, add_zp);
+                o[e >> 2] = (o[e >> 2] & ~(0xffu << (8 * (e & 3)))) | (c << (8 * (e & 3)));
+            } else {
+                o[0] = (o[0] & ~(0xfu << (4 * e))) | (quant_fp4(x, s) << (4 * e));
+            }
+        }
+    }
+    return make_uint2(o[0], o[1]);
+}
+
+// LOG2N: log2(chunks per group): 1 (g16) 2 (g32) 3 (g64) 4 (g128)
+template <int QT, bool SYM, int LOG2N>
+__global__ void __launch_bounds__(kWarps * 32, 1) group_tma_kernel(const TmaParams p) {
+    constexpr int N = 1 << LOG2N;          // chunks per group
+    constexpr int GPL = 16 / N;            // groups per lane per tile
+    constexpr int G = 8 * N;               // group size
+    constexpr int GPT = 32 * GPL;          // groups per tile
+    constexpr int OUT_CHUNK = (QT == QT_FP8) ? 8 : 4;  // output bytes per 8-element chunk
+    constexpr int OUT_BYTES = 512 * OUT_CHUNK;         // per tile
+    constexpr int ROT_SHIFT = (LOG2N >= 3) ? 0 : (3 - LOG2N);
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* my = smem + (size_t)warp * (kStages * kTileBytes + OUT_BYTES + 64);
+    const uint32_t in_base = smem_u32(my);
+    const uint32_t out_base = in_base + kStages * kTileBytes;
+    const uint32_t bar_base = out_base + OUT_BYTES;
+
+    const int64_t n_tiles = (p.n_groups + GPT - 1) / GPT;
+    const int64_t gwarp = (int64_t)blockIdx.x * kWarps + warp;
+    const int64_t wstride = (int64_t)gridDim.x * kWarps;
+
+    if (lane == 0) {
+        for (int s = 0; s < kStages; s++) mbar_init(bar_base + 8 * s, 1);
+        fence_async_smem();
+    }
+    __syncwarp();
+
+    auto issue = [&](int64_t tile, int stage) {
+        const int64_t g0 = tile * GPT;
+        const uint32_t bytes = (uint32_t)(min((int64_t)GPT, p.n_groups - g0) * G * 2);
+        mbar_arrive_expect_tx(bar_base + 8 * stage, bytes);
+        tma_load_1d(in_base + stage * kTileBytes, p.w + g0 * G, bytes, bar_base + 8 * stage);
+    };
+    if (lane == 0) {
+        for (int s = 0; s < kStages; s++) {
+            const int64_t t = gwarp + s * wstride;
+            if (t < n_tiles) issue(t, s);
+        }
+    }
+
+    const uint32_t kMagic = 0x43484348u, kUnbias = 0xbcc0bcc0u;
+    const int rot = lane >> ROT_SHIFT;
+    int it = 0;
+    for (int64_t tile = gwarp; tile < n_tiles; tile += wstride, it++) {
+        const int stage = it % kStages;
+        const uint32_t parity = (uint32_t)(it / kStages) & 1u;
+        const int64_t g0 = tile * GPT;
+        const int n_here = (int)min((int64_t)GPT, p.n_groups - g0);
+        mbar_wait(bar_base + 8 * stage, parity);
+        const uint32_t tin = in_base + stage * kTileBytes;
+
+        // the previous tile's bulk store must have finished READING the staging buffer before we overwrite it
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+
+        // position of the tile's first group (warp-uniform, once per tile): matrix b0, row r0, group-in-row k0
+        int64_t b0 = 0;
+        uint32_t r0 = 0, k0 = 0;
+        if (QT == QT_INT && !SYM) {
+            b0 = g0 / p.groups_per_mat;
+            const int64_t rem0 = g0 - b0 * p.groups_per_mat;
+            r0 = (uint32_t)(rem0 / p.groups_per_row);
+            k0 = (uint32_t)(rem0 - (int64_t)r0 * p.groups_per_row);
+        }
+        float gs_tile = 1.0f;
+        bool gs_uniform = true;
+        if (QT == QT_FP4) {
+            if (p.gs_stride == 0) gs_tile = p.gs[0];
+            else {
+                const int64_t b0 = g0 / p.groups_per_mat, b1 = (g0 + n_here - 1) / p.groups_per_mat;
+                gs_uniform = (b0 == b1);
+                gs_tile = p.gs[b0];
+            }
+        }
+
+#pragma unroll 1
+        for (int gi = 0; gi < GPL; gi++) {
+            const int gl = gi * 32 + lane;           // group index inside the tile
+            if (gl >= n_here) continue;              // partial last tile (no warp-level sync inside this loop)
+            const uint32_t gaddr = tin + (uint32_t)gl * (G * 2);
+            // ---- A. statistics
+            uint32_t st_a = 0, st_b = 0;
+            if (SYM) {
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    const uint4 v = lds128(gaddr + (((i + rot) & (N - 1)) << 4));
+                    st_a = hmaxabs2(st_a, hmaxabs2(hmaxabs2(v.x, v.y), hmaxabs2(v.z, v.w)));
+                }
+                st_a = hmaxabs2(st_a, prmt(st_a, st_a, 0x1032));
+            } else {
+                st_a = 0xff80ff80u;  // (-inf, -inf)
+                st_b = 0x7f807f80u;  // (+inf, +inf)
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    const uint4 v = lds128(gaddr + (((i + rot) & (N - 1)) << 4));
+                    st_a = hmax2(st_a, hmax2(hmax2(v.x, v.y), hmax2(v.z, v.w)));
+                    st_b = hmin2(st_b, hmin2(hmin2(v.x, v.y), hmin2(v.z, v.w)));
+                }
+                st_a = hmax2(st_a, prmt(st_a, st_a, 0x1032));
+                st_b = hmin2(st_b, prmt(st_b, st_b, 0x1032));
+            }
+            // ---- B. qparams (once per group, by the lane that uses them)
+            float s, z = 0.0f;
+            const int64_t gidx = g0 + gl;
+            if (QT == QT_FP4) {
+                float gsv = gs_tile;
+                if (!gs_uniform) gsv = p.gs[gidx / p.groups_per_mat];
+                const uint8_t code = qparams_fp4<DT_BF16>(__uint_as_float((st_a << 16) & 0x7fff0000u), gsv, s);
+                ((uint8_t*)p.scale)[gidx] = code;
+            } else {
+                if (SYM) s = scale_sym<DT_BF16>(__uint_as_float((st_a << 16) & 0x7fff0000u), QT == QT_INT ? 7.5f : 448.0f);
+                else qparams_asym<DT_BF16>(__uint_as_float(st_b << 16), __uint_as_float(st_a << 16), -8.0f, 7.0f, s, z);
+                ((uint16_t*)p.scale)[gidx] = (uint16_t)(__float_as_uint(s) >> 16);
+                if (QT == QT_INT && !SYM) {
+                    const uint32_t gpr = (uint32_t)p.groups_per_row;  // launcher guarantees < 2^31
+                    const uint32_t t = k0 + (uint32_t)gl, dr = t / gpr, k = t - dr * gpr;
+                    int64_t b = b0, r = (int64_t)r0 + dr;
+                    while (r >= p.rows) { r -= p.rows; b++; }
+                    const int64_t zrows = (p.rows + 7) >> 3;
+                    atomicOr((unsigned int*)&p.zp_packed[(b * zrows + (r >> 3)) * p.groups_per_row + k],
+                             ((uint32_t)((int)z + 8) & 0xfu) << (4 * (int)(r & 7)));
+                }
+            }
+            // ---- C. quantize + pack into the staging buffer
+            Bracket br;
+            br.init(s);
+            const bool unsafe = (QT == QT_FP4) ? !fp4_scale_is_safe(s) : !scale_is_safe(__float_as_uint(s));
+            const bool add_zp = (QT == QT_FP8) ? (p.has_zp != 0) : true;
+            const uint32_t z2 = (__float_as_uint(z) >> 16) * 0x10001u;
+            const uint32_t oaddr = out_base + (uint32_t)gl * (N * OUT_CHUNK);
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                const int c = (i + rot) & (N - 1);
+                const uint4 v = lds128(gaddr + (c << 4));
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                uint32_t h[4], diff = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const f32x2 x = bf16x2_to_f32x2(w[k]);
+                    float al, ah, bl, bh;
+                    if (QT == QT_INT) {
+                        unpack2(mul2(x, br.lo), al, ah);
+                        unpack2(mul2(x, br.hi), bl, bh);
+                        uint32_t u = cvt_bf16x2(ah, al);
+                        diff |= u ^ cvt_bf16x2(bh, bl);
+                        if (!SYM) u = hadd2(u, z2);
+                        h[k] = __viaddmin_s16x2_relu(hadd2(u, kMagic), kUnbias, 0x000f000fu);
+                    } else if (QT == QT_FP8) {
+                        unpack2(add_zp ? mul2_plus0(x, br.lo) : mul2(x, br.lo), al, ah);
+                        unpack2(add_zp ? mul2_plus0(x, br.hi) : mul2(x, br.hi), bl, bh);
+                        const uint32_t u = cvt_bf16x2(ah, al);
+                        diff |= u ^ cvt_bf16x2(bh, bl);
+                        h[k] = cvt_e4m3x2(__uint_as_float(u & 0xffff0000u), __uint_as_float(u << 16));
+                    } else {
+                        unpack2(mul2_plus0(x, br.lo), al, ah);
+                        unpack2(mul2_plus0(x, br.hi), bl, bh);
+                        h[k] = cvt_e2m1x2(ah, al);
+                        diff |= h[k] ^ cvt_e2m1x2(bh, bl);
+                    }
+                }
+                uint2 packed;
+                if (QT == QT_INT) {
+                    const uint32_t x01 = prmt(h[0], h[1], 0x6420), x23 = prmt(h[2], h[3], 0x6420);
+                    packed = make_uint2(prmt(x01 | (x01 >> 4), x23 | (x23 >> 4), 0x6420), 0u);
+                } else if (QT == QT_FP8) {
+                    packed = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+                } else {
+                    packed = make_uint2(h[0] | (h[1] << 8) | (h[2] << 16) | (h[3] << 24), 0u);
+                }
+                if (diff != 0 || unsafe) packed = repair_chunk<QT, SYM>(v, s, z, add_zp, unsafe, packed);
+                if (QT == QT_FP8) sts64(oaddr + c * 8, packed);
+                else sts32(oaddr + c * 4, packed.x);
+            }
+        }
+        // ---- D. hand the packed tile to the TMA engine, refill this input stage
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_1d(p.out + g0 * (N * OUT_CHUNK), out_base, (uint32_t)n_here * (N * OUT_CHUNK));
+            bulk_commit();
+            const int64_t nt = tile + (int64_t)kStages * wstride;
+            if (nt < n_tiles) issue(nt, stage);
+        }
+    }
+    if (lane == 0) bulk_wait0();
+}
+
+template <int QT, bool SYM, int LOG2N>
+int launch_tma(const TmaParams& p, cudaStream_t st) {
+    constexpr int OUT_BYTES = 512 * ((QT == QT_FP8) ? 8 : 4);
+    const size_t smem = (size_t)kWarps * (kStages * kTileBytes + OUT_BYTES + 64);
+    static bool configured = false;  // benign race: idempotent attribute
+    if (!configured) {
+        cudaFuncSetAttribute(group_tma_kernel<QT, SYM, LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    constexpr int GPT = 32 * (16 >> LOG2N);
+    const int64_t n_tiles = (p.n_groups + GPT - 1) / GPT;
+    const int64_t ctas = max((int64_t)1, min((int64_t)kNumSMs, (n_tiles + kWarps - 1) / kWarps));
+    group_tma_kernel<QT, SYM, LOG2N><<<(unsigned)ctas, kWarps * 32, smem, st>>>(p);
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+}  // namespace
+
+// bf16 only.  Returns B200Q_ENOSYS when the scheme / shape is not covered.
+int launch_group_tma(int qt, const GroupParams& gp, int64_t batch, cudaStream_t st) {
+    const int g = gp.group;
+    if (!(g == 16 || g == 32 || g == 64 || g == 128) || gp.cols % g != 0) return B200Q_ENOSYS;
+    if ((((uintptr_t)gp.w) & 15) != 0 || (((uintptr_t)gp.out) & 15) != 0 || batch * gp.rows * gp.cols == 0) return B200Q_ENOSYS;
+    if ((batch * gp.rows * gp.cols) % 32 != 0) return B200Q_ENOSYS;  // bulk copies move multiples of 16 bytes
+    if (gp.cols / g >= (1ll << 30) || gp.rows >= (1ll << 40)) return B200Q_ENOSYS;
+    TmaParams p{};
+    p.w = (const uint16_t*)gp.w;
+    p.groups_per_row = gp.cols / g;
+    p.groups_per_mat = gp.rows * p.groups_per_row;
+    p.n_groups = batch * p.groups_per_mat;
+    p.rows = gp.rows;
+    p.out = (uint8_t*)gp.out;
+    p.scale = gp.scale;
+    p.zp_packed = gp.zp_packed;
+    p.gs = gp.gs;
+    p.gs_stride = gp.gs_stride;
+    p.has_zp = gp.has_zp;
+    if (qt == QT_INT && gp.nbits == 4) {
+        if (!gp.symmetric) {
+            if (gp.zp_packed == nullptr) return B200Q_ENOSYS;
+            cudaMemsetAsync(gp.zp_packed, 0, sizeof(int32_t) * batch * ((gp.rows + 7) / 8) * p.groups_per_row, st);
+        }
+        switch (g) {
+        case 32: return gp.symmetric ? launch_tma<QT_INT, true, 2>(p, st) : launch_tma<QT_INT, false, 2>(p, st);
+        case 64: return gp.symmetric ? launch_tma<QT_INT, true, 3>(p, st) : launch_tma<QT_INT, false, 3>(p, st);
+        case 128: return gp.symmetric ? launch_tma<QT_INT, true, 4>(p, st) : launch_tma<QT_INT, false, 4>(p, st);
+        default: return B200Q_ENOSYS;
+        }
+    }
+    if (qt == QT_FP8) {
+        switch (g) {
+        case 32: return launch_tma<QT_FP8, true, 2>(p, st);
+        case 64: return launch_tma<QT_FP8, true, 3>(p, st);
+        case 128: return launch_tma<QT_FP8, true, 4>(p, st);
+        default: return B200Q_ENOSYS;
+        }
+    }
+    if (qt == QT_FP4 && g == 16) return launch_tma<QT_FP4, true, 1>(p, st);
+    return B200Q_ENOSYS;
+}
+
+}  // namespace b200q

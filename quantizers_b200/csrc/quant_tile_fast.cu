@@ -103,6 +103,11 @@ __global__ void __launch_bounds__(256, 3) block_fp8_fast_kernel(const TileParams
 // thread = U2 groups of 16 contiguous elements; warp = 512 contiguous columns per step; CTA = 8 rows
 constexpr int U2 = 2;
 
+// fast path: reciprocal normal (s_eff >= 2^-100) and no quotient of a non-zero bf16 (>= 2^-133) underflows to zero
+// (s_eff <= 2^16): an underflowed -0.0 would keep its sign through the fused "+ 0.0", the reference's two-step
+// (divide, then add the zero-point) turns it into +0.0.
+__device__ __forceinline__ bool fp4_scale_is_safe(float s_eff) { return s_eff >= 7.8886090522101181e-31f && s_eff <= 65536.0f; }
+
 __device__ __noinline__ uint32_t fix_group_fp4(const uint4 raw, float s_eff, uint32_t packed) {
     const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
     Bracket br;
@@ -110,7 +115,7 @@ __device__ __noinline__ uint32_t fix_group_fp4(const uint4 raw, float s_eff, uin
     float rl, rh, dummy;
     unpack2(br.lo, rl, dummy);
     unpack2(br.hi, rh, dummy);
-    const bool all = !(s_eff >= 7.8886090522101181e-31f && s_eff <= 1.2676506002282294e30f);
+    const bool all = !fp4_scale_is_safe(s_eff);
 #pragma unroll 1
     for (int e = 0; e < 8; e++) {
         const uint32_t half = (e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16);
@@ -153,8 +158,7 @@ __global__ void __launch_bounds__(256, 4) nvfp4_fast_kernel(const GroupParams p)
         ((uint8_t*)p.scale)[(b * p.rows + row) * gtot + (cbase[j] >> 4)] = code;
         Bracket br;
         br.init(s_eff);
-        // fast path needs a normal reciprocal and no overflow: 2^-100 <= s_eff <= 2^100
-        const bool unsafe = !(s_eff >= 7.8886090522101181e-31f && s_eff <= 1.2676506002282294e30f);
+        const bool unsafe = !fp4_scale_is_safe(s_eff);
         uint32_t out[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
