@@ -45,6 +45,17 @@ struct Bracket {
         hi = pack2(b, b);
     }
 };
+// exact T(a / divisor) for a non-negative bf16 statistic and a compile-time divisor, without an IEEE division on the
+// common path: multiply by the bracketed constant reciprocal, fall back when the two ends round differently.
+__device__ __forceinline__ float div_const_bf16(float a, float divisor) {
+    const float c = 1.0f / divisor;  // folded at compile time (round-to-nearest)
+    const float lo = __fmul_rn(a, c * 0.99999952316284179688f), hi = __fmul_rn(a, c * 1.00000047683715820312f);
+    const uint32_t u = cvt_bf16x2(hi, lo);
+    const bool ok = ((u >> 16) == (u & 0xffffu)) && (a == 0.0f || (a >= 7.8886090522101181e-31f && a <= 1.2676506002282294e30f));
+    if (ok) return __uint_as_float(u << 16);
+    return round_to<DT_BF16>(__fdiv_rn(a, divisor));
+}
+
 // 2^-100 <= s <= 1: reciprocal normal, quotients of in-group data neither overflow nor lose their sign
 __device__ __forceinline__ bool scale_is_safe(uint32_t s_bits) { return (s_bits - 0x0d800000u) <= (0x3f800000u - 0x0d800000u); }
 

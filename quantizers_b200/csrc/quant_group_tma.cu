@@ -14,6 +14,7 @@
 // Arithmetic is the same bit-exact chain as the other kernels (qmath.cuh); elements whose reciprocal bracket is
 // ambiguous are recomputed with the IEEE path.  Zero-points of asymmetric INT4 are OR-ed into the row-packed int32
 // layout with one atomic per group (the buffer is zeroed by the launcher).
+#include <cstdlib>
 #include "common.cuh"
 #include "fastmath.cuh"
 #include "kernels.cuh"
@@ -22,9 +23,11 @@ namespace b200q {
 namespace {
 using namespace fast;
 
-constexpr int kWarps = 8;
-constexpr int kStages = 3;
+constexpr int kStages = 2;
 constexpr int kTileElems = 4096;
+// warps per CTA (one CTA per SM): as many as shared memory allows -- ncu showed 8 warps/SM leave the issue slots
+// half idle (serial qparam chains, LDS/MUFU latency)
+template <int QT> struct WarpsFor { static constexpr int value = (QT == QT_FP8) ? 10 : 12; };
 constexpr int kTileBytes = kTileElems * 2;
 
 // ---- mbarrier / bulk-copy PTX
@@ -126,7 +129,8 @@ __device__ __noinline__ uint2 repair_chunk(const uint4 raw, float s, float z, bo
 
 // LOG2N: log2(chunks per group): 1 (g16) 2 (g32) 3 (g64) 4 (g128)
 template <int QT, bool SYM, int LOG2N>
-__global__ void __launch_bounds__(kWarps * 32, 1) group_tma_kernel(const TmaParams p) {
+__global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(const TmaParams p) {
+    constexpr int kWarps = WarpsFor<QT>::value;
     constexpr int N = 1 << LOG2N;          // chunks per group
     constexpr int GPL = 16 / N;            // groups per lane per tile
     constexpr int G = 8 * N;               // group size
@@ -200,45 +204,93 @@ __global__ void __launch_bounds__(kWarps * 32, 1) group_tma_kernel(const TmaPara
             }
         }
 
-#pragma unroll 1
+        // FP4: s_eff = fp32(s) / gs with s = M * 2^E (M in 1..15): RN(M / gs) * 2^E is the same fp32 value, so one
+        // IEEE division per lane per TILE (lane = M) replaces one per group; groups fetch their entry by shuffle.
+        float tab = 0.0f;
+        const bool gs_tab_ok = gs_uniform && gs_tile >= 8.6736173798840355e-19f && gs_tile <= 1.152921504606846976e18f;  // 2^+-60
+        if (QT == QT_FP4) tab = __fdiv_rn((float)(lane & 15), gs_tile);
+
+#pragma unroll (GPL >= 4 ? 2 : 1)
         for (int gi = 0; gi < GPL; gi++) {
             const int gl = gi * 32 + lane;           // group index inside the tile
-            if (gl >= n_here) continue;              // partial last tile (no warp-level sync inside this loop)
+            const bool act = gl < n_here;            // partial last tile: inactive lanes compute on stale smem, store nothing
             const uint32_t gaddr = tin + (uint32_t)gl * (G * 2);
-            // ---- A. statistics
-            uint32_t st_a = 0, st_b = 0;
+            // ---- A. statistics (two independent chains for ILP)
+            uint32_t st_a, st_b = 0;
             if (SYM) {
+                uint32_t a0 = 0, a1 = 0;
 #pragma unroll
-                for (int i = 0; i < N; i++) {
-                    const uint4 v = lds128(gaddr + (((i + rot) & (N - 1)) << 4));
-                    st_a = hmaxabs2(st_a, hmaxabs2(hmaxabs2(v.x, v.y), hmaxabs2(v.z, v.w)));
+                for (int i = 0; i < N; i += 2) {
+                    const uint4 v0 = lds128(gaddr + (((i + rot) & (N - 1)) << 4));
+                    const uint4 v1 = lds128(gaddr + (((i + 1 + rot) & (N - 1)) << 4));
+                    a0 = hmaxabs2(a0, hmaxabs2(hmaxabs2(v0.x, v0.y), hmaxabs2(v0.z, v0.w)));
+                    a1 = hmaxabs2(a1, hmaxabs2(hmaxabs2(v1.x, v1.y), hmaxabs2(v1.z, v1.w)));
                 }
+                st_a = hmaxabs2(a0, a1);
                 st_a = hmaxabs2(st_a, prmt(st_a, st_a, 0x1032));
             } else {
-                st_a = 0xff80ff80u;  // (-inf, -inf)
-                st_b = 0x7f807f80u;  // (+inf, +inf)
+                uint32_t a0 = 0xff80ff80u, a1 = 0xff80ff80u, b0 = 0x7f807f80u, b1 = 0x7f807f80u;  // -inf / +inf
 #pragma unroll
-                for (int i = 0; i < N; i++) {
-                    const uint4 v = lds128(gaddr + (((i + rot) & (N - 1)) << 4));
-                    st_a = hmax2(st_a, hmax2(hmax2(v.x, v.y), hmax2(v.z, v.w)));
-                    st_b = hmin2(st_b, hmin2(hmin2(v.x, v.y), hmin2(v.z, v.w)));
+                for (int i = 0; i < N; i += 2) {
+                    const uint4 v0 = lds128(gaddr + (((i + rot) & (N - 1)) << 4));
+                    const uint4 v1 = lds128(gaddr + (((i + 1 + rot) & (N - 1)) << 4));
+                    a0 = hmax2(a0, hmax2(hmax2(v0.x, v0.y), hmax2(v0.z, v0.w)));
+                    b0 = hmin2(b0, hmin2(hmin2(v0.x, v0.y), hmin2(v0.z, v0.w)));
+                    a1 = hmax2(a1, hmax2(hmax2(v1.x, v1.y), hmax2(v1.z, v1.w)));
+                    b1 = hmin2(b1, hmin2(hmin2(v1.x, v1.y), hmin2(v1.z, v1.w)));
                 }
+                st_a = hmax2(a0, a1);
+                st_b = hmin2(b0, b1);
                 st_a = hmax2(st_a, prmt(st_a, st_a, 0x1032));
                 st_b = hmin2(st_b, prmt(st_b, st_b, 0x1032));
             }
-            // ---- B. qparams (once per group, by the lane that uses them)
+            // ---- B. qparams (once per group, by the lane that uses them; same rounding chain as qmath.cuh)
             float s, z = 0.0f;
+            Bracket br;
             const int64_t gidx = g0 + gl;
             if (QT == QT_FP4) {
+                const float amax = __uint_as_float((st_a << 16) & 0x7fff0000u);
                 float gsv = gs_tile;
-                if (!gs_uniform) gsv = p.gs[gidx / p.groups_per_mat];
-                const uint8_t code = qparams_fp4<DT_BF16>(__uint_as_float((st_a << 16) & 0x7fff0000u), gsv, s);
-                ((uint8_t*)p.scale)[gidx] = code;
+                if (!gs_uniform && act) gsv = p.gs[gidx / p.groups_per_mat];
+                const float loc = div_const_bf16(amax, 6.0f);
+                float sf = fminf(__fmul_rn(gsv, loc), 448.0f);  // >= 0; helpers.py:101-108
+                uint32_t code = cvt_e4m3x2(0.0f, sf) & 0xffu;
+                if (code == 0) code = 0x20;                      // zero scale -> 0.125 (helpers.py:364-366)
+                const uint32_t e = code >> 3, mm = code & 7u;
+                const uint32_t M = e ? (mm | 8u) : mm;
+                const int E = e ? (int)e - 10 : -9;
+                const float t = __shfl_sync(0xffffffffu, tab, (int)M);
+                if (gs_tab_ok) s = __fmul_rn(t, __uint_as_float((uint32_t)(E + 127) << 23));
+                else s = __fdiv_rn(e4m3_decode((uint8_t)code), gsv);
+                if (act) ((uint8_t*)p.scale)[gidx] = (uint8_t)code;
+                br.init(s);
+            } else if (SYM) {
+                s = div_const_bf16(__uint_as_float((st_a << 16) & 0x7fff0000u), QT == QT_INT ? 7.5f : 448.0f);
+                if (s == 0.0f) s = eps_of<DT_BF16>();
+                br.init(s);
             } else {
-                if (SYM) s = scale_sym<DT_BF16>(__uint_as_float((st_a << 16) & 0x7fff0000u), QT == QT_INT ? 7.5f : 448.0f);
-                else qparams_asym<DT_BF16>(__uint_as_float(st_b << 16), __uint_as_float(st_a << 16), -8.0f, 7.0f, s, z);
-                ((uint16_t*)p.scale)[gidx] = (uint16_t)(__float_as_uint(s) >> 16);
-                if (QT == QT_INT && !SYM) {
+                const float mn = fminf(__uint_as_float(st_b << 16), 0.0f), mx = fmaxf(__uint_as_float(st_a << 16), 0.0f);
+                const float d = round_to<DT_BF16>(__fadd_rn(mx, -mn));
+                const float s0 = div_const_bf16(d, 15.0f);  // helpers.py:96
+                br.init(s0);
+                // zp = clamp(T(-8 - T(mn / s0))), helpers.py:97-98 (un-eps'ed scale: 0/0 -> NaN -> 0 after the int8 cast)
+                float t;
+                {
+                    float rl, rh, dummy;
+                    unpack2(br.lo, rl, dummy);
+                    unpack2(br.hi, rh, dummy);
+                    const uint32_t u = cvt_bf16x2(__fmul_rn(mn, rh), __fmul_rn(mn, rl));
+                    if (((u >> 16) == (u & 0xffffu)) && scale_is_safe(__float_as_uint(s0))) t = __uint_as_float(u << 16);
+                    else t = round_to<DT_BF16>(__fdiv_rn(mn, s0));
+                }
+                z = round_to<DT_BF16>(__fadd_rn(-8.0f, -t));
+                z = (z == z) ? rintf(fminf(fmaxf(z, -8.0f), 7.0f)) : 0.0f;
+                s = s0;
+                if (s0 == 0.0f) { s = eps_of<DT_BF16>(); br.init(s); }
+            }
+            if (QT != QT_FP4) {
+                if (act) ((uint16_t*)p.scale)[gidx] = (uint16_t)(__float_as_uint(s) >> 16);
+                if (QT == QT_INT && !SYM && act) {
                     const uint32_t gpr = (uint32_t)p.groups_per_row;  // launcher guarantees < 2^31
                     const uint32_t t = k0 + (uint32_t)gl, dr = t / gpr, k = t - dr * gpr;
                     int64_t b = b0, r = (int64_t)r0 + dr;
@@ -249,8 +301,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) group_tma_kernel(const TmaPara
                 }
             }
             // ---- C. quantize + pack into the staging buffer
-            Bracket br;
-            br.init(s);
             const bool unsafe = (QT == QT_FP4) ? !fp4_scale_is_safe(s) : !scale_is_safe(__float_as_uint(s));
             const bool add_zp = (QT == QT_FP8) ? (p.has_zp != 0) : true;
             const uint32_t z2 = (__float_as_uint(z) >> 16) * 0x10001u;
@@ -315,6 +365,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) group_tma_kernel(const TmaPara
 template <int QT, bool SYM, int LOG2N>
 int launch_tma(const TmaParams& p, cudaStream_t st) {
     constexpr int OUT_BYTES = 512 * ((QT == QT_FP8) ? 8 : 4);
+    constexpr int kWarps = WarpsFor<QT>::value;
     const size_t smem = (size_t)kWarps * (kStages * kTileBytes + OUT_BYTES + 64);
     static bool configured = false;  // benign race: idempotent attribute
     if (!configured) {
@@ -370,7 +421,9 @@ int launch_group_tma(int qt, const GroupParams& gp, int64_t batch, cudaStream_t 
         default: return B200Q_ENOSYS;
         }
     }
-    if (qt == QT_FP4 && g == 16) return launch_tma<QT_FP4, true, 1>(p, st);
+    // NVFP4 (g16): measured slower than the thread-owns-group register kernel (quant_tile_fast.cu: 122 us vs 173 us on
+    // 128 experts) -- the per-group chain dominates at 16 elements per group; opt-in for experiments only.
+    if (qt == QT_FP4 && g == 16 && getenv("B200Q_FP4_TMA") != nullptr) return launch_tma<QT_FP4, true, 1>(p, st);
     return B200Q_ENOSYS;
 }
 
