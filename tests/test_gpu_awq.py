@@ -1,0 +1,101 @@
+"""GPU: AWQ statistics kernels and the scale search against the restated oracle (loss curve within 1e-3 relative,
+same argmin ratio -- BASELINE.json north_star tolerance), plus activation observers."""
+import pytest
+import torch
+
+from oracle import llmc_restated as R
+from oracle import oracle as O
+from tests.test_gpu_compress import Args
+from tests.util import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(T=1024, K=512, N=256, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(T, K, generator=g) * (1 + 3 * torch.rand(K, generator=g))).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.02).to(torch.bfloat16)
+    w[:, 7] *= 20
+    return x, w
+
+
+def test_abs_sum_and_wmean():
+    from quantizers_b200 import awq
+
+    x, w = _problem()
+    want = O.abs_sum_cols(x)
+    got = awq.abs_sum_cols(x.cuda()).double().cpu()
+    assert torch.allclose(got, want, rtol=1e-5)
+    for g in (32, 128):
+        wm = awq.compute_layer_means([w.cuda(), w.flip(0).cuda()], g).cpu()
+        ref = O.w_mean([w, w.flip(0)], g).float()
+        assert torch.equal(wm, ref), g  # fp64 accumulation of bf16 values is exact => order independent
+    # empty activation batch (unrouted expert) is skipped
+    acc = awq.abs_sum_cols(torch.zeros(0, 512, dtype=torch.bfloat16).cuda())
+    assert float(acc.sum()) == 0.0
+
+
+def test_awq_scales_and_scaled_fake_quantize():
+    from quantizers_b200 import awq
+
+    x, w = _problem(seed=2)
+    xm, _ = R.accumulate_abs_mean([x])
+    for name, geom, qtype, nb, sym in (("int4_g32_sym", O.Geom(O.GROUP, 32), O.INT, 4, True),
+                                       ("int4_g128_asym", O.Geom(O.GROUP, 128), O.INT, 4, False),
+                                       ("fp8_g32", O.Geom(O.GROUP, 32), O.FP8, 8, True)):
+        wm = R.compute_layer_means([w], geom.group)
+        ratios = [i / 20 for i in range(20)]
+        got = awq.awq_scales(xm.cuda(), wm.cuda(), ratios, True).cpu()
+        for i, r in enumerate(ratios):
+            ref = R.awq_scales(xm, wm, r, True)
+            assert torch.allclose(got[i], ref, rtol=2e-6, atol=0), (name, r)  # powf vs torch.pow: ulp-level
+        # identical scales in -> bit-identical weights out
+        s = R.awq_scales(xm, wm, 0.35, True)
+        out = awq.scaled_fake_quantize(w.cuda(), s.cuda(), Args(name))
+        assert_bits_equal(out, R.scaled_fake_quantize(w, s, geom, qtype, nb, sym), name)
+
+
+@pytest.mark.parametrize("name,geom,qtype,nb,sym", [("int4_g32_sym", O.Geom(O.GROUP, 32), O.INT, 4, True),
+                                                    ("int4_g128_asym", O.Geom(O.GROUP, 128), O.INT, 4, False)])
+def test_compute_best_scale_linear_parent(name, geom, qtype, nb, sym):
+    from quantizers_b200 import awq
+
+    x, w = _problem(T=768, K=512, N=256, seed=4)
+    s_ref, r_ref, l_ref = R.compute_best_scale([x[:384], x[384:]], [w], R.linear_parent, geom, qtype, nb, sym)
+    s, r, l = awq.compute_best_scale(x.cuda(), [w.cuda()], awq.linear_parent, Args(name), token_chunk=500)
+    rel = [abs(a - b) / b for a, b in zip(l, l_ref)]
+    assert max(rel) < 1e-3, rel          # per-ratio losses within 1e-3 relative
+    assert r == r_ref                     # same argmin ratio (first minimum wins)
+    assert torch.allclose(s, s_ref, rtol=1e-5)
+
+
+def test_compute_best_scale_mlp_parent():
+    from quantizers_b200 import awq
+
+    g = torch.Generator().manual_seed(9)
+    x, gate = _problem(T=512, K=256, N=384, seed=6)
+    up = (torch.randn(384, 256, generator=g) * 0.02).to(torch.bfloat16)
+    down = (torch.randn(256, 384, generator=g) * 0.02).to(torch.bfloat16)
+    geom = O.Geom(O.GROUP, 32)
+    s_ref, r_ref, l_ref = R.compute_best_scale([x], [gate, up], R.mlp_parent(down), geom, O.INT, 4, True)
+    s, r, l = awq.compute_best_scale(x.cuda(), [gate.cuda(), up.cuda()], awq.mlp_parent(down.cuda()), Args("int4_g32_sym"))
+    rel = [abs(a - b) / b for a, b in zip(l, l_ref)]
+    assert max(rel) < 1e-3, rel
+    assert r == r_ref
+
+
+def test_activation_global_scale_running():
+    """static_minmax input_global_scale: running min/max over batches == one pass over the concatenation."""
+    from quantizers_b200 import ops
+
+    x, _ = _problem(seed=8)
+    xd = x.cuda()
+    state = torch.tensor([float("inf"), float("-inf")], device="cuda")
+    for lo, hi in ((0, 100), (100, 100), (100, 1024)):
+        if hi > lo:
+            gs = ops.observe_global_scale(xd[lo:hi], state)
+    want = R.activation_global_scale([x[:100], x[100:]])
+    assert gs.item() == want.item()
+    assert ops.observe_global_scale(xd).item() == want.item()
+    mn, mx = float(x.float().min()), float(x.float().max())
+    assert state[0].item() == mn and state[1].item() == mx
