@@ -121,7 +121,7 @@ template <int DT> HD void qparams_asym(float mn, float mx, float bit_min, float 
     if (z == z) z = fminf(fmaxf(z, bit_min), bit_max);
     z = (z == z) ? frint(z) : 0.0f;  // NaN -> int8 cast gives 0 on the reference's CPU path
     s_out = s == 0.0f ? eps_of<DT>() : s;
-    z_out = z;
+    z_out = fadd(z, 0.0f);  // the zero-point is stored as int8: a rounded -0.0 becomes +0 (matters for fake-quant signs of zero)
 }
 
 // NVFP4 local scale (helpers.py:86,101-126): loc = T(absmax/6); s = e4m3(clamp(gs * loc)); 0 -> 0.125
