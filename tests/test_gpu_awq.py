@@ -99,3 +99,48 @@ def test_activation_global_scale_running():
     assert ops.observe_global_scale(xd).item() == want.item()
     mn, mx = float(x.float().min()), float(x.float().max())
     assert state[0].item() == mn and state[1].item() == mx
+
+
+def _torch_gemm_loss(x, w_ref, w_q):
+    """Plain torch restatement of _run_samples + _compute_loss for a single-Linear parent (bf16 GEMM, fp32 accumulate,
+    bf16 outputs, bf16 difference squared and summed in fp32/fp64)."""
+    ref = torch.nn.functional.linear(x, w_ref)
+    out = []
+    for r in range(w_q.shape[0]):
+        d = ref - torch.nn.functional.linear(x, w_q[r])
+        out.append(d.float().pow(2).double().sum())
+    return torch.stack(out)
+
+
+@pytest.mark.parametrize("T,K,N,R", [(256, 128, 256, 2), (1024, 512, 256, 3), (1000, 520, 300, 2), (4096, 2560, 1024, 4),
+                                     (77, 64, 40, 1), (20000, 256, 512, 2)])
+def test_gemm_loss_fused_vs_torch(T, K, N, R):
+    """tcgen05 fused loss GEMM against torch bf16 matmul on the same device; ragged M/N/K tiles included."""
+    from quantizers_b200 import awq
+
+    g = torch.Generator().manual_seed(T + K + N)
+    x = (torch.randn(T, K, generator=g) * (1 + 3 * torch.rand(K, generator=g))).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) * 0.02).to(torch.bfloat16).cuda()
+    wq = torch.stack([(w.float() + 0.002 * (r + 1) * torch.randn(N, K, generator=g).cuda()).to(torch.bfloat16) for r in range(R)])
+    got = awq.gemm_loss_fused(x, w, wq).double().cpu()
+    want = _torch_gemm_loss(x, w, wq).cpu()
+    rel = ((got - want).abs() / want).max().item()
+    assert rel < 1e-3, (got, want)
+    # identical weights -> exactly zero loss (same accumulation order for both operands)
+    z = awq.gemm_loss_fused(x, w, w[None].contiguous())
+    assert float(z[0]) == 0.0
+
+
+@pytest.mark.parametrize("name,geom,qtype,nb,sym", [("int4_g32_sym", O.Geom(O.GROUP, 32), O.INT, 4, True),
+                                                    ("int4_g128_asym", O.Geom(O.GROUP, 128), O.INT, 4, False)])
+def test_compute_best_scale_fused_linear(name, geom, qtype, nb, sym):
+    """Whole search through the fused tensor-core loss kernel against the restated CPU oracle."""
+    from quantizers_b200 import awq
+
+    x, w = _problem(T=768, K=512, N=256, seed=4)
+    s_ref, r_ref, l_ref = R.compute_best_scale([x[:384], x[384:]], [w], R.linear_parent, geom, qtype, nb, sym)
+    s, r, l = awq.compute_best_scale(x.cuda(), [w.cuda()], awq.linear_parent, Args(name), fused_linear=True)
+    rel = [abs(a - b) / b for a, b in zip(l, l_ref)]
+    assert max(rel) < 1e-3, rel
+    assert r == r_ref
+    assert torch.allclose(s, s_ref, rtol=1e-5)
