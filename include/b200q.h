@@ -159,6 +159,18 @@ int b200q_sq_err_accumulate(const void* y_ref, const void* y_q, int64_t numel, i
 int b200q_awq_gemm_loss(const void* x, int64_t tokens, int64_t k, const void* w_ref, const void* w_q, int64_t n,
                         int32_t n_ratios, float* loss, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t b200q_awq_gemm_loss_workspace(int64_t tokens, int64_t k, int64_t n, int32_t n_ratios);
+/* Same kernel with either operand varying per ratio (multi-layer parents):
+ *   loss[r] += sum ( bf16(A_ref B_ref^T) - bf16(A_r B_r^T) )^2,   A_r = a_q ? a_q[r] : a_ref  (T [n_ratios, tokens, k]),
+ *                                                                 B_r = b_q ? b_q[r] : b_ref  (T [n_ratios, n, k]).
+ * MLP parent: a_q[r] = silu(x Wg'_r^T) * (x Wu'_r^T), b_ref = W_down; attention parent: a_q[r] = attention output, b_ref = W_o. */
+int b200q_awq_gemm_loss_pairs(const void* a_ref, const void* a_q, int64_t tokens, int64_t k, const void* b_ref, const void* b_q,
+                              int64_t n, int32_t n_ratios, float* loss, void* workspace, int64_t workspace_bytes, void* stream);
+/* W2 first stage of a multi-layer parent, all weight variants in one launch (tcgen05, double-buffered TMEM):
+ *   swiglu == 0:  out[v] = bf16(x W[v]^T)                                   W: T [n_variants, n_out, k]      (q/k/v projections)
+ *   swiglu != 0:  out[v] = silu(bf16(x Wg[v]^T)) * bf16(x Wu[v]^T)           W: T [n_variants, 2*n_out, k]    (gate rows, then up rows)
+ * out: T [n_variants, tokens, n_out], rounded exactly where torch's bf16 Linear / silu / mul round.  bf16 only. */
+int b200q_awq_gemm_project(const void* x, int64_t tokens, int64_t k, const void* w, int64_t n_variants, int64_t n_out, int32_t swiglu,
+                           void* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Host-buffer pipeline: what LLMC model_free_ptq's per-tensor job does (load -> device -> observe ->

@@ -185,3 +185,43 @@ def mlp_parent(down: torch.Tensor):
         return torch.nn.functional.linear(torch.nn.functional.silu(g) * u, down)
 
     return f
+
+
+def attention_parent(o_proj: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, q_norm: torch.Tensor, k_norm: torch.Tensor,
+                     rope_theta: float = 1e6, eps: float = 1e-6):
+    """parent of q/k/v: transformers ``Qwen3Attention.forward`` on one calibration sample ``x [S, K]`` (batch 1, causal mask,
+    positions 0..S-1): q/k per-head RMSNorm, rotary embedding, grouped-query softmax attention, o_proj.  Written with
+    elementary ops (explicit softmax) so it does not share code with the product path."""
+
+    def rms(x, w):
+        v = x.float()
+        v = v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps)
+        return w * v.to(x.dtype)
+
+    def f(weights: List[torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+        S = x.shape[0]
+        lin = torch.nn.functional.linear
+        q = lin(x, weights[0]).view(S, n_heads, head_dim)
+        k = lin(x, weights[1]).view(S, n_kv, head_dim)
+        v = lin(x, weights[2]).view(S, n_kv, head_dim)
+        q, k = rms(q, q_norm).transpose(0, 1), rms(k, k_norm).transpose(0, 1)  # [H, S, d]
+        v = v.transpose(0, 1)
+        inv = 1.0 / (rope_theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+        fr = torch.outer(torch.arange(S, dtype=torch.float32), inv)
+        emb = torch.cat((fr, fr), dim=-1)
+        cos, sin = emb.cos().to(x.dtype), emb.sin().to(x.dtype)
+
+        def rot(t):
+            t1, t2 = t[..., : head_dim // 2], t[..., head_dim // 2:]
+            return t * cos + torch.cat((-t2, t1), dim=-1) * sin
+
+        q, k = rot(q), rot(k)
+        rep = n_heads // n_kv
+        k, v = k.repeat_interleave(rep, dim=0), v.repeat_interleave(rep, dim=0)
+        att = (q.float() @ k.float().transpose(-1, -2)) / (head_dim ** 0.5)
+        att = att.masked_fill(torch.ones(S, S, dtype=torch.bool).triu(1), float("-inf"))
+        p = torch.softmax(att, dim=-1).to(x.dtype)
+        o = (p.float() @ v.float()).to(x.dtype).transpose(0, 1).reshape(S, n_heads * head_dim)
+        return lin(o, o_proj)
+
+    return f

@@ -83,45 +83,157 @@ def sq_err_accumulate(y_ref: torch.Tensor, y_q: torch.Tensor, acc: torch.Tensor)
                                             L.ptr(acc), L.stream_ptr(y_ref.device)))
 
 
-def linear_parent(weights: List[torch.Tensor], x: torch.Tensor) -> torch.Tensor:
-    return torch.nn.functional.linear(x, weights[0])
-
-
-def mlp_parent(down: torch.Tensor) -> Callable:
-    def f(weights, x):
-        g = torch.nn.functional.linear(x, weights[0])
-        u = torch.nn.functional.linear(x, weights[1])
-        return torch.nn.functional.linear(torch.nn.functional.silu(g) * u, down)
-
-    return f
+def _ws(lib, T, K, N, R, dev):
+    ws_bytes = int(lib.b200q_awq_gemm_loss_workspace(T, K, N, R))
+    return torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev), ws_bytes
 
 
 @torch.no_grad()
-def gemm_loss_fused(x: torch.Tensor, w_ref: torch.Tensor, w_q: torch.Tensor) -> torch.Tensor:
-    """Single-Linear parent: loss[r] = sum_{t,n} (bf16(x w_ref^T) - bf16(x w_q[r]^T))^2 for all stacked variants
-    ``w_q [R, N, K]`` in one tcgen05 kernel, outputs never materialised.  bf16 only.  Returns fp32 [R] (sums)."""
-    L.require_cuda(x, w_ref, w_q)
-    assert x.dtype == torch.bfloat16 and w_ref.dtype == torch.bfloat16 and w_q.dtype == torch.bfloat16
-    x, w_ref, w_q = x.contiguous(), w_ref.contiguous(), w_q.contiguous()
-    T, K = x.shape
-    R, N, _ = w_q.shape
+def gemm_loss_pairs(a_ref: torch.Tensor, a_q: Optional[torch.Tensor], b_ref: torch.Tensor, b_q: Optional[torch.Tensor]) -> torch.Tensor:
+    """loss[r] = sum_{t,n} (bf16(a_ref b_ref^T) - bf16(A_r B_r^T))^2 with A_r = a_q[r] (or a_ref), B_r = b_q[r] (or b_ref), in one
+    tcgen05 kernel; outputs are never materialised.  bf16 only.  Returns fp32 [R] (sums, not means)."""
+    L.require_cuda(a_ref, a_q, b_ref, b_q)
+    for t in (a_ref, a_q, b_ref, b_q):
+        if t is not None and (t.dtype != torch.bfloat16 or not t.is_contiguous()):
+            raise L.B200QError("gemm_loss_pairs takes contiguous bf16 tensors")
+    if a_q is None and b_q is None:
+        raise L.B200QError("gemm_loss_pairs: neither operand varies")
+    T, K = a_ref.shape
+    N = b_ref.shape[0]
+    R = (a_q if a_q is not None else b_q).shape[0]
+    if (a_q is not None and tuple(a_q.shape) != (R, T, K)) or (b_q is not None and tuple(b_q.shape) != (R, N, K)) or b_ref.shape[1] != K:
+        raise L.B200QError("gemm_loss_pairs: operand shapes do not agree")
     lib = L.lib()
-    ws_bytes = int(lib.b200q_awq_gemm_loss_workspace(T, K, N, R))
-    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
-    loss = torch.zeros(R, dtype=torch.float32, device=x.device)
-    L.check(lib.b200q_awq_gemm_loss(L.ptr(x), T, K, L.ptr(w_ref), L.ptr(w_q), N, R, L.ptr(loss), L.ptr(ws), ws_bytes, L.stream_ptr(x.device)))
+    ws, ws_bytes = _ws(lib, T, K, N, R, a_ref.device)
+    loss = torch.zeros(R, dtype=torch.float32, device=a_ref.device)
+    L.check(lib.b200q_awq_gemm_loss_pairs(L.ptr(a_ref), L.ptr(a_q), T, K, L.ptr(b_ref), L.ptr(b_q), N, R, L.ptr(loss), L.ptr(ws), ws_bytes,
+                                          L.stream_ptr(a_ref.device)))
     return loss
 
 
 @torch.no_grad()
+def gemm_loss_fused(x: torch.Tensor, w_ref: torch.Tensor, w_q: torch.Tensor) -> torch.Tensor:
+    """Single-Linear parent: loss[r] = sum_{t,n} (bf16(x w_ref^T) - bf16(x w_q[r]^T))^2 for all stacked variants ``w_q [R, N, K]``."""
+    return gemm_loss_pairs(x.contiguous(), None, w_ref.contiguous(), w_q.contiguous())
+
+
+@torch.no_grad()
+def gemm_project(x: torch.Tensor, w_all: torch.Tensor, swiglu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """First stage of a multi-layer parent for all weight variants ``w_all [V, rows, K]`` at once (tcgen05):
+    ``out[v] = x w_all[v]^T`` (bf16), or with ``swiglu`` ``silu(x Wg[v]^T) * (x Wu[v]^T)`` where ``w_all[v] = [Wg; Wu]``."""
+    L.require_cuda(x, w_all, out)
+    if x.dtype != torch.bfloat16 or w_all.dtype != torch.bfloat16:
+        raise L.B200QError("gemm_project takes bf16 tensors")
+    x, w_all = x.contiguous(), w_all.contiguous()
+    T, K = x.shape
+    V, rows, _ = w_all.shape
+    n_out = rows // 2 if swiglu else rows
+    if out is None:
+        out = torch.empty((V, T, n_out), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().b200q_awq_gemm_project(L.ptr(x), T, K, L.ptr(w_all), V, n_out, int(bool(swiglu)), L.ptr(out), L.stream_ptr(x.device)))
+    return out
+
+
+# ----------------------------------------------------------------------------- fused parents (W2 + W3 on the tensor cores)
+class LinearParent:
+    """Parent == the single balance Linear (up_proj -> down_proj, v_proj -> o_proj, per-expert w3 -> w2)."""
+
+    def fused_losses(self, x: torch.Tensor, w_all: torch.Tensor) -> Tuple[torch.Tensor, int]:
+        return gemm_loss_pairs(x, None, w_all[0], w_all[1:]), x.shape[0] * w_all.shape[1]
+
+    def __call__(self, weights, x):
+        return torch.nn.functional.linear(x, weights[0])
+
+
+class MLPParent:
+    """Parent == the gated MLP whose gate/up projections are the balance layers (post_attention_layernorm -> gate, up):
+    out = down(silu(gate(x)) * up(x)).  Balance weights are stacked [gate; up]."""
+
+    def __init__(self, down: torch.Tensor):
+        self.down = down.contiguous()
+
+    def fused_losses(self, x, w_all):
+        h = gemm_project(x, w_all, swiglu=True)                      # [1 + R, T, inter]
+        return gemm_loss_pairs(h[0], h[1:], self.down, None), x.shape[0] * self.down.shape[0]
+
+    def __call__(self, weights, x):
+        F = torch.nn.functional
+        return F.linear(F.silu(F.linear(x, weights[0])) * F.linear(x, weights[1]), self.down)
+
+
+def _rms_norm(x, w, eps):
+    v = x.float()
+    v = v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps)
+    return w * v.to(x.dtype)
+
+
+def _rope(x, cos, sin):
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return x * cos + torch.cat((-x2, x1), dim=-1) * sin
+
+
+def attention_core(qkv: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, seq_len: int, q_norm, k_norm, cos, sin, eps=1e-6):
+    """Qwen3 attention between the q/k/v projections and o_proj (transformers Qwen3Attention.forward): per-head RMSNorm
+    on q and k, rotary embedding, causal GQA attention.  ``qkv [T, (H + 2 Hkv) d]`` with T = samples * seq_len."""
+    T = qkv.shape[0]
+    B = T // seq_len
+    q, k, v = qkv.split([n_heads * head_dim, n_kv * head_dim, n_kv * head_dim], dim=-1)
+    q = _rms_norm(q.reshape(B, seq_len, n_heads, head_dim), q_norm, eps).transpose(1, 2)
+    k = _rms_norm(k.reshape(B, seq_len, n_kv, head_dim), k_norm, eps).transpose(1, 2)
+    v = v.reshape(B, seq_len, n_kv, head_dim).transpose(1, 2)
+    q, k = _rope(q, cos, sin), _rope(k, cos, sin)
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=n_heads != n_kv)
+    return o.transpose(1, 2).reshape(T, n_heads * head_dim)
+
+
+class AttentionParent:
+    """Parent == self_attn whose q/k/v projections are the balance layers (input_layernorm -> q, k, v).  Balance weights
+    are stacked [Wq; Wk; Wv].  The projections and the o_proj + loss run on the tcgen05 kernels; the softmax(QK^T)V core
+    between them is torch SDPA (library flash attention), as in the reference's ``_run_samples``."""
+
+    def __init__(self, o_proj: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, seq_len: int, q_norm: torch.Tensor,
+                 k_norm: torch.Tensor, rope_theta: float = 1e6, eps: float = 1e-6):
+        self.o = o_proj.contiguous()
+        self.cfg = (n_heads, n_kv, head_dim, seq_len)
+        self.q_norm, self.k_norm, self.eps = q_norm, k_norm, eps
+        inv = 1.0 / (rope_theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32, device=o_proj.device) / head_dim))
+        fr = torch.outer(torch.arange(seq_len, dtype=torch.float32, device=o_proj.device), inv)
+        emb = torch.cat((fr, fr), dim=-1)
+        self.cos, self.sin = emb.cos().to(o_proj.dtype), emb.sin().to(o_proj.dtype)
+
+    def core(self, qkv):
+        return attention_core(qkv, *self.cfg, self.q_norm, self.k_norm, self.cos, self.sin, self.eps)
+
+    def fused_losses(self, x, w_all):
+        qkv = gemm_project(x, w_all, swiglu=False)                   # [1 + R, T, (H + 2 Hkv) d]
+        attn = torch.empty((qkv.shape[0], x.shape[0], self.o.shape[1]), dtype=x.dtype, device=x.device)
+        for v in range(qkv.shape[0]):
+            attn[v] = self.core(qkv[v])
+        return gemm_loss_pairs(attn[0], attn[1:], self.o, None), x.shape[0] * self.o.shape[0]
+
+    def __call__(self, weights, x):
+        F = torch.nn.functional
+        qkv = torch.cat([F.linear(x, w) for w in weights], dim=-1)
+        return F.linear(self.core(qkv), self.o)
+
+
+linear_parent = LinearParent()
+
+
+def mlp_parent(down: torch.Tensor) -> MLPParent:
+    return MLPParent(down)
+
+
+@torch.no_grad()
 def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent: Callable, args, n_grid: int = 20,
-                       duo_scaling: bool = True, process_group=None, fused_linear: bool = False,
+                       duo_scaling: bool = True, process_group=None, fused: Optional[bool] = None, fused_linear: Optional[bool] = None,
                        token_chunk: int = 8192) -> Tuple[torch.Tensor, float, List[float]]:
     """``AWQModifier._compute_best_scale`` for one mapping.
 
-    x        [T_local, K] inputs of the balance layers (this rank's token shard; rows are independent for Linear / MLP
-             parents, so samples are concatenated)
+    x        [T_local, K] inputs of the balance layers (this rank's token shard; whole samples for an attention parent)
     weights  balance-layer weights [N_i, K];  parent(weights, x_chunk) -> parent-module output
+    parent   a LinearParent / MLPParent / AttentionParent (fused tensor-core evaluation, bf16) or any callable (generic
+             evaluation: the parent runs through torch, the squared error through ``b200q_sq_err_accumulate``)
     Returns (best_scales fp32 [K] on the CPU like the reference, best_ratio, losses[n_grid]).  Raises if no ratio gives
     a finite loss.  With ``process_group`` the |x| sums / token counts and the loss accumulators are all-reduced (SUM),
     so every rank returns the same argmin."""
@@ -131,6 +243,8 @@ def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent:
     K = x.shape[-1]
     x = x.reshape(-1, K)
     dist_on = process_group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+    if fused is None:
+        fused = fused_linear if fused_linear is not None else (hasattr(parent, "fused_losses") and x.dtype == torch.bfloat16)
     # ---- statistics
     xsum = abs_sum_cols(x)
     cnt = torch.tensor([float(x.shape[0])], dtype=torch.float64, device=dev)
@@ -143,12 +257,20 @@ def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent:
     scales = awq_scales(x_mean, w_mean, ratios, duo_scaling)
     # ---- losses
     acc = torch.zeros(n_grid + 1, dtype=torch.float32, device=dev)  # [n_grid] sums + numel
-    if fused_linear and len(weights) == 1:
-        wq = torch.empty((n_grid,) + tuple(weights[0].shape), dtype=weights[0].dtype, device=dev)
-        for i in range(n_grid):
-            scaled_fake_quantize(weights[0], scales[i], args, out=wq[i])
-        acc[:n_grid] = gemm_loss_fused(x, weights[0], wq)
-        acc[n_grid] = float(x.shape[0] * weights[0].shape[0])
+    if fused:
+        if not hasattr(parent, "fused_losses"):
+            raise L.B200QError("fused evaluation needs a LinearParent / MLPParent / AttentionParent")
+        rows = [w.shape[0] for w in weights]
+        w_all = torch.empty((n_grid + 1, sum(rows), K), dtype=weights[0].dtype, device=dev)  # [0] = reference weights
+        off = 0
+        for w, n in zip(weights, rows):
+            w_all[0, off:off + n].copy_(w)
+            for i in range(n_grid):
+                scaled_fake_quantize(w, scales[i], args, out=w_all[1 + i, off:off + n])
+            off += n
+        sums, numel = parent.fused_losses(x.contiguous(), w_all)
+        acc[:n_grid] = sums
+        acc[n_grid] = float(numel)
     else:
         wq = [torch.empty_like(w) for w in weights]
         chunks = [x[t0:t0 + token_chunk] for t0 in range(0, x.shape[0], token_chunk)]
