@@ -172,6 +172,12 @@ int b200q_awq_gemm_loss_pairs(const void* a_ref, const void* a_q, int64_t tokens
 int b200q_awq_gemm_project(const void* x, int64_t tokens, int64_t k, const void* w, int64_t n_variants, int64_t n_out, int32_t swiglu,
                            void* out, void* stream);
 
+/* W2, attention parent (input_layernorm -> q/k/v mapping; transformers Qwen3Attention.forward between the projections and
+ * SDPA): in-place per-head RMSNorm (weights T [head_dim]) + rotary embedding of the q and k columns of
+ * qkv T [tokens, (n_heads + 2 n_kv) * head_dim]; position = token index % seq_len; cos/sin T [seq_len, head_dim].  bf16 only. */
+int b200q_qk_norm_rope(void* qkv, int64_t tokens, int32_t n_heads, int32_t n_kv, int32_t head_dim, int32_t seq_len,
+                       const void* q_norm_weight, const void* k_norm_weight, const void* cos, const void* sin, float eps, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Host-buffer pipeline: what LLMC model_free_ptq's per-tensor job does (load -> device -> observe ->
  * compress -> host), /root/reference/scripts/quant_GLM-4.7-Flash-FP8.py:11-24.  Pinned staging buffers and two

@@ -161,27 +161,21 @@ class MLPParent:
         return F.linear(F.silu(F.linear(x, weights[0])) * F.linear(x, weights[1]), self.down)
 
 
-def _rms_norm(x, w, eps):
-    v = x.float()
-    v = v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps)
-    return w * v.to(x.dtype)
-
-
-def _rope(x, cos, sin):
-    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
-    return x * cos + torch.cat((-x2, x1), dim=-1) * sin
-
-
 def attention_core(qkv: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, seq_len: int, q_norm, k_norm, cos, sin, eps=1e-6):
     """Qwen3 attention between the q/k/v projections and o_proj (transformers Qwen3Attention.forward): per-head RMSNorm
-    on q and k, rotary embedding, causal GQA attention.  ``qkv [T, (H + 2 Hkv) d]`` with T = samples * seq_len."""
+    on q and k, rotary embedding, causal GQA attention.  ``qkv [T, (H + 2 Hkv) d]`` with T = samples * seq_len is
+    normalised / rotated IN PLACE by one CUDA kernel (``b200q_qk_norm_rope``); softmax(QK^T)V is torch SDPA on strided views."""
+    L.require_cuda(qkv)
     T = qkv.shape[0]
     B = T // seq_len
+    if qkv.dtype != torch.bfloat16 or not qkv.is_contiguous() or B * seq_len != T:
+        raise L.B200QError("attention_core takes a contiguous bf16 [samples * seq_len, (H + 2 Hkv) d] tensor")
+    L.check(L.lib().b200q_qk_norm_rope(L.ptr(qkv), T, n_heads, n_kv, head_dim, seq_len, L.ptr(q_norm), L.ptr(k_norm), L.ptr(cos), L.ptr(sin),
+                                       ctypes.c_float(eps), L.stream_ptr(qkv.device)))
     q, k, v = qkv.split([n_heads * head_dim, n_kv * head_dim, n_kv * head_dim], dim=-1)
-    q = _rms_norm(q.reshape(B, seq_len, n_heads, head_dim), q_norm, eps).transpose(1, 2)
-    k = _rms_norm(k.reshape(B, seq_len, n_kv, head_dim), k_norm, eps).transpose(1, 2)
-    v = v.reshape(B, seq_len, n_kv, head_dim).transpose(1, 2)
-    q, k = _rope(q, cos, sin), _rope(k, cos, sin)
+    q = q.unflatten(-1, (n_heads, head_dim)).unflatten(0, (B, seq_len)).transpose(1, 2)
+    k = k.unflatten(-1, (n_kv, head_dim)).unflatten(0, (B, seq_len)).transpose(1, 2)
+    v = v.unflatten(-1, (n_kv, head_dim)).unflatten(0, (B, seq_len)).transpose(1, 2)
     o = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=n_heads != n_kv)
     return o.transpose(1, 2).reshape(T, n_heads * head_dim)
 
@@ -195,11 +189,11 @@ class AttentionParent:
                  k_norm: torch.Tensor, rope_theta: float = 1e6, eps: float = 1e-6):
         self.o = o_proj.contiguous()
         self.cfg = (n_heads, n_kv, head_dim, seq_len)
-        self.q_norm, self.k_norm, self.eps = q_norm, k_norm, eps
+        self.q_norm, self.k_norm, self.eps = q_norm.contiguous(), k_norm.contiguous(), eps
         inv = 1.0 / (rope_theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32, device=o_proj.device) / head_dim))
         fr = torch.outer(torch.arange(seq_len, dtype=torch.float32, device=o_proj.device), inv)
         emb = torch.cat((fr, fr), dim=-1)
-        self.cos, self.sin = emb.cos().to(o_proj.dtype), emb.sin().to(o_proj.dtype)
+        self.cos, self.sin = emb.cos().to(o_proj.dtype).contiguous(), emb.sin().to(o_proj.dtype).contiguous()
 
     def core(self, qkv):
         return attention_core(qkv, *self.cfg, self.q_norm, self.k_norm, self.cos, self.sin, self.eps)
@@ -213,7 +207,7 @@ class AttentionParent:
 
     def __call__(self, weights, x):
         F = torch.nn.functional
-        qkv = torch.cat([F.linear(x, w) for w in weights], dim=-1)
+        qkv = torch.cat([F.linear(x, w) for w in weights], dim=-1).contiguous()
         return F.linear(self.core(qkv), self.o)
 
 
@@ -306,3 +300,49 @@ def smooth(weights: Sequence[torch.Tensor], smooth_weight: torch.Tensor, scales:
     else:
         k = s.numel()
         smooth_weight[-k:].copy_((smooth_weight[-k:].float() / s.to(smooth_weight.device).view(-1, 1)).to(smooth_weight.dtype))
+
+
+# ----------------------------------------------------------------------------- one dense decoder layer (config 1)
+def decoder_layer_flops(T: int, hidden: int, inter: int, n_heads: int, n_kv: int, head_dim: int, seq_len: int, n_grid: int = 20) -> float:
+    """ALGORITHMIC FLOPs of the AWQ search of one dense decoder layer: (n_grid + 1) parent evaluations of
+    the q/k/v mapping (q,k,v,o projections + dense attention), the gate/up mapping (gate, up, down) and the down mapping."""
+    qkv = 2.0 * T * hidden * (n_heads + 2 * n_kv) * head_dim
+    o = 2.0 * T * n_heads * head_dim * hidden
+    attn = 4.0 * seq_len * seq_len * head_dim * n_heads * (T // seq_len)
+    mlp = 3 * 2.0 * T * hidden * inter
+    down = 2.0 * T * hidden * inter
+    return (n_grid + 1) * (qkv + o + attn + mlp + down)
+
+
+@torch.no_grad()
+def search_decoder_layer(weights: dict, acts: dict, args, n_heads: int, n_kv: int, head_dim: int, seq_len: int, n_grid: int = 20,
+                         duo_scaling: bool = True, apply: bool = True, process_group=None) -> dict:
+    """AWQ scale search of one dense decoder layer with llmcompressor's default Llama/Qwen mappings
+    (LLMC modifiers/awq/mappings.py; REF:configs/recipes/recipe_awq_w4a16.yaml uses the defaults):
+
+        input_layernorm          -> q_proj, k_proj, v_proj     parent self_attn
+        v_proj                   -> o_proj                     skipped under GQA (v rows != o cols), as upstream does
+        post_attention_layernorm -> gate_proj, up_proj         parent mlp
+        up_proj                  -> down_proj                  parent down_proj
+
+    weights: q,k,v,o,gate,up,down [N,K] + input_layernorm, post_attention_layernorm, q_norm, k_norm (1-D)
+    acts:    "attn_in" [T, hidden], "mlp_in" [T, hidden], "down_in" [T, inter]   (inputs of the balance layers)
+    With ``apply`` the best scales are folded in like ``_smooth`` (balance W *= s, smooth layer /= s) before the next mapping.
+    Returns {mapping: (best_scales cpu, best_ratio, losses)}."""
+    out = {}
+    w = weights
+    attn = AttentionParent(w["o"], n_heads, n_kv, head_dim, seq_len, w["q_norm"], w["k_norm"])
+    out["qkv"] = compute_best_scale(acts["attn_in"], [w["q"], w["k"], w["v"]], attn, args, n_grid, duo_scaling, process_group)
+    if apply:
+        smooth([w["q"], w["k"], w["v"]], w["input_layernorm"], out["qkv"][0])
+    if w["v"].shape[0] == w["o"].shape[1]:
+        out["v_o"] = compute_best_scale(acts["o_in"], [w["o"]], linear_parent, args, n_grid, duo_scaling, process_group)
+        if apply:
+            smooth([w["o"]], w["v"], out["v_o"][0])
+    out["gate_up"] = compute_best_scale(acts["mlp_in"], [w["gate"], w["up"]], MLPParent(w["down"]), args, n_grid, duo_scaling, process_group)
+    if apply:
+        smooth([w["gate"], w["up"]], w["post_attention_layernorm"], out["gate_up"][0])
+    out["down"] = compute_best_scale(acts["down_in"], [w["down"]], linear_parent, args, n_grid, duo_scaling, process_group)
+    if apply:
+        smooth([w["down"]], w["up"], out["down"][0])
+    return out

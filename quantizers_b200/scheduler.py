@@ -149,6 +149,31 @@ def build_arena(spec: ModelSpec, units: Sequence[int], device, dtype=torch.bfloa
     return arena
 
 
+def synth_awq_layer(layer_idx: int, tokens: int, device, hidden: int = 2560, inter: int = 9728, n_heads: int = 32, n_kv: int = 8,
+                    head_dim: int = 128, dtype=torch.bfloat16):
+    """One Qwen3-4B-shaped decoder layer + the balance-layer inputs of its AWQ mappings: weights
+    randn*0.02 (seed 1234 + layer*1000 + matrix), activations randn * (1 + 3 rand(K)) (seed 4321 + layer) so that the
+    per-channel means x_mean spread; down_proj's input is the layer's own silu(gate x) * up x."""
+    shapes = {"q": (n_heads * head_dim, hidden), "k": (n_kv * head_dim, hidden), "v": (n_kv * head_dim, hidden),
+              "o": (hidden, n_heads * head_dim), "gate": (inter, hidden), "up": (inter, hidden), "down": (hidden, inter)}
+    w = {}
+    for mi, (name, (r, c)) in enumerate(shapes.items()):
+        w[name] = synth_stack([layer_idx], r, c, mi, device, dtype)[0]
+    g = torch.Generator(device=device).manual_seed(4321 + layer_idx)
+    for name, n in (("input_layernorm", hidden), ("post_attention_layernorm", hidden), ("q_norm", head_dim), ("k_norm", head_dim)):
+        w[name] = (1 + 0.1 * torch.randn(n, generator=g, device=device)).to(dtype)
+    acts = {}
+    for name in ("attn_in", "mlp_in"):
+        spread = 1 + 3 * torch.rand(hidden, generator=g, device=device)
+        acts[name] = (torch.randn(tokens, hidden, generator=g, device=device) * spread).to(dtype)
+    F = torch.nn.functional
+    acts["down_in"] = torch.empty(tokens, inter, dtype=dtype, device=device)
+    for t0 in range(0, tokens, 8192):
+        xc = acts["mlp_in"][t0:t0 + 8192]
+        acts["down_in"][t0:t0 + 8192] = F.silu(F.linear(xc, w["gate"])) * F.linear(xc, w["up"])
+    return w, acts
+
+
 # ----------------------------------------------------------------------------- RTN quantize + pack of a shard
 def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Optional[list] = None) -> Dict[str, dict]:
     """Fused observe -> qparams -> quantize -> pack for every stacked weight class of this rank's shard.

@@ -224,3 +224,41 @@ def test_compute_best_scale_fused_attention_parent():
         rel = [abs(a - b) / b for a, b in zip(res[fused][2], l_ref)]
         assert max(rel) < 5e-3, (fused, rel)
         assert res[fused][1] == r_ref
+
+
+@pytest.mark.parametrize("H,HKV,D,S,B", [(4, 2, 64, 64, 3), (32, 8, 128, 512, 2)])
+def test_qk_norm_rope_vs_eager(H, HKV, D, S, B):
+    """In-place q/k RMSNorm + RoPE kernel against the eager bf16 op chain of transformers' Qwen3Attention."""
+    from quantizers_b200 import awq
+
+    g = torch.Generator().manual_seed(5)
+    T = B * S
+    qkv = torch.randn(T, (H + 2 * HKV) * D, generator=g).to(torch.bfloat16).cuda()
+    qn = (1 + 0.1 * torch.randn(D, generator=g)).to(torch.bfloat16).cuda()
+    kn = (1 + 0.1 * torch.randn(D, generator=g)).to(torch.bfloat16).cuda()
+    par = awq.AttentionParent(torch.zeros(8, H * D, dtype=torch.bfloat16).cuda(), H, HKV, D, S, qn, kn)
+
+    def rms(x, w):
+        v = x.float()
+        v = v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + 1e-6)
+        return w * v.to(x.dtype)
+
+    def rope(x):  # x [B, S, h, D]
+        cos, sin = par.cos[None, :, None, :], par.sin[None, :, None, :]
+        x1, x2 = x[..., : D // 2], x[..., D // 2:]
+        return x * cos + torch.cat((-x2, x1), dim=-1) * sin
+
+    q, k, v = qkv.split([H * D, HKV * D, HKV * D], dim=-1)
+    q_ref = rope(rms(q.reshape(B, S, H, D), qn)).reshape(T, H * D)
+    k_ref = rope(rms(k.reshape(B, S, HKV, D), kn)).reshape(T, HKV * D)
+    want = torch.cat([q_ref, k_ref, v], dim=-1)
+    got = qkv.clone()
+    from quantizers_b200 import _lib as L
+    import ctypes
+    L.check(L.lib().b200q_qk_norm_rope(L.ptr(got), T, H, HKV, D, S, L.ptr(qn), L.ptr(kn), L.ptr(par.cos), L.ptr(par.sin), ctypes.c_float(1e-6),
+                                       L.stream_ptr(got.device)))
+    assert torch.equal(got[:, (H + HKV) * D:], v)  # v columns untouched
+    diff = (got.float() - want.float()).abs()
+    # the only freedom is the summation order of mean(x^2): at most one bf16 ulp, on a small fraction of the elements
+    assert bool((diff <= want.float().abs() * 2 ** -7 + 1e-6).all()), float(diff.max())
+    assert float((diff > 0).float().mean()) < 0.02
