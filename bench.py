@@ -161,7 +161,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16->int4/fp8", "data": "synthetic",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "qwen3-4b mixed FP8_BLOCK(attn)+INT4 g128 asym(MLP) RTN quantize+pack", "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -222,16 +222,103 @@ def run_e2e(spec, arena, steps, warmup, device_index):
     return h2d * steps / dt / 1e9, h2d, d2h, dt
 
 
+# ----------------------------------------------------------------------------- AWQ search leg (BASELINE.json metric part 2)
+def awq_cpu_sample(tokens: int = 512):
+    """The restated reference search (oracle/llmc_restated.py on the pinned compressed-tensors arithmetic, torch CPU GEMMs) for
+    the up_proj -> down_proj mapping of one Qwen3-4B layer on ``tokens`` calibration tokens; returns seconds."""
+    from oracle import llmc_restated as R
+    from oracle import oracle as O
+
+    g = torch.Generator().manual_seed(4321)
+    x = (torch.randn(tokens, 9728, generator=g) * (1 + 3 * torch.rand(9728, generator=g))).to(torch.bfloat16)
+    w = (torch.randn(2560, 9728, generator=g) * 0.02).to(torch.bfloat16)
+    t0 = time.perf_counter()
+    R.compute_best_scale([x], [w], R.linear_parent, O.Geom(O.GROUP, 128), O.INT, 4, False)
+    return time.perf_counter() - t0
+
+
+def run_awq(args, dev, world, rank, peaks):
+    """AWQ scale search (n_grid 20, duo_scaling, W4A16 g128 asym) of whole Qwen3-4B decoder layers, config 1 shapes:
+    T = 64 x 512 tokens, mappings q/k/v (attention parent), gate/up (MLP parent), down (Linear parent).  Each rank searches
+    its own layers (layer-sharded, weak scaling).  Device-timed with CUDA events; e2e adds the H2D copy of the layer's
+    weights + calibration activations from pinned host memory and the D2H read of the best scales."""
+    import torch.distributed as dist
+
+    from quantizers_b200 import awq
+    from quantizers_b200 import scheduler as S
+
+    T = args.awq_tokens
+    cfg = dict(n_heads=32, n_kv=8, head_dim=128, seq_len=512)
+    qargs = S.PRESETS["W4A16_ASYM"]
+    w, acts = S.synth_awq_layer(rank, T, dev)
+    flops = awq.decoder_layer_flops(T, 2560, 9728, 32, 8, 128, 512)
+
+    def layer(ww, aa):
+        return awq.search_decoder_layer({k: v.clone() for k, v in ww.items()}, aa, qargs, **cfg)
+
+    layer(w, acts)  # warm-up (allocator, SDPA planning)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.awq_layers):
+        res = layer(w, acts)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    # e2e: pinned host -> device every layer, best scales back on the host (compute_best_scale returns CPU tensors)
+    hw = {k: v.cpu().pin_memory() for k, v in w.items()}
+    ha = {k: v.cpu().pin_memory() for k, v in acts.items()}
+    h2d = sum(v.numel() * v.element_size() for v in list(hw.values()) + list(ha.values()))
+    d2h = sum(v[0].numel() * 4 for v in res.values())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.awq_layers, 2))
+    for _ in range(n_e2e):
+        dw = {k: v.to(dev, non_blocking=True) for k, v in hw.items()}
+        da = {k: v.to(dev, non_blocking=True) for k, v in ha.items()}
+        awq.search_decoder_layer(dw, da, qargs, **cfg)
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    ms_layer = float(ms.item()) / args.awq_layers
+    tf = flops / (ms_layer * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1500.0)))
+    out = {"metric": "awq_search_layers_per_s", "value": world * 1e3 / ms_layer, "unit": "layers/s", "ms_per_layer": ms_layer,
+           "layers_timed_per_gpu": args.awq_layers,
+           "config": {"workload": "qwen3-4b decoder layer AWQ W4A16 g128 asym search, n_grid 20, duo_scaling, mappings qkv/gate_up/down",
+                      "tokens": T, "seq_len": 512, "flops_per_layer": flops, "best_ratios": {k: v[1] for k, v in res.items()}},
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a long step)" if peaks else "fallback",
+                        "frac_of_burst": tf / float(peaks.get("bf16_tflops", 1667.5)) if peaks else None,
+                        "kernels": "awq_gemm_project_kernel / awq_gemm_loss_kernel (tcgen05, TMEM)"},
+           "e2e": {"value": world * 1e3 / float(e2e_ms.item()), "unit": "layers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        sec = awq_cpu_sample(512)
+        # one mapping of three, 512 of T tokens: the GEMM + loss part scales with tokens and is 1.63/8.5 of a layer's FLOPs
+        est = sec * (T / 512) * (8.5 / 1.63)
+        out["cpu_baseline"] = {"value": 1.0 / est, "unit": "layers/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"restated search of the down_proj mapping on 512 tokens took {sec:.1f} s; scaled by tokens ({T}/512) "
+                                         "and by the mapping's share of a layer's FLOPs (1.63/8.5)"}
+    return out
+
+
 # ----------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--layers", type=int, default=36, help="decoder layers per rank (36 = full Qwen3-4B)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--awq-layers", type=int, default=3, help="decoder layers of the AWQ search leg per rank (0 disables it)")
+    ap.add_argument("--awq-tokens", type=int, default=64 * 512, help="calibration tokens per layer (64 samples x 512)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -314,10 +401,14 @@ def main():
                                   "share_of_step": v["ms"] / sum(x["ms"] for x in per.values())} for k, v in per.items()}}
     traffic_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(traffic_file):
-        try:
-            roofline["traffic"] = json.load(open(traffic_file)).get(dom)
+        try:  # ncu --set full: (dram__bytes_read.sum + dram__bytes_write.sum) / elements of the captured launch, scaled to this launch
+            t = json.load(open(traffic_file)).get(dom)
+            if t:
+                roofline["traffic"] = t["dram_bytes_per_element"] * per[dom]["elems"] / per[dom]["n"]
+                roofline["traffic_source"] = t["source"]
         except Exception:
             pass
+    roofline["alg_bytes_per_launch"] = alg_bytes / per[dom]["n"]
     del out
 
     # ---- e2e through the host pipeline (same metric, host buffers, copies in the timed region)
@@ -328,10 +419,13 @@ def main():
         e2e_v = float(ev.item()) * world
     barrier()
 
+    awq_line = run_awq(args, dev, world, rank, peaks) if args.awq_layers > 0 else None
+    barrier()
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16->int4/fp8", "data": "synthetic",
+        "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "qwen3-4b mixed FP8_BLOCK(attn)+INT4 g128 asym(MLP) RTN quantize+pack",
                    "layers_per_gpu": spec.units, "matrices_per_step": 7 * spec.units, "bytes_per_step_per_gpu": step_bytes,
                    "l2": "inputs (7.27 GB/step) far larger than the 126 MB L2; no flush needed", "parallelism": f"layer-sharded x{world}"},
@@ -340,6 +434,8 @@ def main():
         "gpu_launches": S.launches_per_step(spec) * args.steps,
         "clocks": sampler.summary() if rank == 0 else None,
     }
+    if awq_line is not None:
+        line["awq"] = awq_line
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             kind = cpu_kind()

@@ -218,6 +218,37 @@ def mlp_parent(down: torch.Tensor) -> MLPParent:
     return MLPParent(down)
 
 
+def reduce_token_stats(xsum: torch.Tensor, count: torch.Tensor, group=None) -> torch.Tensor:
+    """x_mean of token-sharded calibration: all-reduce(SUM) the per-channel |x| sums and the token count, then divide
+    (``_accumulate_mean`` keeps exactly this running sum / count pair).  Works on any device / backend (NCCL, gloo)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(xsum, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+    return xsum / count.to(xsum.dtype)
+
+
+def reduce_and_select(acc: torch.Tensor, group=None, distributed: bool = True) -> Tuple[int, List[float]]:
+    """Finish ``_compute_best_scale``: ``acc = [sum_sq_err(ratio_0..n-1), numel]`` (fp32, this rank's token shard) is
+    all-reduced (SUM) so every rank sees the same totals, the losses are sums / numel, and the FIRST minimum wins
+    (upstream scans ``if loss < best_error``).  Raises when no ratio has a finite loss."""
+    import torch.distributed as dist
+
+    if distributed and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    host = acc.double().cpu()
+    n_grid = host.numel() - 1
+    losses = (host[:n_grid] / host[n_grid]).tolist()
+    best_err, best_i = float("inf"), -1
+    for i, v in enumerate(losses):
+        if v < best_err:
+            best_err, best_i = v, i
+    if best_i < 0:
+        raise RuntimeError("AWQ: no finite loss for any ratio")
+    return best_i, losses
+
+
 @torch.no_grad()
 def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent: Callable, args, n_grid: int = 20,
                        duo_scaling: bool = True, process_group=None, fused: Optional[bool] = None, fused_linear: Optional[bool] = None,
@@ -242,10 +273,7 @@ def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent:
     # ---- statistics
     xsum = abs_sum_cols(x)
     cnt = torch.tensor([float(x.shape[0])], dtype=torch.float64, device=dev)
-    if dist_on:
-        dist.all_reduce(xsum, op=dist.ReduceOp.SUM, group=process_group)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=process_group)
-    x_mean = xsum / cnt.float()
+    x_mean = reduce_token_stats(xsum, cnt, process_group) if dist_on else xsum / cnt.float()
     w_mean = compute_layer_means(weights, args.group_size) if duo_scaling else None
     ratios = [i / n_grid for i in range(n_grid)]
     scales = awq_scales(x_mean, w_mean, ratios, duo_scaling)
@@ -276,16 +304,7 @@ def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent:
             for xc, ref in zip(chunks, refs):
                 sq_err_accumulate(ref, parent(wq, xc), acc[i:i + 1])
         acc[n_grid] = float(numel)
-    if dist_on:
-        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=process_group)
-    host = acc.double().cpu()
-    losses = (host[:n_grid] / host[n_grid]).tolist()
-    best_err, best_i = float("inf"), -1
-    for i, v in enumerate(losses):  # first minimum wins (loss < best_error scan)
-        if v < best_err:
-            best_err, best_i = v, i
-    if best_i < 0:
-        raise RuntimeError("AWQ: no finite loss for any ratio")
+    best_i, losses = reduce_and_select(acc, process_group if dist_on else None, dist_on)
     return scales[best_i].cpu(), ratios[best_i], losses
 
 

@@ -1,0 +1,139 @@
+"""CPU, world_size 2, gloo: the host-side logic of the N > 1 path -- unit partitioning, the statistics exchange
+(MIN / MAX / SUM all-reduce) and the token-sharded AWQ search finishing with the same argmin on every rank.
+The per-rank arithmetic is the CPU oracle here (the CUDA kernels need a GPU); what is under test is the partition /
+reduction / selection code in quantizers_b200.scheduler and quantizers_b200.awq that runs unchanged over NCCL."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run(fn, world=2):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_entry, args=(fn, r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for r in out:
+        if isinstance(r, tuple) and r and r[0] == "error":
+            raise AssertionError(r[1])
+    return sorted(out, key=lambda t: t[0])
+
+
+def _entry(fn, rank, world, port, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        q.put((rank, fn(rank, world)))
+        dist.destroy_process_group()
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        q.put(("error", f"rank {rank}: {e}\n{traceback.format_exc()}"))
+
+
+# ------------------------------------------------------------------------------------------------ partitioning
+def test_partition_covers_all_units_once():
+    from quantizers_b200.scheduler import owner_of, partition
+
+    for n in (1, 7, 36, 128, 18432):
+        for w in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(w):
+                rg = partition(n, w, r)
+                seen.extend(rg)
+                for u in rg:
+                    assert owner_of(u, n, w) == r
+            assert seen == list(range(n))
+            sizes = [len(partition(n, w, r)) for r in range(w)]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        partition(4, 2, 2)
+
+
+def _stats_worker(rank, world):
+    from quantizers_b200.scheduler import allreduce_stats
+
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(64, 32, generator=g)
+    mins, maxs, sums = x.amin(0), x.amax(0), x.abs().sum(0)
+    allreduce_stats(mins, maxs, sums)
+    return mins.tolist(), maxs.tolist(), sums.tolist()  # plain lists: tensors in an mp.Queue need the sender alive
+
+
+def test_allreduce_stats_matches_unsharded():
+    res = _run(_stats_worker)
+    xs = [torch.randn(64, 32, generator=torch.Generator().manual_seed(100 + r)) for r in range(2)]
+    full = torch.cat(xs)
+    for _, (mins, maxs, sums) in res:
+        assert mins == full.amin(0).tolist() and maxs == full.amax(0).tolist()  # MIN/MAX: bit-identical for any world size
+        assert torch.allclose(torch.tensor(sums), full.abs().sum(0), rtol=1e-6)
+
+
+def _problem():
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(512, 256, generator=g) * (1 + 3 * torch.rand(256, generator=g))).to(torch.bfloat16)
+    w = (torch.randn(128, 256, generator=g) * 0.02).to(torch.bfloat16)
+    w[:, 7] *= 20
+    return x, w
+
+
+def _awq_worker(rank, world):
+    """Token-sharded search: each rank owns half of the calibration tokens."""
+    from oracle import llmc_restated as R
+    from oracle import oracle as O
+    from quantizers_b200 import awq
+
+    x, w = _problem()
+    xs = x[rank * 256:(rank + 1) * 256]
+    geom = O.Geom(O.GROUP, 32)
+    xsum = xs.abs().float().sum(0)
+    cnt = torch.tensor([float(xs.shape[0])], dtype=torch.float64)
+    x_mean = awq.reduce_token_stats(xsum, cnt)
+    w_mean = R.compute_layer_means([w], 32)
+    n_grid = 20
+    acc = torch.zeros(n_grid + 1)
+    ref = R.linear_parent([w], xs)
+    for i in range(n_grid):
+        s = R.awq_scales(x_mean, w_mean, i / n_grid, True)
+        wq = R.scaled_fake_quantize(w, s, geom, O.INT, 4, True)
+        acc[i] = (ref - R.linear_parent([wq], xs)).float().pow(2).sum()
+    acc[n_grid] = ref.numel()
+    best_i, losses = awq.reduce_and_select(acc)
+    return best_i, losses, x_mean.tolist()
+
+
+def test_token_sharded_awq_search_agrees_with_unsharded():
+    from oracle import llmc_restated as R
+    from oracle import oracle as O
+
+    res = _run(_awq_worker)
+    x, w = _problem()
+    _, r_ref, l_ref = R.compute_best_scale([x], [w], R.linear_parent, O.Geom(O.GROUP, 32), O.INT, 4, True)
+    (_, (b0, l0, m0)), (_, (b1, l1, m1)) = res
+    assert b0 == b1 and l0 == l1 and m0 == m1      # every rank ends with identical totals and argmin
+    assert b0 / 20 == r_ref
+    assert max(abs(a - b) / b for a, b in zip(l0, l_ref)) < 1e-3
+
+
+def test_reduce_and_select_first_minimum_and_failure():
+    from quantizers_b200 import awq
+
+    acc = torch.tensor([3.0, 1.0, 1.0, 2.0, 10.0])
+    i, losses = awq.reduce_and_select(acc, distributed=False)
+    assert i == 1 and losses == [0.3, 0.1, 0.1, 0.2]
+    with pytest.raises(RuntimeError):
+        awq.reduce_and_select(torch.tensor([float("nan"), float("inf"), 4.0]), distributed=False)
