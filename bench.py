@@ -256,16 +256,21 @@ def run_awq(args, dev, world, rank, peaks):
     def layer(ww, aa):
         return awq.search_decoder_layer({k: v.clone() for k, v in ww.items()}, aa, qargs, **cfg)
 
-    layer(w, acts)  # warm-up (allocator, SDPA planning)
+    for _ in range(2):  # warm-up: workspace growth, SDPA planning, kernel attributes
+        layer(w, acts)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.awq_layers + 1)]
     e0.record()
-    for _ in range(args.awq_layers):
+    marks[0].record()
+    for i in range(args.awq_layers):
         res = layer(w, acts)
+        marks[i + 1].record()
     e1.record()
     torch.cuda.synchronize()
+    log("awq per-layer ms:", [round(marks[i].elapsed_time(marks[i + 1]), 1) for i in range(args.awq_layers)])
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     # e2e: pinned host -> device every layer, best scales back on the host (compute_best_scale returns CPU tensors)
     hw = {k: v.cpu().pin_memory() for k, v in w.items()}

@@ -83,6 +83,31 @@ def sq_err_accumulate(y_ref: torch.Tensor, y_q: torch.Tensor, acc: torch.Tensor)
                                             L.ptr(acc), L.stream_ptr(y_ref.device)))
 
 
+class Workspace:
+    """Persistent HBM scratch for the search (weight variants, projected activations): one flat buffer per role that only
+    grows, so a layer-by-layer run re-uses the same 10-30 GB instead of cycling it through the caching allocator.
+    One process drives one GPU and the search is sequential, so a single pool per device is enough."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def get(self, role: str, shape, dtype, device) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        key = (role, dtype, str(device))
+        buf = self._buf.get(key)
+        if buf is None or buf.numel() < n:
+            self._buf[key] = buf = torch.empty(n, dtype=dtype, device=device)
+        return buf[:n].view(*shape)
+
+    def release(self):
+        self._buf.clear()
+
+
+workspace = Workspace()
+
+
 def _ws(lib, T, K, N, R, dev):
     ws_bytes = int(lib.b200q_awq_gemm_loss_workspace(T, K, N, R))
     return torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev), ws_bytes
@@ -153,7 +178,7 @@ class MLPParent:
         self.down = down.contiguous()
 
     def fused_losses(self, x, w_all):
-        h = gemm_project(x, w_all, swiglu=True)                      # [1 + R, T, inter]
+        h = gemm_project(x, w_all, swiglu=True, out=workspace.get("proj", (w_all.shape[0], x.shape[0], w_all.shape[1] // 2), x.dtype, x.device))
         return gemm_loss_pairs(h[0], h[1:], self.down, None), x.shape[0] * self.down.shape[0]
 
     def __call__(self, weights, x):
@@ -199,8 +224,8 @@ class AttentionParent:
         return attention_core(qkv, *self.cfg, self.q_norm, self.k_norm, self.cos, self.sin, self.eps)
 
     def fused_losses(self, x, w_all):
-        qkv = gemm_project(x, w_all, swiglu=False)                   # [1 + R, T, (H + 2 Hkv) d]
-        attn = torch.empty((qkv.shape[0], x.shape[0], self.o.shape[1]), dtype=x.dtype, device=x.device)
+        qkv = gemm_project(x, w_all, swiglu=False, out=workspace.get("proj", (w_all.shape[0], x.shape[0], w_all.shape[1]), x.dtype, x.device))
+        attn = workspace.get("attn", (qkv.shape[0], x.shape[0], self.o.shape[1]), x.dtype, x.device)
         for v in range(qkv.shape[0]):
             attn[v] = self.core(qkv[v])
         return gemm_loss_pairs(attn[0], attn[1:], self.o, None), x.shape[0] * self.o.shape[0]
@@ -283,7 +308,7 @@ def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent:
         if not hasattr(parent, "fused_losses"):
             raise L.B200QError("fused evaluation needs a LinearParent / MLPParent / AttentionParent")
         rows = [w.shape[0] for w in weights]
-        w_all = torch.empty((n_grid + 1, sum(rows), K), dtype=weights[0].dtype, device=dev)  # [0] = reference weights
+        w_all = workspace.get("w_all", (n_grid + 1, sum(rows), K), weights[0].dtype, dev)  # [0] = reference weights
         off = 0
         for w, n in zip(weights, rows):
             w_all[0, off:off + n].copy_(w)
