@@ -37,6 +37,7 @@ _SIGS = {
     "b200q_compress_int_packed": (_I, [_P, c_int64, c_int64, c_int64, _S, _P, _P, _P, _P]),
     "b200q_compress_fp8": (_I, [_P, c_int64, c_int64, c_int64, _S, _P, _P, _P, _P]),
     "b200q_compress_nvfp4": (_I, [_P, c_int64, c_int64, c_int64, c_int32, c_int32, _P, _P, _P, _P]),
+    "b200q_compress_nvfp4_fused": (_I, [_P, c_int64, c_int64, c_int64, c_int32, c_int32, _P, _P, _P, _P, c_int64, _P]),
     "b200q_minmax": (_I, [_P, c_int64, c_int64, c_int64, _S, _P, _P, _P]),
     "b200q_global_scale": (_I, [_P, c_int64, c_int64, c_int32, _P, c_int32, _P, _P]),
     "b200q_calculate_qparams": (_I, [_P, _P, c_int64, _S, _P, _P, _P, _P]),

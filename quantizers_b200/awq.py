@@ -285,14 +285,16 @@ def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent:
     parent   a LinearParent / MLPParent / AttentionParent (fused tensor-core evaluation, bf16) or any callable (generic
              evaluation: the parent runs through torch, the squared error through ``b200q_sq_err_accumulate``)
     Returns (best_scales fp32 [K] on the CPU like the reference, best_ratio, losses[n_grid]).  Raises if no ratio gives
-    a finite loss.  With ``process_group`` the |x| sums / token counts and the loss accumulators are all-reduced (SUM),
-    so every rank returns the same argmin."""
+    a finite loss.  With ``process_group`` (token-sharded calibration; pass ``dist.group.WORLD`` for all ranks) the |x| sums /
+    token counts and the loss accumulators are all-reduced (SUM), so every rank of the group returns the same argmin."""
     import torch.distributed as dist
 
     dev = x.device
     K = x.shape[-1]
     x = x.reshape(-1, K)
-    dist_on = process_group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+    # token-sharded calibration is explicit: layer- / expert-sharded ranks search different mappings and must NOT be reduced
+    # together, so nothing is exchanged unless the caller names the group whose ranks hold shards of the same tokens
+    dist_on = process_group is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
     if fused is None:
         fused = fused_linear if fused_linear is not None else (hasattr(parent, "fused_losses") and x.dtype == torch.bfloat16)
     # ---- statistics

@@ -109,27 +109,50 @@ int b200q_compress_fp8(const void* weight, int64_t batch, int64_t rows, int64_t 
     return launch_tensor_fp8_compress(sc->dtype, p, batch, st);
 }
 
-int b200q_compress_nvfp4(const void* weight, int64_t batch, int64_t rows, int64_t cols, int32_t dtype, int32_t compute_global,
-                         float* global_scale, uint8_t* packed, uint8_t* scale_e4m3, void* stream) {
+static int compress_nvfp4_impl(const void* weight, int64_t batch, int64_t rows, int64_t cols, int32_t dtype, int32_t compute_global,
+                               int32_t fuse_span, float* global_scale, uint8_t* packed, uint8_t* scale_e4m3, void* workspace,
+                               int64_t workspace_bytes, cudaStream_t st) {
     REQ_PTR(weight); REQ_PTR(global_scale); REQ_PTR(packed); REQ_PTR(scale_e4m3);
     B200Q_REQUIRE(cols % 16 == 0, "tensor column shape must be divisible by the given group_size 16 but got %lld", (long long)cols);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (compute_global) {
-        // the min/max state lives in the first 8*batch bytes of the (not yet written) scale output buffer
-        B200Q_REQUIRE(rows * cols / 16 >= 8, "weight too small to stage the min/max state");
-        float* state = (float*)scale_e4m3;
-        B200Q_REQUIRE(((uintptr_t)state & 3) == 0, "scale buffer must be 4-byte aligned");
-        if (int rc = launch_global_scale(dtype, weight, batch, rows * cols, state, 0, global_scale, st)) return rc;
-    }
+    B200Q_REQUIRE(fuse_span >= 1 && batch % fuse_span == 0, "fuse_span must divide the batch");
+    if (rows * cols == 0 || batch == 0) return B200Q_OK;
     GroupParams p{};
     p.w = weight; p.rows = rows; p.cols = cols; p.group = 16; p.nbits = 4; p.symmetric = 1; p.has_zp = 1;
     p.scale = scale_e4m3; p.gs = global_scale; p.gs_stride = 1; p.out = packed;
-    if (dtype == B200Q_BF16 && fast_paths_enabled()) {
+    const bool fast = dtype == B200Q_BF16 && fast_paths_enabled();
+    if (compute_global) {
+        int rc = B200Q_ENOSYS;
+        if (fast && workspace && workspace_bytes >= 8 * (batch / fuse_span) && (((uintptr_t)workspace) & 3) == 0)
+            rc = launch_nvfp4_fused(p, batch, fuse_span, global_scale, (uint32_t*)workspace, st);  // one launch, one HBM read
+        if (rc != B200Q_ENOSYS) return rc;
+        // generic: min/max state staged in the first 8*batch bytes of the (not yet written) scale output buffer
+        B200Q_REQUIRE(rows * cols / 16 >= 8, "weight too small to stage the min/max state");
+        float* state = (float*)scale_e4m3;
+        B200Q_REQUIRE(((uintptr_t)state & 3) == 0, "scale buffer must be 4-byte aligned");
+        if (int rc2 = launch_global_scale(dtype, weight, batch, rows * cols, state, 0, global_scale, st)) return rc2;
+        if (fuse_span > 1) {
+            if (int rc2 = launch_span_min(global_scale, batch, fuse_span, st)) return rc2;
+        }
+    }
+    if (fast) {
         int rc = tma_paths_enabled() ? launch_group_tma(QT_FP4, p, batch, st) : B200Q_ENOSYS;
         if (rc == B200Q_ENOSYS) rc = launch_nvfp4_fast(p, batch, st);
         if (rc != B200Q_ENOSYS) return rc;
     }
     return dispatch_group<MODE_COMPRESS>(dtype, QT_FP4, p, batch, st);
+}
+
+int b200q_compress_nvfp4(const void* weight, int64_t batch, int64_t rows, int64_t cols, int32_t dtype, int32_t compute_global,
+                         float* global_scale, uint8_t* packed, uint8_t* scale_e4m3, void* stream) {
+    return compress_nvfp4_impl(weight, batch, rows, cols, dtype, compute_global, 1, global_scale, packed, scale_e4m3, nullptr, 0,
+                               (cudaStream_t)stream);
+}
+
+int b200q_compress_nvfp4_fused(const void* weight, int64_t batch, int64_t rows, int64_t cols, int32_t dtype, int32_t fuse_span,
+                               float* global_scale, uint8_t* packed, uint8_t* scale_e4m3, void* workspace, int64_t workspace_bytes,
+                               void* stream) {
+    return compress_nvfp4_impl(weight, batch, rows, cols, dtype, 1, fuse_span, global_scale, packed, scale_e4m3, workspace, workspace_bytes,
+                               (cudaStream_t)stream);
 }
 
 int b200q_minmax(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* sc, void* mn, void* mx,

@@ -30,6 +30,7 @@ bool tma_paths_enabled();
 int launch_group_fast(int qt, const GroupParams& p, int64_t batch, cudaStream_t st);
 int launch_block_fp8_fast(const TileParams& p, int64_t batch, cudaStream_t st);
 int launch_nvfp4_fast(const GroupParams& p, int64_t batch, cudaStream_t st);
+int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_out, uint32_t* sync, cudaStream_t st);
 bool fast_paths_enabled();
 
 // ---- generic element-wise path with caller-supplied qparams, any strategy (quant_elementwise.cu)
@@ -50,6 +51,7 @@ int launch_minmax(int dt, const void* w, int64_t batch, int64_t rows, int64_t co
                   void* mn, void* mx, cudaStream_t st);
 int launch_global_scale(int dt, const void* x, int64_t batch, int64_t numel, float* state, int running, float* gs,
                         cudaStream_t st);
+int launch_span_min(float* gs, int64_t batch, int span, cudaStream_t st);
 int launch_qparams(int dt, int qt, int nbits, int symmetric, const void* mn, const void* mx, int64_t n, const float* gs,
                    void* scale, int8_t* zp, cudaStream_t st);
 

@@ -151,6 +151,21 @@ int launch_global_scale(int dt, const void* x, int64_t batch, int64_t numel, flo
     return B200Q_OK;
 }
 
+// update_fused_layer_weight_global_scales: `span` consecutive matrices (gate/up of one expert) share min(global_scale)
+__global__ void span_min_kernel(float* gs, int64_t n_spans, int span) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_spans) return;
+    float m = gs[s * span];
+    for (int i = 1; i < span; i++) m = fminf(m, gs[s * span + i]);
+    for (int i = 0; i < span; i++) gs[s * span + i] = m;
+}
+int launch_span_min(float* gs, int64_t batch, int span, cudaStream_t st) {
+    const int64_t n = batch / span;
+    span_min_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gs, n, span);
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
 int launch_minmax(int dt, const void* w, int64_t batch, int64_t rows, int64_t cols, int strategy, int group, int bh, int bw,
                   void* mn, void* mx, cudaStream_t st) {
     B200Q_REQUIRE(((uintptr_t)w & 15) == 0, "weight pointer must be 16-byte aligned");

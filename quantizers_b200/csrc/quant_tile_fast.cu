@@ -24,6 +24,27 @@ __device__ __forceinline__ uint32_t cvt_e2m1x2(float hi, float lo) {  // byte: l
     return r;
 }
 
+// eight fp32 values (four f32x2 pairs, element order) -> one word of eight e2m1 nibbles, element 0 in bits 0-3.  Written as one
+// PTX block so the four byte results are merged by the conversion itself instead of being masked and permuted one by one.
+__device__ __forceinline__ uint32_t cvt_e2m1x8(f32x2 p0, f32x2 p1, f32x2 p2, f32x2 p3) {
+    uint32_t r;
+    asm("{\n"
+        ".reg .b8 t0, t1, t2, t3;\n"
+        ".reg .f32 a0, a1, a2, a3, a4, a5, a6, a7;\n"
+        "mov.b64 {a0, a1}, %1;\n"
+        "mov.b64 {a2, a3}, %2;\n"
+        "mov.b64 {a4, a5}, %3;\n"
+        "mov.b64 {a6, a7}, %4;\n"
+        "cvt.rn.satfinite.e2m1x2.f32 t0, a1, a0;\n"
+        "cvt.rn.satfinite.e2m1x2.f32 t1, a3, a2;\n"
+        "cvt.rn.satfinite.e2m1x2.f32 t2, a5, a4;\n"
+        "cvt.rn.satfinite.e2m1x2.f32 t3, a7, a6;\n"
+        "mov.b32 %0, {t0, t1, t2, t3};\n"
+        "}\n"
+        : "=r"(r) : "l"(p0.v), "l"(p1.v), "l"(p2.v), "l"(p3.v));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------ FP8 block
 constexpr int NC = 8;
 
@@ -181,6 +202,223 @@ __global__ void __launch_bounds__(256, 4) nvfp4_fast_kernel(const GroupParams p)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ NVFP4, flat groups
+// [batch, rows, cols] with cols % 16 == 0 is a flat array of 16-element groups.  A thread owns whole groups (2 x LDG.128,
+// UF groups in flight); a CTA works inside ONE matrix so that everything that depends only on (e4m3 scale code, global
+// scale) is tabulated once per CTA in shared memory: there are just 127 non-negative e4m3 codes, so
+//     s_eff = fp32(e4m3) / gs,   the bracketed reciprocal pair of s_eff   and   the "safe" flag
+// come from one LDS.128 per group instead of an IEEE division + rcp + 2 multiplies (ncu on the previous kernel: 14.9
+// issued instructions per weight, ALU pipe 69 % -- instruction bound at 41 % of HBM).  Per group: 9 packed bf16 max ops,
+// the constant division by 6 (bracketed), one F2FP to e4m3, the table fetch; per element pair: 2 unpack ops, 2 FFMA2,
+// 2 F2FP(e2m1x2), 1 LOP3.
+constexpr int FP4_THREADS = 256;
+constexpr int FP4_UF = 4;                                   // groups per thread per tile
+constexpr int FP4_TILE_GROUPS = FP4_THREADS * FP4_UF;       // 1024 groups = 32 KB of bf16 per CTA tile
+
+struct Fp4Entry { float r_lo, r_hi, s_eff, unsafe; };
+
+__device__ __forceinline__ void fp4_build_table(Fp4Entry* table, float gs) {
+    if (threadIdx.x < 128) {
+        // code 0 (scale rounds to zero) is replaced by 0.125 = code 0x20 (helpers.py:101-126); 0x7f is NaN, never produced
+        const uint32_t code = threadIdx.x == 0 ? 0x20u : threadIdx.x;
+        const float s_eff = fdiv(e4m3_decode((uint8_t)code), gs);
+        const float r = rcp_approx(s_eff);
+        Fp4Entry e;
+        e.r_lo = __fmul_rn(r, 0.99999952316284179688f);
+        e.r_hi = __fmul_rn(r, 1.00000047683715820312f);
+        e.s_eff = s_eff;
+        e.unsafe = fp4_scale_is_safe(s_eff) ? 0.0f : 1.0f;
+        table[threadIdx.x] = e;
+    }
+}
+
+__device__ __forceinline__ void fp4_load_tile(uint4 (&raw)[FP4_UF][2], const uint4* wbase, int64_t g0, int64_t groups_per_mat) {
+#pragma unroll
+    for (int u = 0; u < FP4_UF; u++) {
+        const int64_t g = g0 + u * FP4_THREADS;
+        if (g < groups_per_mat) {
+            raw[u][0] = ldg_stream(wbase + 2 * g);
+            raw[u][1] = ldg_stream(wbase + 2 * g + 1);
+        } else {
+            raw[u][0] = raw[u][1] = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+__device__ __forceinline__ uint32_t fp4_group_absmax2(const uint4 (&r)[2]) {  // packed bf16x2 |max| of 16 elements
+    return hmaxabs2(hmaxabs2(hmaxabs2(r[0].x, r[0].y), hmaxabs2(r[0].z, r[0].w)), hmaxabs2(hmaxabs2(r[1].x, r[1].y), hmaxabs2(r[1].z, r[1].w)));
+}
+
+// exact bf16(absmax / 6) from the bf16 |max| bits (<< 16): bracketed constant reciprocal, IEEE fallback when the two ends
+// round apart or the operand is outside [2^-100, 2^100] (zero is fine: both products are 0)
+__device__ __forceinline__ float fp4_loc_scale(uint32_t abits) {
+    const float a = __uint_as_float(abits);
+    const float lo = __fmul_rn(a, (1.0f / 6.0f) * 0.99999952316284179688f), hi = __fmul_rn(a, (1.0f / 6.0f) * 1.00000047683715820312f);
+    const uint32_t u = cvt_bf16x2(hi, lo);
+    const bool in_range = (abits - 0x0d800000u) <= (0x71800000u - 0x0d800000u) || abits == 0;
+    if (in_range && (u >> 16) == (u & 0xffffu)) return __uint_as_float(u << 16);
+    return round_to<DT_BF16>(__fdiv_rn(a, 6.0f));
+}
+
+// one 1024-group tile of one matrix, already in registers: scale codes + packed e2m1 out
+__device__ __forceinline__ void fp4_compress_regs(const uint4 (&raw)[FP4_UF][2], const Fp4Entry* table, float gs, uint8_t* sbase, uint2* obase,
+                                                  int64_t g0, int64_t groups_per_mat) {
+#pragma unroll
+    for (int u = 0; u < FP4_UF; u++) {
+        const int64_t g = g0 + u * FP4_THREADS;
+        if (g >= groups_per_mat) continue;
+        uint32_t m = fp4_group_absmax2(raw[u]);
+        m = hmaxabs2(m, prmt(m, m, 0x1032));
+        const float loc = fp4_loc_scale((m << 16) & 0x7fff0000u);          // T(absmax / 6)
+        const float sf = fminf(__fmul_rn(gs, loc), 448.0f);                // gs * loc, clamp (non-negative)
+        uint32_t code = cvt_e4m3x2(0.0f, sf) & 0xffu;
+        const Fp4Entry e = table[code];
+        if (code == 0) code = 0x20;
+        sbase[g] = (uint8_t)code;
+        const f32x2 rl = pack2(e.r_lo, e.r_lo), rh = pack2(e.r_hi, e.r_hi);
+        uint32_t out[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            // x * r + 0.0: exact -0.0 inputs carry no sign nibble (torch.sign(-0.) == 0); satfinite == clamp to +-6; the sign
+            // bit of a value that rounds to zero comes from the pre-round sign, like the reference's sign(x) * |q|
+            const f32x2 x0 = bf16x2_to_f32x2(raw[u][h].x), x1 = bf16x2_to_f32x2(raw[u][h].y);
+            const f32x2 x2 = bf16x2_to_f32x2(raw[u][h].z), x3 = bf16x2_to_f32x2(raw[u][h].w);
+            uint32_t packed = cvt_e2m1x8(mul2_plus0(x0, rl), mul2_plus0(x1, rl), mul2_plus0(x2, rl), mul2_plus0(x3, rl));
+            const uint32_t diff = packed ^ cvt_e2m1x8(mul2_plus0(x0, rh), mul2_plus0(x1, rh), mul2_plus0(x2, rh), mul2_plus0(x3, rh));
+            if (diff != 0 || e.unsafe != 0.0f) packed = fix_group_fp4(raw[u][h], e.s_eff, packed);
+            out[h] = packed;
+        }
+        stg_stream(obase + g, make_uint2(out[0], out[1]));
+    }
+}
+__device__ __forceinline__ void fp4_compress_tile(const Fp4Entry* table, float gs, const uint4* wbase, uint8_t* sbase, uint2* obase, int64_t g0,
+                                                  int64_t groups_per_mat) {
+    uint4 raw[FP4_UF][2];
+    fp4_load_tile(raw, wbase, g0, groups_per_mat);
+    fp4_compress_regs(raw, table, gs, sbase, obase, g0, groups_per_mat);
+}
+
+// caller-supplied global scales (fused q/k/v siblings, decompress round trips): one pass
+__global__ void __launch_bounds__(FP4_THREADS) nvfp4_flat_kernel(const GroupParams p, int64_t groups_per_mat, int tiles_per_mat) {
+    __shared__ Fp4Entry table[128];
+    const int64_t b = blockIdx.y;
+    const float gs = p.gs[p.gs_stride ? b : 0];
+    fp4_build_table(table, gs);
+    __syncthreads();
+    const uint4* wbase = reinterpret_cast<const uint4*>((const char*)p.w + b * groups_per_mat * 32);
+    uint8_t* sbase = (uint8_t*)p.scale + b * groups_per_mat;
+    uint2* obase = reinterpret_cast<uint2*>((uint8_t*)p.out + b * groups_per_mat * 8);
+    for (int tile = blockIdx.x; tile < tiles_per_mat; tile += gridDim.x)
+        fp4_compress_tile(table, gs, wbase, sbase, obase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, groups_per_mat);
+}
+
+// Global scale computed here: the whole-matrix |max| must be known before the first code is emitted, i.e. two passes over the
+// weight.  One launch does both.  Block A(s) = |max| items of sibling span s (matrices that share min(global_scale): gate/up
+// of one expert), block B(s) = compress items of span s; an item is FP4_NT consecutive tiles of one matrix.  CTAs are laid out
+// in the order
+//     A(0) .. A(L-1),  B(0), A(L), B(1), A(L+1), ...,  B(S-L) .. B(S-1)
+// so the reduction runs L spans (<= ~14 MB; measured: larger windows start missing in L2) ahead of the compression and B's re-read is served by the L2: HBM sees every weight
+// once.  A B-CTA polls the span's completion counter.  Hardware dispatches a 1-D grid in blockIdx order, so in practice the
+// counter is already complete; the launch does not DEPEND on that: a B-CTA that waits too long reduces the span itself, so it
+// never blocks on a CTA that has not been scheduled.
+// sync words (zeroed by the launcher): per span {|max| bits, finished A items}.
+constexpr int FP4_NT = 4;
+struct Fp4FusedParams {
+    int64_t groups_per_mat;
+    int32_t tiles_per_mat, items_per_mat, span, n_spans, lookahead;
+    uint32_t* sync;
+    float* gs_out;  // [batch]
+};
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// |max| bits of tiles [tile0, tile1) of one matrix, reduced over the CTA (valid in thread 0)
+__device__ __forceinline__ uint32_t fp4_absmax_tiles(const uint4* wbase, int tile0, int tile1, int64_t groups_per_mat, uint32_t* s_red) {
+    uint32_t mm = 0;
+    for (int tile = tile0; tile < tile1; tile++) {
+        uint4 raw[FP4_UF][2];
+        fp4_load_tile(raw, wbase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, groups_per_mat);
+        mm = hmaxabs2(mm, hmaxabs2(hmaxabs2(fp4_group_absmax2(raw[0]), fp4_group_absmax2(raw[1])),
+                                   hmaxabs2(fp4_group_absmax2(raw[2]), fp4_group_absmax2(raw[3]))));
+    }
+    mm = hmaxabs2(mm, prmt(mm, mm, 0x1032));
+    uint32_t bits = (mm << 16) & 0x7fff0000u;                  // |max| as fp32 bits: non-negative floats order like uints
+    bits = __reduce_max_sync(0xffffffffu, bits);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 1; i < FP4_THREADS / 32; i++) bits = max(bits, s_red[i]);
+    }
+    return bits;
+}
+
+__global__ void __launch_bounds__(FP4_THREADS, 4) nvfp4_fused_kernel(const GroupParams p, const Fp4FusedParams f) {
+    __shared__ Fp4Entry table[128];
+    __shared__ float s_gs;
+    __shared__ int s_need_fallback;
+    __shared__ uint32_t s_red[FP4_THREADS / 32];
+    const int nblk = f.items_per_mat * f.span;                 // items per block
+    const int S = f.n_spans, Lh = f.lookahead;
+    const int k = (int)(blockIdx.x / (unsigned)nblk), j = (int)(blockIdx.x - (unsigned)k * (unsigned)nblk);
+    bool is_b;
+    int s;
+    if (k < Lh) { is_b = false; s = k; }
+    else if (k >= 2 * S - Lh) { is_b = true; s = k - S; }
+    else { const int r = k - Lh; is_b = (r & 1) == 0; s = is_b ? r / 2 : Lh + r / 2; }
+    const int mi = j / f.items_per_mat, item = j - mi * f.items_per_mat;
+    const int64_t m = (int64_t)s * f.span + mi;
+    const int tile0 = item * FP4_NT, tile1 = min(tile0 + FP4_NT, f.tiles_per_mat);
+    uint32_t* st = f.sync + 2 * s;
+    const uint4* wbase = reinterpret_cast<const uint4*>((const char*)p.w + m * f.groups_per_mat * 32);
+    if (!is_b) {
+        const uint32_t bits = fp4_absmax_tiles(wbase, tile0, tile1, f.groups_per_mat, s_red);
+        if (threadIdx.x == 0) {
+            atomicMax(&st[0], bits);
+            __threadfence();
+            atomicAdd(&st[1], 1u);
+        }
+        return;
+    }
+    uint4 raw[FP4_UF][2];
+    fp4_load_tile(raw, wbase, (int64_t)tile0 * FP4_TILE_GROUPS + threadIdx.x, f.groups_per_mat);  // in flight while we poll
+    if (threadIdx.x == 0) {
+        int spins = 0;
+        while (ld_acquire(&st[1]) < (uint32_t)nblk && spins < 20000) { __nanosleep(64); spins++; }
+        s_need_fallback = ld_acquire(&st[1]) < (uint32_t)nblk;
+    }
+    __syncthreads();
+    uint32_t bits;
+    if (s_need_fallback) {  // never taken when CTAs start in blockIdx order; keeps the kernel independent of that assumption
+        bits = 0;
+        for (int q = 0; q < f.span; q++) {
+            const uint4* wq = reinterpret_cast<const uint4*>((const char*)p.w + ((int64_t)s * f.span + q) * f.groups_per_mat * 32);
+            bits = max(bits, fp4_absmax_tiles(wq, 0, f.tiles_per_mat, f.groups_per_mat, s_red));
+        }
+    } else {
+        bits = threadIdx.x == 0 ? ld_acquire(&st[0]) : 0u;
+    }
+    if (threadIdx.x == 0) {
+        const float gs0 = gparam<DT_BF16>(__uint_as_float(bits));
+        s_gs = gs0;
+        if (item == 0) f.gs_out[m] = gs0;
+    }
+    __syncthreads();
+    const float gs = s_gs;
+    fp4_build_table(table, gs);
+    __syncthreads();
+    uint8_t* sbase = (uint8_t*)p.scale + m * f.groups_per_mat;
+    uint2* obase = reinterpret_cast<uint2*>((uint8_t*)p.out + m * f.groups_per_mat * 8);
+    fp4_compress_regs(raw, table, gs, sbase, obase, (int64_t)tile0 * FP4_TILE_GROUPS + threadIdx.x, f.groups_per_mat);
+    for (int tile = tile0 + 1; tile < tile1; tile++)
+        fp4_compress_tile(table, gs, wbase, sbase, obase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, f.groups_per_mat);
+}
+
 }  // namespace
 
 int launch_block_fp8_fast(const TileParams& p, int64_t batch, cudaStream_t st) {
@@ -195,9 +433,41 @@ int launch_block_fp8_fast(const TileParams& p, int64_t batch, cudaStream_t st) {
 
 int launch_nvfp4_fast(const GroupParams& p, int64_t batch, cudaStream_t st) {
     if (p.cols % 16 != 0 || (((uintptr_t)p.w) & 15) != 0 || batch * p.rows * p.cols == 0) return B200Q_ENOSYS;
-    if (batch > 65535 || (p.rows + 7) / 8 > 65535) return B200Q_ENOSYS;
-    dim3 grid((unsigned)((p.cols + 512 * U2 - 1) / (512 * U2)), (unsigned)((p.rows + 7) / 8), (unsigned)batch);
-    nvfp4_fast_kernel<<<grid, 256, 0, st>>>(p);
+    const int64_t groups_per_mat = p.rows * (p.cols >> 4);
+    // every matrix must start 16-byte aligned in the weight and 8-byte aligned in the packed output: groups_per_mat * 32 / * 8 do
+    const int64_t tiles = (groups_per_mat + FP4_TILE_GROUPS - 1) / FP4_TILE_GROUPS;
+    if (batch > 65535 || tiles > (1ll << 30) || (((uintptr_t)p.out) & 7) != 0) return B200Q_ENOSYS;
+    // enough CTAs to fill the machine (8 resident per SM) without rebuilding the table more often than once per ~32 KB
+    const int64_t want = (int64_t)kNumSMs * 8;
+    int64_t gx = tiles;
+    if (batch * tiles > 4 * want) gx = max((int64_t)1, min(tiles, (4 * want + batch - 1) / batch));
+    nvfp4_flat_kernel<<<dim3((unsigned)gx, (unsigned)batch), FP4_THREADS, 0, st>>>(p, groups_per_mat, (int)tiles);
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+// fused |max| -> global scale -> compress; `span` consecutive matrices share min(global_scale); sync: >= 8 * batch / span bytes
+int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_out, uint32_t* sync, cudaStream_t st) {
+    if (p.cols % 16 != 0 || (((uintptr_t)p.w) & 15) != 0 || (((uintptr_t)p.out) & 7) != 0 || batch * p.rows * p.cols == 0) return B200Q_ENOSYS;
+    if (span < 1 || batch % span != 0) return B200Q_ENOSYS;
+    const int64_t groups_per_mat = p.rows * (p.cols >> 4);
+    const int64_t tiles = (groups_per_mat + FP4_TILE_GROUPS - 1) / FP4_TILE_GROUPS;
+    const int64_t items = (tiles + FP4_NT - 1) / FP4_NT;
+    const int64_t n_spans = batch / span;
+    const int64_t grid = 2 * n_spans * items * span;
+    if (tiles >= (1ll << 30) || grid >= (1ll << 31)) return B200Q_ENOSYS;
+    Fp4FusedParams f;
+    f.groups_per_mat = groups_per_mat;
+    f.tiles_per_mat = (int)tiles;
+    f.items_per_mat = (int)items;
+    f.span = span;
+    f.n_spans = (int)n_spans;
+    const int64_t span_bytes = groups_per_mat * 32 * span;
+    f.lookahead = (int)max((int64_t)1, min(n_spans, (int64_t)(14ll << 20) / max(span_bytes, (int64_t)1)));
+    f.sync = sync;
+    f.gs_out = gs_out;
+    cudaMemsetAsync(sync, 0, sizeof(uint32_t) * 2 * n_spans, st);
+    nvfp4_fused_kernel<<<(unsigned)grid, FP4_THREADS, 0, st>>>(p, f);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }

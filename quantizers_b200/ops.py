@@ -367,13 +367,16 @@ def unpack_fp4_from_uint8(a: torch.Tensor, m: int, n: int, dtype: Optional[torch
 
 # ----------------------------------------------------------------------------- fused compress
 @torch.no_grad()
-def compress_weight(weight: torch.Tensor, args, global_scale: Optional[torch.Tensor] = None, has_zp: bool = True) -> dict:
+def compress_weight(weight: torch.Tensor, args, global_scale: Optional[torch.Tensor] = None, has_zp: bool = True,
+                    fuse_span: int = 1) -> dict:
     """Fused observer -> qparams -> quantize -> pack of one weight ``[rows, cols]`` or a stack ``[E, rows, cols]``.
 
     Returns the tensors ``Compressor.compress`` puts in the state dict:
       INT  : weight_packed int32, weight_scale T, weight_shape int64[2], (+ weight_zero_point int32 when asymmetric)
       FP8  : weight e4m3, weight_scale T
-      FP4  : weight_packed uint8, weight_scale e4m3, weight_global_scale fp32 [1] (per stacked weight: [E, 1])
+      FP4  : weight_packed uint8, weight_scale e4m3, weight_global_scale fp32 [1] (per stacked weight: [E, 1]);
+             ``fuse_span`` consecutive stacked weights share min(global_scale) (gate/up siblings, LLMC
+             update_fused_layer_weight_global_scales) when the global scale is computed here
     """
     L.require_cuda(weight, global_scale)
     if weight.ndim not in (2, 3):
@@ -427,8 +430,12 @@ def compress_weight(weight: torch.Tensor, args, global_scale: Optional[torch.Ten
     packed = torch.empty(lead + (rows, cols // 2), dtype=torch.uint8, device=dev)
     scale = torch.empty(lead + (rows, cols // 16), dtype=torch.uint8, device=dev)
     if global_scale is None:
+        # NVFP4 siblings stacked next to each other (gate/up of one expert: fuse_span = 2) share min(global_scale)
         gs = torch.empty(batch, dtype=torch.float32, device=dev)
-        compute = 1
+        ws = torch.empty(2 * max(batch // max(int(fuse_span), 1), 1), dtype=torch.int32, device=dev)
+        L.check(lib.b200q_compress_nvfp4_fused(L.ptr(w), batch, rows, cols, L.DTYPE_CODE[w.dtype], int(fuse_span), L.ptr(gs), L.ptr(packed),
+                                               L.ptr(scale), L.ptr(ws), ws.numel() * 4, st))
+        return {"weight_packed": packed, "weight_scale": scale.view(_FP8), "weight_global_scale": gs.reshape(lead + (1,))}
     else:
         gs = global_scale.to(torch.float32).reshape(-1)
         if gs.numel() == 1 and batch > 1:

@@ -190,6 +190,13 @@ def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Opt
     groups = {}
     for m in nv:
         groups.setdefault(m.fuse_group or m.name, []).append(m)
+    span_of: Dict[str, int] = {}
+    for gname, members in list(groups.items()):
+        if len(members) == 1:
+            # all siblings of the group sit next to each other in ONE stack (gate/up: per_unit = 2): the fused kernel computes
+            # |max| -> min(global_scale) -> codes in a single launch with one HBM read
+            span_of[members[0].name] = members[0].per_unit
+            del groups[gname]
     for gname, members in groups.items():
         per_unit_min = None
         for m in members:
@@ -205,7 +212,7 @@ def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Opt
         if timings is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        out[m.name] = ops.compress_weight(w, args, global_scale=fused_gs.get(m.name))
+        out[m.name] = ops.compress_weight(w, args, global_scale=fused_gs.get(m.name), fuse_span=span_of.get(m.name, 1))
         if ev is not None:
             ev[1].record()
             timings.append((m.name, m.preset, w.numel(), ev[0], ev[1]))
@@ -218,7 +225,7 @@ def launches_per_step(spec: ModelSpec) -> int:
     for m in spec.matrices:
         a = PRESETS[m.preset]
         if a.type == "float" and a.num_bits == 4:
-            n += 3 + 1  # init + min/max reduce + gparam, then the group kernel
+            n += 1  # fused |max| -> global scale -> compress kernel (siblings in one stack)
         elif a.strategy == "tensor":
             n += 3
         else:

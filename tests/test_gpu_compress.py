@@ -89,6 +89,22 @@ def test_nvfp4_supplied_global_scale():
     _cmp_sd(got, want, "nvfp4 gs")
 
 
+@pytest.mark.parametrize("E,R,C,span", [(6, 36, 512, 2), (64, 768, 2048, 2), (9, 200, 1040, 3), (3, 2048, 768, 1)])
+def test_nvfp4_fused_sibling_global_scale(E, R, C, span):
+    """gate/up siblings stacked next to each other share min(global_scale) (LLMC update_fused_layer_weight_global_scales); the
+    ticketed persistent kernel (|max| tiles ahead of compress tiles) must equal the oracle run with that shared scale."""
+    from quantizers_b200 import ops
+
+    ws = [(synth_weight(R, C, torch.bfloat16, 300 + e, edge=R >= 64) * (1.0 + 0.37 * e)).to(torch.bfloat16) for e in range(E)]
+    got = ops.compress_weight(torch.stack(ws).cuda(), Args("nvfp4"), fuse_span=span)
+    for s0 in range(0, E, span):
+        gs = min(float(O.generate_gparam(float(ws[e].float().min()), float(ws[e].float().max()), torch.bfloat16)) for e in range(s0, s0 + span))
+        for e in range(s0, s0 + span):
+            want = O.compress(ws[e], "nvfp4-pack-quantized", geom_of("nvfp4"), 4, True, torch.tensor([gs]))
+            for k in want:
+                assert_bits_equal(got[k][e].reshape(want[k].shape), want[k], f"nvfp4 fused[{e}]:{k}")
+
+
 @pytest.mark.parametrize("name", list(FORMATS))
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_unfused_ops_match_oracle(name, dtype):
