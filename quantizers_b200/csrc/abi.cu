@@ -123,7 +123,15 @@ static int compress_nvfp4_impl(const void* weight, int64_t batch, int64_t rows, 
     if (compute_global) {
         int rc = B200Q_ENOSYS;
         if (fast && workspace && workspace_bytes >= 8 * (batch / fuse_span) && (((uintptr_t)workspace) & 3) == 0)
-            rc = launch_nvfp4_fused(p, batch, fuse_span, global_scale, (uint32_t*)workspace, st);  // one launch, one HBM read
+        {
+            // one launch, one HBM read (the compress pass re-reads through the L2).  Two schedulings of the same idea: one short
+            // CTA per 32-128 KB item (default), or a persistent warp-specialised CTA per SM (B200Q_FP4_PERSISTENT=1, needs one
+            // sync word per tile in the workspace).  Both are bound by the ALU pipe at ~0.55 of the HBM roofline.
+            const char* v = getenv("B200Q_FP4_PERSISTENT");
+            if (v && v[0] == '1' && workspace_bytes >= nvfp4_resident_workspace(batch, rows, cols))
+                rc = launch_nvfp4_resident(p, batch, fuse_span, global_scale, (uint32_t*)workspace, st);
+            if (rc == B200Q_ENOSYS) rc = launch_nvfp4_fused(p, batch, fuse_span, global_scale, (uint32_t*)workspace, st);
+        }
         if (rc != B200Q_ENOSYS) return rc;
         // generic: min/max state staged in the first 8*batch bytes of the (not yet written) scale output buffer
         B200Q_REQUIRE(rows * cols / 16 >= 8, "weight too small to stage the min/max state");
@@ -153,6 +161,12 @@ int b200q_compress_nvfp4_fused(const void* weight, int64_t batch, int64_t rows, 
                                void* stream) {
     return compress_nvfp4_impl(weight, batch, rows, cols, dtype, 1, fuse_span, global_scale, packed, scale_e4m3, workspace, workspace_bytes,
                                (cudaStream_t)stream);
+}
+
+int64_t b200q_compress_nvfp4_workspace(int64_t batch, int64_t rows, int64_t cols, int32_t fuse_span) {
+    const int64_t spans = fuse_span > 0 ? (batch + fuse_span - 1) / fuse_span : batch;
+    const int64_t a = 8 * spans, b = nvfp4_resident_workspace(batch, rows, cols);
+    return a > b ? a : b;
 }
 
 int b200q_minmax(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* sc, void* mn, void* mx,

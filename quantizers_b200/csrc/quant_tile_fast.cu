@@ -5,45 +5,17 @@
 //     no shuffle and the per-group scale chain runs once per group.
 // Both use the bracketed reciprocal of fastmath.cuh for the reference's divisions and fall back to the exact IEEE
 // chain (qmath.cuh) for the rare elements whose bracket ends disagree.
+#include <cstdlib>
+#include "async.cuh"
 #include "common.cuh"
 #include "fastmath.cuh"
+#include "fp4.cuh"
 #include "kernels.cuh"
 
 namespace b200q {
 namespace {
 using namespace fast;
-
-__device__ __forceinline__ uint32_t cvt_e4m3x2(float hi, float lo) {
-    uint16_t r;
-    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-__device__ __forceinline__ uint32_t cvt_e2m1x2(float hi, float lo) {  // byte: lo element in bits 0-3
-    uint16_t r;
-    asm("{ .reg .b8 t; cvt.rn.satfinite.e2m1x2.f32 t, %1, %2; cvt.u16.u8 %0, t; }" : "=h"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-
-// eight fp32 values (four f32x2 pairs, element order) -> one word of eight e2m1 nibbles, element 0 in bits 0-3.  Written as one
-// PTX block so the four byte results are merged by the conversion itself instead of being masked and permuted one by one.
-__device__ __forceinline__ uint32_t cvt_e2m1x8(f32x2 p0, f32x2 p1, f32x2 p2, f32x2 p3) {
-    uint32_t r;
-    asm("{\n"
-        ".reg .b8 t0, t1, t2, t3;\n"
-        ".reg .f32 a0, a1, a2, a3, a4, a5, a6, a7;\n"
-        "mov.b64 {a0, a1}, %1;\n"
-        "mov.b64 {a2, a3}, %2;\n"
-        "mov.b64 {a4, a5}, %3;\n"
-        "mov.b64 {a6, a7}, %4;\n"
-        "cvt.rn.satfinite.e2m1x2.f32 t0, a1, a0;\n"
-        "cvt.rn.satfinite.e2m1x2.f32 t1, a3, a2;\n"
-        "cvt.rn.satfinite.e2m1x2.f32 t2, a5, a4;\n"
-        "cvt.rn.satfinite.e2m1x2.f32 t3, a7, a6;\n"
-        "mov.b32 %0, {t0, t1, t2, t3};\n"
-        "}\n"
-        : "=r"(r) : "l"(p0.v), "l"(p1.v), "l"(p2.v), "l"(p3.v));
-    return r;
-}
+using namespace fp4;
 
 // ------------------------------------------------------------------------------------------------ FP8 block
 constexpr int NC = 8;
@@ -124,29 +96,6 @@ __global__ void __launch_bounds__(256, 3) block_fp8_fast_kernel(const TileParams
 // thread = U2 groups of 16 contiguous elements; warp = 512 contiguous columns per step; CTA = 8 rows
 constexpr int U2 = 2;
 
-// fast path: reciprocal normal (s_eff >= 2^-100) and no quotient of a non-zero bf16 (>= 2^-133) underflows to zero
-// (s_eff <= 2^16): an underflowed -0.0 would keep its sign through the fused "+ 0.0", the reference's two-step
-// (divide, then add the zero-point) turns it into +0.0.
-__device__ __forceinline__ bool fp4_scale_is_safe(float s_eff) { return s_eff >= 7.8886090522101181e-31f && s_eff <= 65536.0f; }
-
-__device__ __noinline__ uint32_t fix_group_fp4(const uint4 raw, float s_eff, uint32_t packed) {
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-    Bracket br;
-    br.init(s_eff);
-    float rl, rh, dummy;
-    unpack2(br.lo, rl, dummy);
-    unpack2(br.hi, rh, dummy);
-    const bool all = !fp4_scale_is_safe(s_eff);
-#pragma unroll 1
-    for (int e = 0; e < 8; e++) {
-        const uint32_t half = (e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16);
-        const float x = __uint_as_float(half);
-        const uint32_t ca = cvt_e2m1x2(0.0f, __fmaf_rn(x, rl, 0.0f)), cb = cvt_e2m1x2(0.0f, __fmaf_rn(x, rh, 0.0f));
-        if (all || ca != cb) packed = (packed & ~(0xfu << (4 * e))) | (quant_fp4(x, s_eff) << (4 * e));
-    }
-    return packed;
-}
-
 __global__ void __launch_bounds__(256, 4) nvfp4_fast_kernel(const GroupParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row = (int64_t)blockIdx.y * 8 + warp;
@@ -216,8 +165,6 @@ constexpr int FP4_THREADS = 256;
 constexpr int FP4_UF = 4;                                   // groups per thread per tile
 constexpr int FP4_TILE_GROUPS = FP4_THREADS * FP4_UF;       // 1024 groups = 32 KB of bf16 per CTA tile
 
-struct Fp4Entry { float r_lo, r_hi, s_eff, unsafe; };
-
 __device__ __forceinline__ void fp4_build_table(Fp4Entry* table, float gs) {
     if (threadIdx.x < 128) {
         // code 0 (scale rounds to zero) is replaced by 0.125 = code 0x20 (helpers.py:101-126); 0x7f is NaN, never produced
@@ -247,17 +194,6 @@ __device__ __forceinline__ void fp4_load_tile(uint4 (&raw)[FP4_UF][2], const uin
 }
 __device__ __forceinline__ uint32_t fp4_group_absmax2(const uint4 (&r)[2]) {  // packed bf16x2 |max| of 16 elements
     return hmaxabs2(hmaxabs2(hmaxabs2(r[0].x, r[0].y), hmaxabs2(r[0].z, r[0].w)), hmaxabs2(hmaxabs2(r[1].x, r[1].y), hmaxabs2(r[1].z, r[1].w)));
-}
-
-// exact bf16(absmax / 6) from the bf16 |max| bits (<< 16): bracketed constant reciprocal, IEEE fallback when the two ends
-// round apart or the operand is outside [2^-100, 2^100] (zero is fine: both products are 0)
-__device__ __forceinline__ float fp4_loc_scale(uint32_t abits) {
-    const float a = __uint_as_float(abits);
-    const float lo = __fmul_rn(a, (1.0f / 6.0f) * 0.99999952316284179688f), hi = __fmul_rn(a, (1.0f / 6.0f) * 1.00000047683715820312f);
-    const uint32_t u = cvt_bf16x2(hi, lo);
-    const bool in_range = (abits - 0x0d800000u) <= (0x71800000u - 0x0d800000u) || abits == 0;
-    if (in_range && (u >> 16) == (u & 0xffffu)) return __uint_as_float(u << 16);
-    return round_to<DT_BF16>(__fdiv_rn(a, 6.0f));
 }
 
 // one 1024-group tile of one matrix, already in registers: scale codes + packed e2m1 out
@@ -322,19 +258,12 @@ __global__ void __launch_bounds__(FP4_THREADS) nvfp4_flat_kernel(const GroupPara
 // counter is already complete; the launch does not DEPEND on that: a B-CTA that waits too long reduces the span itself, so it
 // never blocks on a CTA that has not been scheduled.
 // sync words (zeroed by the launcher): per span {|max| bits, finished A items}.
-constexpr int FP4_NT = 4;
 struct Fp4FusedParams {
     int64_t groups_per_mat;
-    int32_t tiles_per_mat, items_per_mat, span, n_spans, lookahead;
+    int32_t tiles_per_mat, items_per_mat, span, n_spans, lookahead, nt;
     uint32_t* sync;
     float* gs_out;  // [batch]
 };
-
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // |max| bits of tiles [tile0, tile1) of one matrix, reduced over the CTA (valid in thread 0)
 __device__ __forceinline__ uint32_t fp4_absmax_tiles(const uint4* wbase, int tile0, int tile1, int64_t groups_per_mat, uint32_t* s_red) {
@@ -373,7 +302,7 @@ __global__ void __launch_bounds__(FP4_THREADS, 4) nvfp4_fused_kernel(const Group
     else { const int r = k - Lh; is_b = (r & 1) == 0; s = is_b ? r / 2 : Lh + r / 2; }
     const int mi = j / f.items_per_mat, item = j - mi * f.items_per_mat;
     const int64_t m = (int64_t)s * f.span + mi;
-    const int tile0 = item * FP4_NT, tile1 = min(tile0 + FP4_NT, f.tiles_per_mat);
+    const int tile0 = item * f.nt, tile1 = min(tile0 + f.nt, f.tiles_per_mat);
     uint32_t* st = f.sync + 2 * s;
     const uint4* wbase = reinterpret_cast<const uint4*>((const char*)p.w + m * f.groups_per_mat * 32);
     if (!is_b) {
@@ -419,7 +348,14 @@ __global__ void __launch_bounds__(FP4_THREADS, 4) nvfp4_fused_kernel(const Group
         fp4_compress_tile(table, gs, wbase, sbase, obase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, f.groups_per_mat);
 }
 
+
 }  // namespace
+
+// tuning knob read from the environment (development sweeps); `dflt` when unset
+static int tune_env(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
 
 int launch_block_fp8_fast(const TileParams& p, int64_t batch, cudaStream_t st) {
     if (p.cols % 8 != 0 || (((uintptr_t)p.w) & 15) != 0 || batch * p.rows * p.cols == 0) return B200Q_ENOSYS;
@@ -452,7 +388,8 @@ int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_
     if (span < 1 || batch % span != 0) return B200Q_ENOSYS;
     const int64_t groups_per_mat = p.rows * (p.cols >> 4);
     const int64_t tiles = (groups_per_mat + FP4_TILE_GROUPS - 1) / FP4_TILE_GROUPS;
-    const int64_t items = (tiles + FP4_NT - 1) / FP4_NT;
+    const int nt = tune_env("B200Q_FP4_NT", 4);
+    const int64_t items = (tiles + nt - 1) / nt;
     const int64_t n_spans = batch / span;
     const int64_t grid = 2 * n_spans * items * span;
     if (tiles >= (1ll << 30) || grid >= (1ll << 31)) return B200Q_ENOSYS;
@@ -463,7 +400,8 @@ int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_
     f.span = span;
     f.n_spans = (int)n_spans;
     const int64_t span_bytes = groups_per_mat * 32 * span;
-    f.lookahead = (int)max((int64_t)1, min(n_spans, (int64_t)(14ll << 20) / max(span_bytes, (int64_t)1)));
+    f.nt = nt;
+    f.lookahead = (int)max((int64_t)1, min(n_spans, ((int64_t)tune_env("B200Q_FP4_LOOKAHEAD_MB", 14) << 20) / max(span_bytes, (int64_t)1)));
     f.sync = sync;
     f.gs_out = gs_out;
     cudaMemsetAsync(sync, 0, sizeof(uint32_t) * 2 * n_spans, st);

@@ -432,7 +432,7 @@ def compress_weight(weight: torch.Tensor, args, global_scale: Optional[torch.Ten
     if global_scale is None:
         # NVFP4 siblings stacked next to each other (gate/up of one expert: fuse_span = 2) share min(global_scale)
         gs = torch.empty(batch, dtype=torch.float32, device=dev)
-        ws = torch.empty(2 * max(batch // max(int(fuse_span), 1), 1), dtype=torch.int32, device=dev)
+        ws = torch.empty(max(int(lib.b200q_compress_nvfp4_workspace(batch, rows, cols, int(fuse_span))) // 4, 2), dtype=torch.int32, device=dev)
         L.check(lib.b200q_compress_nvfp4_fused(L.ptr(w), batch, rows, cols, L.DTYPE_CODE[w.dtype], int(fuse_span), L.ptr(gs), L.ptr(packed),
                                                L.ptr(scale), L.ptr(ws), ws.numel() * 4, st))
         return {"weight_packed": packed, "weight_scale": scale.view(_FP8), "weight_global_scale": gs.reshape(lead + (1,))}

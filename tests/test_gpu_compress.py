@@ -89,11 +89,15 @@ def test_nvfp4_supplied_global_scale():
     _cmp_sd(got, want, "nvfp4 gs")
 
 
-@pytest.mark.parametrize("E,R,C,span", [(6, 36, 512, 2), (64, 768, 2048, 2), (9, 200, 1040, 3), (3, 2048, 768, 1)])
-def test_nvfp4_fused_sibling_global_scale(E, R, C, span):
-    """gate/up siblings stacked next to each other share min(global_scale) (LLMC update_fused_layer_weight_global_scales); the
-    ticketed persistent kernel (|max| tiles ahead of compress tiles) must equal the oracle run with that shared scale."""
+@pytest.mark.parametrize("persistent", ["0", "1"])
+@pytest.mark.parametrize("E,R,C,span", [(6, 36, 512, 2), (64, 768, 2048, 2), (9, 200, 1040, 3), (3, 2048, 768, 1), (320, 256, 2048, 2)])
+def test_nvfp4_fused_sibling_global_scale(E, R, C, span, persistent, monkeypatch):
+    """gate/up siblings stacked next to each other share min(global_scale) (LLMC update_fused_layer_weight_global_scales); both
+    schedulings of the single-launch kernel (one CTA per item with the |max| pass running ahead; persistent warp-specialised CTA
+    per SM, B200Q_FP4_PERSISTENT=1) must equal the oracle run with that shared scale."""
     from quantizers_b200 import ops
+
+    monkeypatch.setenv("B200Q_FP4_PERSISTENT", persistent)
 
     ws = [(synth_weight(R, C, torch.bfloat16, 300 + e, edge=R >= 64) * (1.0 + 0.37 * e)).to(torch.bfloat16) for e in range(E)]
     got = ops.compress_weight(torch.stack(ws).cuda(), Args("nvfp4"), fuse_span=span)
