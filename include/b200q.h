@@ -106,6 +106,15 @@ int b200q_compress_nvfp4_fused(const void* weight, int64_t batch, int64_t rows, 
 /* O1: min / max per quantization chunk (flatten_for_calibration + amin/amax).  mn, mx: T, qparam-grid shaped. */
 int b200q_minmax(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* scheme, void* mn,
                  void* mx, void* stream);
+/* O4: MSE observer (LLMC observers/mse.py `mse`; defaults maxshrink 0.2, patience 5, grid 100, norm 2.4).  For every
+ * quantization chunk (GROUP / TENSOR_GROUP: group_size consecutive elements of a row; CHANNEL: a row) the (min, max) range is
+ * shrunk by p = 1 - i/grid, i < int(maxshrink * grid), and the range with the smallest sum |fake_quantize(x) - x|^norm is kept,
+ * with the reference's tensor-wide early stop (`patience` steps without an improvement in any chunk; per batch entry).
+ * mn, mx: T, qparam-grid shaped, feed b200q_calculate_qparams.  global_scale: fp32[1] for NVFP4 (TENSOR_GROUP), else NULL.
+ * workspace: device scratch of >= 4 * (number of chunks + batch) bytes.  One HBM read of the weight. */
+int b200q_mse_minmax(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* scheme,
+                     const float* global_scale, float maxshrink, int32_t patience, int32_t grid, float norm, void* mn, void* mx,
+                     void* workspace, int64_t workspace_bytes, void* stream);
 /* O2 + Q2: per-tensor global scale = generate_gparam(min, max) -> fp32 [batch].
  * Also O3 (static_minmax activation global scale): pass running != 0 to fold the previous min/max kept in
  * minmax_state (fp32 [batch,2], initialise to {+inf,-inf}) before deriving the scale. */

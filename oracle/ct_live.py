@@ -116,6 +116,43 @@ def fake_quantize(w, scale, zp, args, gs=None):
     return fq(w, scale, zp, args, global_scale=gs)
 
 
+def mse_minmax(w: torch.Tensor, args, gs: torch.Tensor | None = None, maxshrink: float = 0.2, patience: int = 5, grid: float = 100.0,
+               norm: float = 2.4):
+    """llmcompressor observers/mse.py::_grid_search_mse restated on the LIVE compressed-tensors calls (calculate_qparams,
+    fake_quantize with the strategy patched to TOKEN, as upstream does): only the loop and the reductions are re-typed."""
+    import copy
+
+    from compressed_tensors.quantization import QuantizationStrategy
+    from compressed_tensors.quantization.utils.helpers import calculate_qparams
+
+    observed = flatten_weight(w, args)
+    min_val, max_val = torch.amin(observed, dim=(0, -1)), torch.amax(observed, dim=(0, -1))
+    best_error = torch.full_like(min_val, torch.finfo(min_val.dtype).max)
+    best_min, best_max = min_val.clone(), max_val.clone()
+    token_args = copy.deepcopy(args)
+    token_args.strategy = QuantizationStrategy.TOKEN
+    no_improve = 0
+    for i in range(int(maxshrink * grid)):
+        p = 1 - i / grid
+        smin, smax = p * min_val, p * max_val
+        scales, zps = calculate_qparams(min_vals=smin, max_vals=smax, quantization_args=args, global_scale=gs)
+        q = fake_quantize(observed, scales.unsqueeze(-1), zps.unsqueeze(-1), token_args, gs).to(observed.dtype)
+        q -= observed
+        q.abs_()
+        q.pow_(norm)
+        err = torch.sum(q, dim=(0, -1))
+        better = err < best_error
+        if torch.any(better):
+            best_error[better] = err[better]
+            best_min[better], best_max[better] = smin[better], smax[better]
+            no_improve = 0
+        else:
+            no_improve += 1
+            if no_improve >= patience:
+                break
+    return best_min, best_max
+
+
 # ----------------------------------------------------------------------------- canonical format table
 FORMATS = {
     # name: (compressor format, qtype, num_bits, symmetric, strategy, group, block)

@@ -61,25 +61,33 @@ def activation_global_scale(batches: Sequence[torch.Tensor]) -> torch.Tensor:
 
 
 def mse_minmax(w: torch.Tensor, geom: O.Geom, qtype: int, num_bits: int, symmetric: bool, maxshrink: float = 0.2,
-               patience: int = 5, grid: int = 100, norm: float = 2.4):
-    """observers/mse.py: shrink the (min, max) range on a grid, keep per-chunk the range with the smallest
-    sum |q - x|^norm; early stop after `patience` rounds without any improvement.  GROUP / CHANNEL geometries."""
+               patience: int = 5, grid: int = 100, norm: float = 2.4, global_scale: Optional[torch.Tensor] = None):
+    """observers/mse.py ``_grid_search_mse``: shrink the (min, max) range on a grid, keep per chunk the range with the smallest
+    ``sum |q - x|^norm``; stop after ``patience`` rounds without an improvement in ANY chunk.  GROUP / CHANNEL geometries.
+
+    Dtype chain as upstream's in-place ops on the observed tensor's dtype T: ``p * min`` rounds to T, ``q -= x``, ``abs_``,
+    ``pow_(norm)`` each round to T, ``torch.sum`` accumulates in fp32 and rounds to T, ``err < best_error`` compares in T
+    (``best_error`` starts at finfo(T).max).  The fake-quantize uses one (scale, zero_point) per chunk -- upstream patches the
+    strategy to TOKEN for this; with the chunk's qparams that is the GROUP / CHANNEL fake-quantize of the pinned arithmetic."""
     mn, mx = O.minmax(w, geom)
-    best = torch.full(mn.shape, float("inf"))
+    best = torch.full(mn.shape, torch.finfo(w.dtype).max, dtype=w.dtype)
     bmn, bmx = mn.clone(), mx.clone()
     R, C = w.shape
     gsz = geom.group if geom.strategy == O.GROUP else C
     no_improve = 0
     for i in range(int(maxshrink * grid)):
         p = 1 - i / grid
-        pmn, pmx = (p * mn.float()).to(w.dtype), (p * mx.float()).to(w.dtype)
-        s, z = O.calculate_qparams(pmn, pmx, qtype, num_bits, symmetric)
-        q = O.fake_quantize(w, s, z if qtype == O.INT else torch.zeros(1), geom, qtype, num_bits)
-        err = (q.float() - w.float()).abs().pow(norm).reshape(R, -1, gsz).sum(-1).reshape(mn.shape)
+        pmn, pmx = p * mn, p * mx
+        s, z = O.calculate_qparams(pmn, pmx, qtype, num_bits, symmetric, global_scale)
+        q = O.fake_quantize(w, s, z, geom, qtype, num_bits, global_scale)
+        q -= w
+        q.abs_()
+        q.pow_(norm)
+        err = torch.sum(q.reshape(R, -1, gsz), dim=-1).reshape(mn.shape)
         better = err < best
         if better.any():
-            best = torch.where(better, err, best)
-            bmn, bmx = torch.where(better, pmn, bmn), torch.where(better, pmx, bmx)
+            best[better] = err[better]
+            bmn[better], bmx[better] = pmn[better], pmx[better]
             no_improve = 0
         else:
             no_improve += 1

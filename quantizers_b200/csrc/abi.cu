@@ -177,6 +177,22 @@ int b200q_minmax(const void* weight, int64_t batch, int64_t rows, int64_t cols, 
                          (cudaStream_t)stream);
 }
 
+int b200q_mse_minmax(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* sc, const float* global_scale,
+                     float maxshrink, int32_t patience, int32_t grid, float norm, void* mn, void* mx, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
+    if (int rc = check_scheme(sc)) return rc;
+    REQ_PTR(weight); REQ_PTR(mn); REQ_PTR(mx); REQ_PTR(workspace);
+    B200Q_REQUIRE(sc->strategy == B200Q_GROUP || sc->strategy == B200Q_CHANNEL, "mse observer: GROUP / TENSOR_GROUP / CHANNEL strategies only");
+    const int64_t len = sc->strategy == B200Q_CHANNEL ? cols : sc->group_size;
+    B200Q_REQUIRE(len > 0 && cols % len == 0, "tensor column shape must be divisible by the given group_size %lld but got %lld",
+                  (long long)len, (long long)cols);
+    const int64_t n_chunks = batch * rows * (cols / len);
+    B200Q_REQUIRE(workspace_bytes >= 4 * (n_chunks + batch) && (((uintptr_t)workspace) & 3) == 0,
+                  "mse observer: workspace of %lld bytes needed", (long long)(4 * (n_chunks + batch)));
+    return launch_mse_minmax(sc->dtype, sc->qtype, sc->num_bits, sc->symmetric, sc->strategy, sc->group_size, weight, batch, rows, cols,
+                             global_scale, maxshrink, patience, grid, norm, mn, mx, (uint32_t*)workspace, (cudaStream_t)stream);
+}
+
 int b200q_global_scale(const void* x, int64_t batch, int64_t numel, int32_t dtype, float* minmax_state, int32_t running,
                        float* global_scale, void* stream) {
     REQ_PTR(x); REQ_PTR(minmax_state);

@@ -57,6 +57,11 @@ int launch_span_min(float* gs, int64_t batch, int span, cudaStream_t st);
 int launch_qparams(int dt, int qt, int nbits, int symmetric, const void* mn, const void* mx, int64_t n, const float* gs,
                    void* scale, int8_t* zp, cudaStream_t st);
 
+// O4: workspace = uint32 [n_chunks + batch]
+int launch_mse_minmax(int dt, int qt, int nbits, int symmetric, int strategy, int group, const void* w, int64_t batch, int64_t rows,
+                      int64_t cols, const float* gs, float maxshrink, int patience, int grid_n, float norm, void* mn, void* mx,
+                      uint32_t* workspace, cudaStream_t st);
+
 // ---- pack / unpack (pack.cu)
 int launch_pack_int32(const int8_t* v, int64_t rows, int64_t cols, int nbits, int packed_dim, int32_t* out, cudaStream_t st);
 int launch_unpack_int32(const int32_t* p, int64_t rows, int64_t cols, int nbits, int packed_dim, int8_t* out, cudaStream_t st);

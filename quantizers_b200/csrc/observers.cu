@@ -189,6 +189,131 @@ int launch_minmax(int dt, const void* w, int64_t batch, int64_t rows, int64_t co
     return B200Q_OK;
 }
 
+// ---- O4 MSE observer  (LLMC observers/mse.py, restated in SURVEY.md Appendix A)
+// Per quantization chunk (GROUP: g consecutive elements of a row, CHANNEL: a row): for i < n_steps, p = 1 - i / grid:
+//     (s, z) = calculate_qparams(T(p * min), T(p * max));  q = fake_quantize(x, s, z)  [strategy patched to TOKEN: one qparam per chunk]
+//     err    = T(sum over the chunk of T(|T(q - x)| ^ norm))          -- the reference's in-place chain on tensors of dtype T
+//     keep (T(p * min), T(p * max)) where err < best
+// and a TENSOR-wide early stop after `patience` consecutive steps without an improvement in ANY chunk.  The early stop only cuts
+// the tail of every chunk's search, so one pass computes each chunk's "improved at step i" bit mask for all steps plus the OR of
+// the masks over the tensor; the select kernel derives the stop index from the OR and picks each chunk's last improvement before
+// it.  The weight is read from HBM once; the search itself is ALU/MUFU work (n_steps fake-quantize + pow per element).
+template <int DT, int QT>
+__global__ void __launch_bounds__(256) mse_search_kernel(const void* __restrict__ w, int64_t n_chunks, int64_t chunks_per_batch, int len,
+                                                         int lanes, int nbits, int symmetric, const float* __restrict__ gs_ptr,
+                                                         int n_steps, int grid_n, float norm, void* __restrict__ mn_out,
+                                                         void* __restrict__ mx_out, uint32_t* __restrict__ mask_out,
+                                                         uint32_t* __restrict__ gmask) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / lanes, sl = lane % lanes;            // sub-warp and lane within it
+    const int per_warp = 32 / lanes;
+    const int64_t chunk = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * per_warp + sub;
+    const bool live = chunk < n_chunks;
+    const int64_t base = (live ? chunk : 0) * (int64_t)len;
+    const float lo = (QT == QT_INT) ? -(float)(1 << (nbits - 1)) : (QT == QT_FP8 ? -448.0f : -6.0f);
+    const float hi = (QT == QT_INT) ? (float)((1 << (nbits - 1)) - 1) : (QT == QT_FP8 ? 448.0f : 6.0f);
+    const float gs = gs_ptr ? gs_ptr[0] : 1.0f;
+    // Tensor.pow_(python float) casts the exponent to the tensor dtype first (ATen PowKernel: exp_scalar.to<scalar_t>()): a bf16
+    // tensor is raised to 2.40625, an fp16 one to 2.400390625
+    const float nrm = round_to<DT>(norm);
+    // raw min / max of the chunk
+    float mn = INFINITY, mx = -INFINITY;
+    for (int e = sl; e < len; e += lanes) {
+        const float x = load_T<DT>(w, base + e);
+        mn = fminf(mn, x);
+        mx = fmaxf(mx, x);
+    }
+    mn = subwarp_min(mn, lanes);
+    mx = subwarp_max(mx, lanes);
+    uint32_t mask = 0;
+    float best = DT == DT_F16 ? 65504.0f : (DT == DT_BF16 ? 3.3895313892515355e38f : 3.4028234663852886e38f);  // finfo(T).max
+    for (int i = 0; i < n_steps; i++) {
+        const float p = (float)(1.0 - (double)i / (double)grid_n);
+        const float pmn = round_to<DT>(fmul(p, mn)), pmx = round_to<DT>(fmul(p, mx));
+        const float cmn = fminf(pmn, 0.0f), cmx = fmaxf(pmx, 0.0f);
+        float s, z = 0.0f;
+        if (QT == QT_FP4) {
+            qparams_fp4<DT>(fmaxf(fabsf(cmn), fabsf(cmx)), gs, s);  // s = s_eff
+        } else if (symmetric) {
+            s = scale_sym<DT>(fmaxf(fabsf(cmn), fabsf(cmx)), (hi - lo) * 0.5f);
+        } else {
+            qparams_asym<DT>(cmn, cmx, lo, hi, s, z);
+        }
+        float err = 0.0f;
+        for (int e = sl; e < len; e += lanes) {
+            const float x = load_T<DT>(w, base + e);  // L1-resident after the min/max pass
+            float q;
+            if (QT == QT_INT) q = fq_int<DT>(x, s, z, true, lo, hi);
+            else if (QT == QT_FP8) q = fq_fp8<DT>(x, s, true);
+            else q = fq_fp4<DT>(x, s);
+            const float d = fabsf(round_to<DT>(fadd(q, -x)));
+            err = fadd(err, round_to<DT>(powf(d, nrm)));
+        }
+        for (int o = lanes >> 1; o > 0; o >>= 1) err = fadd(err, __shfl_xor_sync(0xffffffffu, err, o));
+        err = round_to<DT>(err);
+        if (err < best) { best = err; mask |= 1u << i; }
+    }
+    if (live && sl == 0) {
+        store_T<DT>(mn_out, chunk, mn);
+        store_T<DT>(mx_out, chunk, mx);
+        mask_out[chunk] = mask;
+        atomicOr(&gmask[chunk / chunks_per_batch], mask);
+    }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) mse_select_kernel(int64_t n_chunks, int64_t chunks_per_batch, int n_steps, int grid_n, int patience,
+                                                         const uint32_t* __restrict__ mask_in, const uint32_t* __restrict__ gmask,
+                                                         void* __restrict__ mn_io, void* __restrict__ mx_io) {
+    const int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk >= n_chunks) return;
+    const uint32_t any = gmask[chunk / chunks_per_batch];
+    int executed = n_steps, quiet = 0;
+    for (int i = 0; i < n_steps; i++) {
+        if (any & (1u << i)) quiet = 0;
+        else if (++quiet >= patience) { executed = i + 1; break; }
+    }
+    const uint32_t sel = mask_in[chunk] & (executed >= 32 ? 0xffffffffu : ((1u << executed) - 1u));
+    if (sel == 0) return;  // nothing beat finfo.max: the un-shrunk range stays
+    const int i = 31 - __clz(sel);
+    const float p = (float)(1.0 - (double)i / (double)grid_n);
+    store_T<DT>(mn_io, chunk, round_to<DT>(fmul(p, load_T<DT>(mn_io, chunk))));
+    store_T<DT>(mx_io, chunk, round_to<DT>(fmul(p, load_T<DT>(mx_io, chunk))));
+}
+
+int launch_mse_minmax(int dt, int qt, int nbits, int symmetric, int strategy, int group, const void* w, int64_t batch, int64_t rows,
+                      int64_t cols, const float* gs, float maxshrink, int patience, int grid_n, float norm, void* mn, void* mx,
+                      uint32_t* workspace, cudaStream_t st) {
+    B200Q_REQUIRE(strategy == ST_GROUP || strategy == ST_CHANNEL, "mse observer: GROUP / TENSOR_GROUP / CHANNEL strategies only");
+    B200Q_REQUIRE(grid_n > 0 && patience > 0, "mse observer: grid and patience must be positive");
+    const int n_steps = (int)(maxshrink * (float)grid_n);
+    B200Q_REQUIRE(n_steps >= 1 && n_steps <= 32, "mse observer: int(maxshrink * grid) must be in [1, 32], got %d", n_steps);
+    B200Q_REQUIRE(symmetric || qt == QT_INT, "Asymmetric Quantization is not supported for FP4/FP8 here");
+    B200Q_REQUIRE(qt != QT_FP4 || gs, "mse observer: NVFP4 needs the global scale");
+    if (batch * rows * cols == 0) return B200Q_OK;
+    const int len = strategy == ST_CHANNEL ? (int)cols : group;
+    B200Q_REQUIRE(len > 0 && cols % len == 0, "tensor column shape must be divisible by the given group_size %d but got %lld", len, (long long)cols);
+    const int64_t chunks_per_batch = rows * (cols / len), n_chunks = batch * chunks_per_batch;
+    int lanes = 32;
+    while (lanes > 1 && lanes * 4 > len) lanes >>= 1;  // >= 4 elements per lane
+    const int per_cta = 8 * (32 / lanes);
+    uint32_t* gmask = workspace + n_chunks;
+    cudaMemsetAsync(gmask, 0, sizeof(uint32_t) * batch, st);
+    const unsigned g1 = (unsigned)((n_chunks + per_cta - 1) / per_cta);
+    B200Q_DISPATCH_DT(dt, {
+        switch (qt) {
+        case QT_INT: mse_search_kernel<DT, QT_INT><<<g1, 256, 0, st>>>(w, n_chunks, chunks_per_batch, len, lanes, nbits, symmetric, gs, n_steps, grid_n, norm, mn, mx, workspace, gmask); break;
+        case QT_FP8: mse_search_kernel<DT, QT_FP8><<<g1, 256, 0, st>>>(w, n_chunks, chunks_per_batch, len, lanes, nbits, symmetric, gs, n_steps, grid_n, norm, mn, mx, workspace, gmask); break;
+        case QT_FP4: mse_search_kernel<DT, QT_FP4><<<g1, 256, 0, st>>>(w, n_chunks, chunks_per_batch, len, lanes, nbits, symmetric, gs, n_steps, grid_n, norm, mn, mx, workspace, gmask); break;
+        default: set_error("bad qtype %d", qt); return B200Q_EINVAL;
+        }
+    });
+    B200Q_CHECK_LAUNCH();
+    B200Q_DISPATCH_DT(dt, { mse_select_kernel<DT><<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(n_chunks, chunks_per_batch, n_steps, grid_n, patience, workspace, gmask, mn, mx); });
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
 // ---- Q1 calculate_qparams
 template <int DT, int QT>
 __global__ void __launch_bounds__(256) qparams_kernel(const void* __restrict__ mn_in, const void* __restrict__ mx_in, int64_t n,

@@ -156,6 +156,35 @@ class MovingAverageMinMaxObserver(Observer):
         return prev_min + c * (mn - prev_min), prev_max + c * (mx - prev_max)
 
 
+class _MSEMixin:
+    """Shrink-grid MSE range search (LLMC observers/mse.py ``_grid_search_mse``; maxshrink 0.2, patience 5, grid 100, norm 2.4,
+    overridable through ``observer_kwargs``) in place of the plain amin / amax: ``ops.observe_mse_minmax`` evaluates all grid
+    points of every quantization chunk in one pass over the weight.  Global (per-tensor) statistics stay plain min / max."""
+
+    def _observe(self, observed: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        L.require_cuda(observed)
+        if self.base_name != "weight":
+            raise NotImplementedError("mse observers are implemented for weights (GROUP / TENSOR_GROUP / CHANNEL)")
+        gs = getattr(self.module, f"{self.base_name}_global_scale", None) if self.module is not None else None
+        kw = self.kwargs
+        return ops.observe_mse_minmax(observed, self.args, global_scale=gs, maxshrink=float(kw.get("maxshrink", 0.2)),
+                                      patience=int(kw.get("patience", 5)), grid=int(float(kw.get("grid", 100.0))),
+                                      norm=float(kw.get("norm", 2.4)))
+
+
+@Observer.register("memoryless_mse")
+class MemorylessMSEObserver(_MSEMixin, MemorylessMinMaxObserver):
+    """MSE-selected range, no state."""
+
+    def sync(self, group=None):
+        raise L.B200QError("mse ranges are not min/max statistics: they cannot be combined across shards")
+
+
+@Observer.register("mse")
+class MovingAverageMSEObserver(_MSEMixin, MovingAverageMinMaxObserver):
+    """MSE-selected range folded into an exponential moving average (first observation taken as is)."""
+
+
 def _allreduce_minmax(obs: Observer, group=None):
     import torch.distributed as dist
 

@@ -306,6 +306,34 @@ def observe_minmax(weight: torch.Tensor, args):
     return mn, mx
 
 
+@torch.no_grad()
+def observe_mse_minmax(weight: torch.Tensor, args, global_scale: Optional[torch.Tensor] = None, maxshrink: float = 0.2,
+                       patience: int = 5, grid: int = 100, norm: float = 2.4):
+    """LLMC ``mse`` observer statistics (observers/mse.py): per quantization chunk the shrunk (min, max) range
+    ``p * (min, max)``, ``p = 1 - i/grid`` for ``i < int(maxshrink * grid)``, with the smallest ``sum |fake_quantize(x) - x|^norm``;
+    tensor-wide early stop after ``patience`` steps without any improvement.  GROUP / TENSOR_GROUP / CHANNEL strategies."""
+    L.require_cuda(weight, global_scale)
+    w = weight.contiguous()
+    strat = _strategy_code(args)
+    if strat not in (L.GROUP, L.CHANNEL):
+        raise NotImplementedError("mse observer: GROUP / TENSOR_GROUP / CHANNEL strategies only")
+    w2, batch = _as2d(w)
+    rows, cols = w.shape[-2], w.shape[-1]
+    sc = scheme_from_args(args, w.dtype)
+    if strat == L.CHANNEL:
+        shp = (*w.shape[:-1], 1)
+    else:
+        if cols % args.group_size != 0:
+            raise B200QError(f"tensor column shape must be divisble by the given group_size {args.group_size} but got {cols}")
+        shp = (*w.shape[:-1], cols // args.group_size)
+    mn = torch.empty(shp, dtype=w.dtype, device=w.device)
+    mx = torch.empty(shp, dtype=w.dtype, device=w.device)
+    ws = torch.empty(mn.numel() + batch, dtype=torch.int32, device=w.device)
+    L.check(L.lib().b200q_mse_minmax(L.ptr(w), batch, rows, cols, ctypes.byref(sc), L.ptr(_gs(global_scale)), float(maxshrink), int(patience),
+                                     int(grid), float(norm), L.ptr(mn), L.ptr(mx), L.ptr(ws), ws.numel() * 4, L.stream_ptr(w.device)))
+    return mn, mx
+
+
 # ----------------------------------------------------------------------------- pack / unpack
 @torch.no_grad()
 def pack_to_int32(value: torch.Tensor, num_bits: int, packed_dim: int = 1) -> torch.Tensor:

@@ -64,3 +64,54 @@ def test_activation_static_global_scale():
     assert gs.item() == want.item()
     with pytest.raises(ValueError):
         obs(torch.zeros(0, 256, dtype=torch.bfloat16).cuda())
+
+
+MSE_CASES = [("int4_g128_asym", O.Geom(O.GROUP, 128), O.INT, 4, False), ("int4_g32_sym", O.Geom(O.GROUP, 32), O.INT, 4, True),
+             ("int4_channel_sym", O.Geom(O.CHANNEL, 0), O.INT, 4, True), ("fp8_g128", O.Geom(O.GROUP, 128), O.FP8, 8, True),
+             ("fp8_channel", O.Geom(O.CHANNEL, 0), O.FP8, 8, True)]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("name,geom,qtype,nb,sym", MSE_CASES)
+def test_mse_observer_matches_oracle(name, geom, qtype, nb, sym, dtype):
+    """O4: the one-pass CUDA grid search picks the restated observer's (min, max) per chunk (bit-identical on the B200 runs so
+    far, including torch's quirk of rounding the exponent 2.4 to the tensor dtype).  The selection hangs on ``err < best``
+    between sums of |q - x|^norm whose fp32 pow / summation order may differ in the last bit between libm and CUDA; after the
+    rounding to T that could flip a near-tie, so the floating-point tolerance is stated as: >= 99.5 % identical chunks and, where
+    the pick differs, a neighbouring grid point (ranges within 2 % of each other)."""
+    from quantizers_b200 import ops
+
+    w = synth_weight(96, 640 if geom.strategy == O.GROUP else 384, dtype, 21)
+    rmn, rmx = R.mse_minmax(w, geom, qtype, nb, sym)
+    gmn, gmx = ops.observe_mse_minmax(w.cuda(), Args(name))
+    gmn, gmx = gmn.cpu().reshape(rmn.shape), gmx.cpu().reshape(rmx.shape)
+    same = (gmn == rmn) & (gmx == rmx)
+    assert same.float().mean().item() >= 0.995, f"{name}/{dtype}: only {same.float().mean().item():.4f} of the chunks agree"
+    span_r, span_g = (rmx.float() - rmn.float()), (gmx.float() - gmn.float())
+    assert torch.all((span_g - span_r).abs() <= 0.021 * span_r.abs() + 1e-30)
+    raw_mn, raw_mx = O.minmax(w, geom)
+    assert not torch.equal(rmn, raw_mn) or not torch.equal(rmx, raw_mx), "the search must shrink some range"
+
+
+def test_mse_observer_early_stop_and_registry():
+    """Weights that sit on the int4 grid of the un-shrunk range (scale exactly 0.25; only the range-defining 7.5 * s element is
+    clamped): every shrink makes things worse, nothing improves after p = 1, the tensor-wide early stop ends the search after
+    `patience` steps and the raw range is kept; the registry serves the observer under the reference's names."""
+    from quantizers_b200.observers import Observer
+
+    g = torch.Generator().manual_seed(3)
+    codes = torch.randint(-7, 8, (32, 256), generator=g).float()
+    codes[:, 0::128] = 7.5   # |max| = 1.875 -> scale = 1.875 / 7.5 = 0.25 exactly
+    w = (codes * 0.25).to(torch.bfloat16)
+    geom = O.Geom(O.GROUP, 128)
+    rmn, rmx = R.mse_minmax(w, geom, O.INT, 4, True)
+    raw_mn, raw_mx = O.minmax(w, geom)
+    assert torch.equal(rmn, raw_mn) and torch.equal(rmx, raw_mx)
+    obs = Observer.load_from_registry("memoryless_mse", base_name="weight", args=Args("int4_g128_sym"))
+    mn, mx = obs.get_min_max(w.cuda())
+    assert_bits_equal(mn.reshape(rmn.shape), rmn, "mse min")
+    assert_bits_equal(mx.reshape(rmx.shape), rmx, "mse max")
+    scale, zp = Observer.load_from_registry("mse", base_name="weight", args=Args("int4_g128_sym"))(w.cuda())
+    s_ref, _ = O.calculate_qparams(rmn, rmx, O.INT, 4, True)
+    assert_bits_equal(scale.reshape(s_ref.shape), s_ref, "mse scale")
+    assert {"mse", "memoryless_mse"} <= set(Observer.registered_names())

@@ -59,3 +59,20 @@ def test_dequantize_roundtrip_live():
             got = O.dequantize(vals, sd["weight_scale"].to(torch.bfloat16), None, geom, qtype, sd["weight_global_scale"],
                                out_dtype=torch.bfloat16)
         assert_bits_equal(got, ref["weight"], name)
+
+
+@pytest.mark.parametrize("name", ["int4_g128_asym", "int4_g32_sym", "int4_channel_sym", "fp8_g128", "fp8_channel"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_mse_observer_live(name, dtype):
+    """mse observer (O4): the restatement on the C oracle picks the same shrunk (min, max) per chunk as the restatement
+    on the live compressed-tensors calls (calculate_qparams, TOKEN-patched fake_quantize)."""
+    from oracle import llmc_restated as R
+
+    _, args = L.format_args(name)
+    _, qtype, nb, sym, *_ = FORMATS[name]
+    w = synth_weight(24, 256, dtype, 5)
+    rmn, rmx = L.mse_minmax(w, args)
+    gmn, gmx = R.mse_minmax(w, geom_of(name), qtype, nb, sym)
+    assert_bits_equal(gmn.reshape(rmn.shape), rmn, f"{name}/{dtype}: min")
+    assert_bits_equal(gmx.reshape(rmx.shape), rmx, f"{name}/{dtype}: max")
+    assert not torch.equal(rmn, torch.amin(L.flatten_weight(w, args), dim=(0, -1))), "the search must shrink some range"
