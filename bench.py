@@ -256,7 +256,11 @@ def run_awq(args, dev, world, rank, peaks):
     def layer(ww, aa):
         return awq.search_decoder_layer({k: v.clone() for k, v in ww.items()}, aa, qargs, **cfg)
 
-    for _ in range(2):  # warm-up: workspace growth, SDPA planning, kernel attributes
+    import gc
+
+    gc.collect()                # the e2e leg's pinned staging buffers and device arenas are released here, not inside the timed region
+    torch.cuda.empty_cache()
+    for _ in range(3):  # warm-up: workspace growth, SDPA planning, kernel attributes
         layer(w, acts)
     torch.cuda.synchronize()
     if world > 1:
@@ -312,6 +316,89 @@ def run_awq(args, dev, world, rank, peaks):
     return out
 
 
+# ----------------------------------------------------------------------------- MoE legs (BASELINE.json configs[3], configs[4])
+def run_moe_nvfp4(args, dev, world, rank, peaks):
+    """configs[3]: Qwen3-30B-A3B NVFP4 RTN, the 128 experts of every layer sharded across the ranks (strong scaling: the job is
+    ``--moe-layers`` layers x 128 experts whatever N is).  One step = fused |max| -> min(gate, up) global scale -> e4m3 group
+    scales -> packed e2m1 codes for this rank's experts of all those layers (two launches: gate/up stack, down stack)."""
+    import torch.distributed as dist
+
+    from quantizers_b200 import scheduler as S
+
+    experts = S.partition(128, world, rank)
+    units = [l * 128 + e for l in range(args.moe_layers) for e in experts]
+    spec = S.qwen3_30b_a3b(layers=1, experts=len(units))
+    arena = S.build_arena(spec, units, dev)
+    nbytes_total = args.moe_layers * 128 * spec.unit_bytes()
+    for _ in range(3):
+        S.quantize_arena(spec, arena)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = args.moe_steps
+    e0.record()
+    for _ in range(steps):
+        S.quantize_arena(spec, arena)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    a = S.PRESETS["NVFP4"]
+    alg = a.bytes_per_element() * (len(units) * spec.unit_elements())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = alg / (ms * 1e-3) / 1e9
+    return {"metric": "bf16_weight_GBps_quantized_packed", "value": nbytes_total / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms,
+            "scaling": "strong", "steps": steps,
+            "config": {"workload": "qwen3-30b-a3b NVFP4 RTN quantize+pack, experts sharded across ranks", "layers": args.moe_layers,
+                       "experts_per_layer": 128, "experts_per_gpu_per_layer": len(experts), "bytes_total": nbytes_total,
+                       "l2": f"inputs ({len(units) * spec.unit_bytes() / 1e9:.2f} GB/step/GPU) larger than the 126 MB L2"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "kernel": "nvfp4_fused_kernel (|max| -> global scale -> compress, one launch per stack)",
+                         "alg_bytes_per_element": a.bytes_per_element(), "note": "per-GPU figure of the slowest rank"}}
+
+
+def run_moe_awq(args, dev, world, rank, peaks):
+    """configs[4] kind (ii): MiniMax-M2.1 experts-only AWQ (INT4 g32 sym), the per-expert ``w3 -> w2`` mappings of one layer
+    (T = 64 x 512 tokens, every expert sees all tokens) with the experts sharded across the ranks (strong scaling over
+    ``--moe-awq-experts`` experts).  Each mapping is an independent n_grid-20 search on the fused tcgen05 loss GEMM."""
+    import torch.distributed as dist
+
+    from quantizers_b200 import awq
+    from quantizers_b200 import scheduler as S
+
+    T = args.awq_tokens
+    qargs = S.PRESETS["INT4_G32_SYM"]
+    experts = S.partition(args.moe_awq_experts, world, rank)
+    w1, w3, w2, xs = S.synth_moe_awq_experts(0, experts, T, dev)
+    del w1
+    res = awq.search_expert_mappings(xs[:1], w2[:1].clone(), qargs)  # warm-up: workspace growth, kernel attributes
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = awq.search_expert_mappings(xs, w2, qargs, smooth_weight=w3)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    flops = awq.expert_mapping_flops(T, 1536, 3072) * args.moe_awq_experts
+    tf = awq.expert_mapping_flops(T, 1536, 3072) * len(experts) / (ms * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1500.0)))
+    return {"metric": "awq_expert_mappings_per_s", "value": args.moe_awq_experts / (ms * 1e-3), "unit": "experts/s", "ms_total": ms,
+            "scaling": "strong",
+            "config": {"workload": "minimax-m2.1 experts-only AWQ INT4 g32 sym, per-expert w3->w2 mappings, n_grid 20, duo_scaling",
+                       "experts": args.moe_awq_experts, "experts_per_gpu": len(experts), "tokens": T, "flops_total": flops,
+                       "best_ratios_first4": [r[1] for r in res[:4]]},
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+                         "kernel": "awq_gemm_loss_kernel (tcgen05, TMEM)", "note": "per-GPU figure of the slowest rank"}}
+
+
 # ----------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
@@ -324,6 +411,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--awq-layers", type=int, default=3, help="decoder layers of the AWQ search leg per rank (0 disables it)")
     ap.add_argument("--awq-tokens", type=int, default=64 * 512, help="calibration tokens per layer (64 samples x 512)")
+    ap.add_argument("--moe-layers", type=int, default=8, help="layers of the Qwen3-30B-A3B NVFP4 expert-sharded leg (0 disables it)")
+    ap.add_argument("--moe-steps", type=int, default=20)
+    ap.add_argument("--moe-awq-experts", type=int, default=16, help="experts of the MiniMax-M2.1 per-expert AWQ leg (0 disables it)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -426,6 +516,16 @@ def main():
 
     awq_line = run_awq(args, dev, world, rank, peaks) if args.awq_layers > 0 else None
     barrier()
+    from quantizers_b200 import awq as _awq
+
+    _awq.workspace.release()
+    del arena
+    torch.cuda.empty_cache()
+    moe_nvfp4 = run_moe_nvfp4(args, dev, world, rank, peaks) if args.moe_layers > 0 else None
+    barrier()
+    torch.cuda.empty_cache()
+    moe_awq = run_moe_awq(args, dev, world, rank, peaks) if args.moe_awq_experts > 0 else None
+    barrier()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -441,6 +541,10 @@ def main():
     }
     if awq_line is not None:
         line["awq"] = awq_line
+    if moe_nvfp4 is not None:
+        line["moe_nvfp4"] = moe_nvfp4
+    if moe_awq is not None:
+        line["moe_awq"] = moe_awq
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             kind = cpu_kind()

@@ -392,3 +392,35 @@ def search_decoder_layer(weights: dict, acts: dict, args, n_heads: int, n_kv: in
     if apply:
         smooth([w["down"]], w["up"], out["down"][0])
     return out
+
+
+# ----------------------------------------------------------------------------- MoE experts (config 5)
+def expert_mapping_flops(T: int, k: int, n: int, n_grid: int = 20) -> float:
+    """ALGORITHMIC FLOPs of one per-expert single-Linear mapping search: (n_grid + 1) evaluations of x [T,k] @ W[n,k]^T."""
+    return (n_grid + 1) * 2.0 * T * k * n
+
+
+@torch.no_grad()
+def search_expert_mappings(x_in: Sequence[torch.Tensor], balance: torch.Tensor, args, n_grid: int = 20, duo_scaling: bool = True,
+                           smooth_weight: Optional[torch.Tensor] = None, process_group=None) -> List[Tuple[torch.Tensor, float, List[float]]]:
+    """The per-expert mappings of a MoE layer whose parent is the balance Linear itself -- ``w3 -> w2`` in
+    REF:configs/recipes/recipe_Minimax-M2.1-Experts-only-AWQ.yaml:29-34 (``up_proj -> down_proj`` for Qwen3-MoE): one
+    independent ``_compute_best_scale`` per expert, the embarrassingly expert-parallel part of SURVEY.md §8d config 5 (ii).
+
+    x_in          per local expert the input of its balance layer ``[T, K]`` (= act(w1 x) * (w3 x); under
+                  ``moe_calibrate_all_experts`` every expert sees all T tokens, REF:scripts/do_oneshot.py:186)
+    balance       the local experts' balance weights stacked ``[E_local, N, K]`` (w2)
+    smooth_weight optional ``[E_local, K, H]`` smooth layers (w3): when given the best scales are applied like ``_smooth``
+                  (balance ``*= s``, the smooth layer's rows ``/= s``)
+    Experts are sharded across ranks by the caller (``scheduler.partition``); nothing is exchanged between expert shards.
+    ``process_group`` names ranks holding token shards of the SAME experts (statistics and losses are all-reduced over it).
+    Returns one (best_scales cpu fp32 [K], best_ratio, losses[n_grid]) per local expert."""
+    if len(x_in) != balance.shape[0]:
+        raise L.B200QError("search_expert_mappings: one input per stacked expert weight is needed")
+    out = []
+    for e, x in enumerate(x_in):
+        res = compute_best_scale(x, [balance[e]], linear_parent, args, n_grid, duo_scaling, process_group)
+        if smooth_weight is not None:
+            smooth([balance[e]], smooth_weight[e], res[0])
+        out.append(res)
+    return out

@@ -174,6 +174,30 @@ def synth_awq_layer(layer_idx: int, tokens: int, device, hidden: int = 2560, int
     return w, acts
 
 
+def synth_moe_awq_experts(layer_idx: int, experts: Sequence[int], tokens: int, device, hidden: int = 3072, inter: int = 1536,
+                          dtype=torch.bfloat16):
+    """The ``w3 -> w2`` mappings of MiniMax-M2.1-shaped experts: per expert w1, w3 [inter, hidden],
+    w2 [hidden, inter] (seed 1234 + (layer * 256 + expert) * 1000 + matrix) and the balance-layer input
+    ``silu(w1 x) * (w3 x)`` [tokens, inter] of the layer's calibration activations x (seed 4321 + layer; every expert sees
+    all tokens, moe_calibrate_all_experts).  Returns (w1, w3, w2 stacked [E, ...], list of inputs)."""
+    units = [layer_idx * 256 + int(e) for e in experts]
+    w1 = synth_stack(units, inter, hidden, 0, device, dtype)
+    w3 = synth_stack(units, inter, hidden, 1, device, dtype)
+    w2 = synth_stack(units, hidden, inter, 2, device, dtype)
+    g = torch.Generator(device=device).manual_seed(4321 + layer_idx)
+    spread = 1 + 3 * torch.rand(hidden, generator=g, device=device)
+    x = (torch.randn(tokens, hidden, generator=g, device=device) * spread).to(dtype)
+    F = torch.nn.functional
+    xs = []
+    for e in range(len(units)):
+        h = torch.empty(tokens, inter, dtype=dtype, device=device)
+        for t0 in range(0, tokens, 8192):
+            xc = x[t0:t0 + 8192]
+            h[t0:t0 + 8192] = F.silu(F.linear(xc, w1[e])) * F.linear(xc, w3[e])
+        xs.append(h)
+    return w1, w3, w2, xs
+
+
 # ----------------------------------------------------------------------------- RTN quantize + pack of a shard
 def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Optional[list] = None) -> Dict[str, dict]:
     """Fused observe -> qparams -> quantize -> pack for every stacked weight class of this rank's shard.

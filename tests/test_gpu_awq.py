@@ -262,3 +262,33 @@ def test_qk_norm_rope_vs_eager(H, HKV, D, S, B):
     # the only freedom is the summation order of mean(x^2): at most one bf16 ulp, on a small fraction of the elements
     assert bool((diff <= want.float().abs() * 2 ** -7 + 1e-6).all()), float(diff.max())
     assert float((diff > 0).float().mean()) < 0.02
+
+
+def test_search_expert_mappings_matches_oracle():
+    """config 5 (ii): per-expert w3 -> w2 mappings of a MoE layer, each an independent single-Linear search; the best scales
+    are folded in like _smooth (w2 *= s, w3 rows /= s).  Losses within 1e-3 relative, same argmin, per expert."""
+    from quantizers_b200 import awq
+
+    E, T, H, I = 3, 512, 256, 384   # experts, tokens, hidden, expert intermediate
+    g = torch.Generator().manual_seed(17)
+    x = (torch.randn(T, H, generator=g) * (1 + 3 * torch.rand(H, generator=g))).to(torch.bfloat16)
+    w1 = (torch.randn(E, I, H, generator=g) * 0.05).to(torch.bfloat16)
+    w3 = (torch.randn(E, I, H, generator=g) * 0.05).to(torch.bfloat16)
+    w2 = (torch.randn(E, H, I, generator=g) * 0.02).to(torch.bfloat16)
+    F = torch.nn.functional
+    xs = [F.silu(F.linear(x, w1[e])) * F.linear(x, w3[e]) for e in range(E)]
+    geom = O.Geom(O.GROUP, 32)
+    w2_dev, w3_dev = w2.cuda(), w3.cuda()
+    got = awq.search_expert_mappings([v.cuda() for v in xs], w2_dev, Args("int4_g32_sym"), smooth_weight=w3_dev)
+    assert len(got) == E
+    for e in range(E):
+        s_ref, r_ref, l_ref = R.compute_best_scale([xs[e]], [w2[e]], R.linear_parent, geom, O.INT, 4, True)
+        s, r, l = got[e]
+        assert max(abs(a - b) / b for a, b in zip(l, l_ref)) < 1e-3, e
+        assert r == r_ref, e
+        assert torch.allclose(s, s_ref, rtol=1e-5)
+        new_w, new_s = R.smooth([w2[e]], w3[e], s)  # fold the SAME scales in on the CPU
+        assert_bits_equal(w2_dev[e], new_w[0], f"w2[{e}] smoothed")
+        assert_bits_equal(w3_dev[e], new_s, f"w3[{e}] smoothed")
+    with pytest.raises(ValueError):
+        awq.search_expert_mappings([xs[0].cuda()], w2_dev, Args("int4_g32_sym"))
