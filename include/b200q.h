@@ -171,6 +171,10 @@ int b200q_awq_scales(const float* x_mean, const float* w_mean, int64_t k, const 
  * (call_observer + forward_quantize + div), written as T [rows, cols] */
 int b200q_awq_scaled_fake_quantize(const void* weight, int64_t rows, int64_t cols, const b200q_scheme* scheme,
                                    const float* scales, void* out, void* stream);
+/* The same for all grid points in one launch: scales fp32 [n_ratios, cols] (b200q_awq_scales output); variant r is written at
+ * out + r * out_stride elements (out_stride >= rows * cols: the variants of several balance layers interleave in one buffer). */
+int b200q_awq_scaled_fake_quantize_grid(const void* weight, int64_t rows, int64_t cols, const b200q_scheme* scheme,
+                                        const float* scales, int32_t n_ratios, void* out, int64_t out_stride, void* stream);
 /* W3: _compute_loss partial: acc[0] += sum (bf16(y_ref) - bf16(y_q))^2 in fp32 (device fp32 accumulator) */
 int b200q_sq_err_accumulate(const void* y_ref, const void* y_q, int64_t numel, int32_t dtype, float* acc, void* stream);
 /* W1-W3 fused on the tensor cores: for each of n_ratios pre-fake-quantized weight variants Wq[r] (T [n, k]) compute

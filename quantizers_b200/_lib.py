@@ -53,6 +53,7 @@ _SIGS = {
     "b200q_wmean_accumulate": (_I, [_P, c_int64, c_int64, c_int32, c_int32, _P, _P]),
     "b200q_awq_scales": (_I, [_P, _P, c_int64, POINTER(c_float), c_int32, c_int32, _P, _P]),
     "b200q_awq_scaled_fake_quantize": (_I, [_P, c_int64, c_int64, _S, _P, _P, _P]),
+    "b200q_awq_scaled_fake_quantize_grid": (_I, [_P, c_int64, c_int64, _S, _P, c_int32, _P, c_int64, _P]),
     "b200q_sq_err_accumulate": (_I, [_P, _P, c_int64, c_int32, _P, _P]),
     "b200q_awq_gemm_loss": (_I, [_P, c_int64, c_int64, _P, _P, c_int64, c_int32, _P, _P, c_int64, _P]),
     "b200q_awq_gemm_loss_workspace": (c_int64, [c_int64, c_int64, c_int64, c_int32]),

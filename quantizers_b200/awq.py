@@ -77,6 +77,21 @@ def scaled_fake_quantize(w: torch.Tensor, scales: torch.Tensor, args, out: Optio
 
 
 @torch.no_grad()
+def scaled_fake_quantize_grid(w: torch.Tensor, scales: torch.Tensor, args, out: torch.Tensor) -> torch.Tensor:
+    """All grid points at once: ``out[r] = fake_quantize(W * scales[r]) / scales[r]``; ``out`` is ``[R, rows, K]`` or a row slice
+    ``buf[:, off:off + rows]`` of a larger ``[R, total_rows, K]`` buffer (the variants of several balance layers side by side)."""
+    L.require_cuda(w, scales, out)
+    w, scales = w.contiguous(), scales.contiguous()
+    R, rows, K = out.shape
+    if tuple(w.shape) != (rows, K) or tuple(scales.shape) != (R, K) or out.stride(2) != 1 or out.stride(1) != K:
+        raise L.B200QError("scaled_fake_quantize_grid: operand shapes / strides do not agree")
+    sc = ops.scheme_from_args(args, w.dtype, True)
+    L.check(L.lib().b200q_awq_scaled_fake_quantize_grid(L.ptr(w), rows, K, ctypes.byref(sc), L.ptr(scales), R, L.ptr(out),
+                                                        out.stride(0) if R > 1 else rows * K, L.stream_ptr(w.device)))
+    return out
+
+
+@torch.no_grad()
 def sq_err_accumulate(y_ref: torch.Tensor, y_q: torch.Tensor, acc: torch.Tensor) -> None:
     """_compute_loss partial: acc[0] += sum((y_ref - y_q)^2), difference rounded to the output dtype first."""
     L.check(L.lib().b200q_sq_err_accumulate(L.ptr(y_ref.contiguous()), L.ptr(y_q.contiguous()), y_ref.numel(), L.DTYPE_CODE[y_ref.dtype],
@@ -262,7 +277,10 @@ def reduce_and_select(acc: torch.Tensor, group=None, distributed: bool = True) -
 
     if distributed and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
-    host = acc.double().cpu()
+    return _select_host(acc.double().cpu())
+
+
+def _select_host(host: torch.Tensor) -> Tuple[int, List[float]]:
     n_grid = host.numel() - 1
     losses = (host[:n_grid] / host[n_grid]).tolist()
     best_err, best_i = float("inf"), -1
@@ -274,19 +292,22 @@ def reduce_and_select(acc: torch.Tensor, group=None, distributed: bool = True) -
     return best_i, losses
 
 
-@torch.no_grad()
-def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent: Callable, args, n_grid: int = 20,
-                       duo_scaling: bool = True, process_group=None, fused: Optional[bool] = None, fused_linear: Optional[bool] = None,
-                       token_chunk: int = 8192) -> Tuple[torch.Tensor, float, List[float]]:
-    """``AWQModifier._compute_best_scale`` for one mapping.
+def _first_min_device(acc: torch.Tensor) -> torch.Tensor:
+    """Index of the first minimum of ``acc[:-1]`` (the scan ``if loss < best_error``; NaN never wins) as a device int64 [1], no
+    host round trip; -1 when no loss is finite-or-smaller-than-inf (caught when the results are fetched)."""
+    n = acc.numel() - 1
+    v = torch.nan_to_num(acc[:n].double(), nan=float("inf"))
+    idx = torch.arange(n, device=acc.device)
+    m = v.min()
+    first = torch.where(v == m, idx, torch.full_like(idx, n)).min()
+    return torch.where(torch.isinf(m) & (m > 0), torch.full_like(first, -1), first).reshape(1)
 
-    x        [T_local, K] inputs of the balance layers (this rank's token shard; whole samples for an attention parent)
-    weights  balance-layer weights [N_i, K];  parent(weights, x_chunk) -> parent-module output
-    parent   a LinearParent / MLPParent / AttentionParent (fused tensor-core evaluation, bf16) or any callable (generic
-             evaluation: the parent runs through torch, the squared error through ``b200q_sq_err_accumulate``)
-    Returns (best_scales fp32 [K] on the CPU like the reference, best_ratio, losses[n_grid]).  Raises if no ratio gives
-    a finite loss.  With ``process_group`` (token-sharded calibration; pass ``dist.group.WORLD`` for all ranks) the |x| sums /
-    token counts and the loss accumulators are all-reduced (SUM), so every rank of the group returns the same argmin."""
+
+@torch.no_grad()
+def _search_device(x: torch.Tensor, weights: Sequence[torch.Tensor], parent: Callable, args, n_grid: int, duo_scaling: bool,
+                   process_group, fused: Optional[bool], token_chunk: int):
+    """Everything of ``_compute_best_scale`` that runs on the device, enqueued without a host synchronisation:
+    returns (scales fp32 [n_grid, K], acc fp32 [n_grid + 1] = summed squared errors + element count, ratios)."""
     import torch.distributed as dist
 
     dev = x.device
@@ -296,11 +317,14 @@ def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent:
     # together, so nothing is exchanged unless the caller names the group whose ranks hold shards of the same tokens
     dist_on = process_group is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
     if fused is None:
-        fused = fused_linear if fused_linear is not None else (hasattr(parent, "fused_losses") and x.dtype == torch.bfloat16)
+        fused = hasattr(parent, "fused_losses") and x.dtype == torch.bfloat16
     # ---- statistics
     xsum = abs_sum_cols(x)
-    cnt = torch.tensor([float(x.shape[0])], dtype=torch.float64, device=dev)
-    x_mean = reduce_token_stats(xsum, cnt, process_group) if dist_on else xsum / cnt.float()
+    if dist_on:
+        cnt = torch.full((1,), float(x.shape[0]), dtype=torch.float64, device=dev)
+        x_mean = reduce_token_stats(xsum, cnt, process_group)
+    else:
+        x_mean = xsum / float(x.shape[0])
     w_mean = compute_layer_means(weights, args.group_size) if duo_scaling else None
     ratios = [i / n_grid for i in range(n_grid)]
     scales = awq_scales(x_mean, w_mean, ratios, duo_scaling)
@@ -314,8 +338,7 @@ def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent:
         off = 0
         for w, n in zip(weights, rows):
             w_all[0, off:off + n].copy_(w)
-            for i in range(n_grid):
-                scaled_fake_quantize(w, scales[i], args, out=w_all[1 + i, off:off + n])
+            scaled_fake_quantize_grid(w, scales, args, w_all[1:, off:off + n])  # all ratios in one launch
             off += n
         sums, numel = parent.fused_losses(x.contiguous(), w_all)
         acc[:n_grid] = sums
@@ -331,7 +354,28 @@ def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent:
             for xc, ref in zip(chunks, refs):
                 sq_err_accumulate(ref, parent(wq, xc), acc[i:i + 1])
         acc[n_grid] = float(numel)
-    best_i, losses = reduce_and_select(acc, process_group if dist_on else None, dist_on)
+    if dist_on:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=process_group)
+    return scales, acc, ratios
+
+
+@torch.no_grad()
+def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent: Callable, args, n_grid: int = 20,
+                       duo_scaling: bool = True, process_group=None, fused: Optional[bool] = None, fused_linear: Optional[bool] = None,
+                       token_chunk: int = 8192) -> Tuple[torch.Tensor, float, List[float]]:
+    """``AWQModifier._compute_best_scale`` for one mapping.
+
+    x        [T_local, K] inputs of the balance layers (this rank's token shard; whole samples for an attention parent)
+    weights  balance-layer weights [N_i, K];  parent(weights, x_chunk) -> parent-module output
+    parent   a LinearParent / MLPParent / AttentionParent (fused tensor-core evaluation, bf16) or any callable (generic
+             evaluation: the parent runs through torch, the squared error through ``b200q_sq_err_accumulate``)
+    Returns (best_scales fp32 [K] on the CPU like the reference, best_ratio, losses[n_grid]).  Raises if no ratio gives
+    a finite loss.  With ``process_group`` (token-sharded calibration; pass ``dist.group.WORLD`` for all ranks) the |x| sums /
+    token counts and the loss accumulators are all-reduced (SUM), so every rank of the group returns the same argmin."""
+    if fused is None and fused_linear is not None:
+        fused = fused_linear
+    scales, acc, ratios = _search_device(x, weights, parent, args, n_grid, duo_scaling, process_group, fused, token_chunk)
+    best_i, losses = _select_host(acc.double().cpu())
     return scales[best_i].cpu(), ratios[best_i], losses
 
 
@@ -417,10 +461,23 @@ def search_expert_mappings(x_in: Sequence[torch.Tensor], balance: torch.Tensor, 
     Returns one (best_scales cpu fp32 [K], best_ratio, losses[n_grid]) per local expert."""
     if len(x_in) != balance.shape[0]:
         raise L.B200QError("search_expert_mappings: one input per stacked expert weight is needed")
-    out = []
+    # everything stays on the device until all experts are enqueued: no host round trip (and no idle GPU) between experts
+    pend = []
     for e, x in enumerate(x_in):
-        res = compute_best_scale(x, [balance[e]], linear_parent, args, n_grid, duo_scaling, process_group)
+        scales, acc, ratios = _search_device(x, [balance[e]], linear_parent, args, n_grid, duo_scaling, process_group, None, 8192)
+        best = _first_min_device(acc)
+        best_scales = scales.index_select(0, best.clamp(min=0)).reshape(-1)
         if smooth_weight is not None:
-            smooth([balance[e]], smooth_weight[e], res[0])
-        out.append(res)
+            smooth([balance[e]], smooth_weight[e], best_scales)
+        pend.append((best_scales, best, acc, ratios))
+    out = []
+    all_best = torch.cat([p[1] for p in pend]).cpu()
+    all_scales = torch.stack([p[0] for p in pend]).cpu()
+    all_acc = torch.stack([p[2] for p in pend]).double().cpu()
+    for e, (_, _, _, ratios) in enumerate(pend):
+        bi = int(all_best[e])
+        if bi < 0:
+            raise RuntimeError(f"AWQ: no finite loss for any ratio (expert {e})")
+        n = all_acc.shape[1] - 1
+        out.append((all_scales[e], ratios[bi], (all_acc[e, :n] / all_acc[e, n]).tolist()))
     return out

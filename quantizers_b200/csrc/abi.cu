@@ -307,6 +307,19 @@ int b200q_awq_scaled_fake_quantize(const void* weight, int64_t rows, int64_t col
     p.has_zp = sc->has_zp; p.col_scale = scales; p.out = out;
     return dispatch_group<MODE_OBS_FQ>(sc->dtype, sc->qtype, p, 1, (cudaStream_t)stream);
 }
+int b200q_awq_scaled_fake_quantize_grid(const void* weight, int64_t rows, int64_t cols, const b200q_scheme* sc, const float* scales,
+                                        int32_t n_ratios, void* out, int64_t out_stride, void* stream) {
+    if (int rc = check_scheme(sc)) return rc;
+    REQ_PTR(weight); REQ_PTR(out); REQ_PTR(scales);
+    B200Q_REQUIRE(sc->strategy == B200Q_GROUP, "AWQ fused fake-quantize supports GROUP strategies");
+    B200Q_REQUIRE(sc->qtype != B200Q_FP4, "AWQ over NVFP4 goes through b200q_global_scale + b200q_fake_quantize");
+    B200Q_REQUIRE(n_ratios >= 1 && cols % 8 == 0, "need n_ratios >= 1 and a multiple of 8 columns");
+    B200Q_REQUIRE(out_stride >= rows * cols && out_stride % 8 == 0, "out_stride must cover one weight and keep 16-byte alignment");
+    GroupParams p{};
+    p.w = weight; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = sc->num_bits; p.symmetric = sc->symmetric;
+    p.has_zp = sc->has_zp; p.col_scale = scales; p.col_scale_stride = cols; p.out_batch_stride = out_stride; p.out = out;
+    return dispatch_group<MODE_OBS_FQ>(sc->dtype, sc->qtype, p, n_ratios, (cudaStream_t)stream);
+}
 int b200q_sq_err_accumulate(const void* y_ref, const void* y_q, int64_t numel, int32_t dtype, float* acc, void* stream) {
     REQ_PTR(y_ref); REQ_PTR(y_q); REQ_PTR(acc);
     return launch_sq_err(dtype, y_ref, y_q, numel, acc, (cudaStream_t)stream);

@@ -21,6 +21,8 @@ struct GroupParams {
     const float* gs;        // fp32 [b] (FP4) or null
     int32_t gs_stride;      // 1: per batch entry, 0: shared
     const float* col_scale; // fp32 [cols]: AWQ smoothing scale (MODE_OBS_FQ) or null
+    int64_t col_scale_stride; // 0: one scale vector; cols: one per batch entry applied to the SAME weight (AWQ ratio grid)
+    int64_t out_batch_stride; // AWQ ratio grid: elements between consecutive ratios' outputs
     void* out;              // codes / packed words / T values, depending on mode
 };
 template <int MODE> int dispatch_group(int dt, int qt, const GroupParams& p, int64_t batch, cudaStream_t st);

@@ -45,7 +45,9 @@ __global__ void __launch_bounds__(256) group_kernel(const GroupParams p) {
 #pragma unroll
     for (int j = 0; j < U; j++) {
         const int64_t c0 = tile_c0 + j * 256 + lane * 8;
-        if (row_ok && c0 < p.cols) load_chunk<DT>(ch[j], p.w, mat_off + row * p.cols + c0);
+        // AWQ grid (col_scale_stride != 0): every batch entry is the SAME weight under another ratio's scale vector
+        const int64_t in_off = (MODE == MODE_OBS_FQ && p.col_scale_stride != 0) ? 0 : mat_off;
+        if (row_ok && c0 < p.cols) load_chunk<DT>(ch[j], p.w, in_off + row * p.cols + c0);
         else zero_chunk<DT>(ch[j]);
     }
 
@@ -67,8 +69,9 @@ __global__ void __launch_bounds__(256) group_kernel(const GroupParams p) {
         float cs[8];
         if (MODE == MODE_OBS_FQ && p.col_scale != nullptr) {
             if (ok) {
-                const float4 s0 = *reinterpret_cast<const float4*>(p.col_scale + c0);
-                const float4 s1 = *reinterpret_cast<const float4*>(p.col_scale + c0 + 4);
+                const float* csp = p.col_scale + b * p.col_scale_stride;
+                const float4 s0 = *reinterpret_cast<const float4*>(csp + c0);
+                const float4 s1 = *reinterpret_cast<const float4*>(csp + c0 + 4);
                 cs[0] = s0.x; cs[1] = s0.y; cs[2] = s0.z; cs[3] = s0.w; cs[4] = s1.x; cs[5] = s1.y; cs[6] = s1.z; cs[7] = s1.w;
             } else {
 #pragma unroll
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(256) group_kernel(const GroupParams p) {
         if (!ok) continue;
 
         // ---- codes
-        const int64_t e0 = mat_off + row * p.cols + c0;
+        const int64_t e0 = ((MODE == MODE_OBS_FQ && p.col_scale_stride != 0) ? b * p.out_batch_stride : mat_off) + row * p.cols + c0;
         if (kCodes) {
             if (QT == QT_INT) {
                 int c[8];
