@@ -342,7 +342,7 @@ def _search_device(x: torch.Tensor, weights: Sequence[torch.Tensor], parent: Cal
             off += n
         sums, numel = parent.fused_losses(x.contiguous(), w_all)
         acc[:n_grid] = sums
-        acc[n_grid] = float(numel)
+        acc[n_grid:].fill_(float(numel))  # fill_ takes the scalar by value: `acc[i] = python_float` stages a host copy and blocks
     else:
         wq = [torch.empty_like(w) for w in weights]
         chunks = [x[t0:t0 + token_chunk] for t0 in range(0, x.shape[0], token_chunk)]
@@ -353,7 +353,7 @@ def _search_device(x: torch.Tensor, weights: Sequence[torch.Tensor], parent: Cal
                 scaled_fake_quantize(w, scales[i], args, out=o)
             for xc, ref in zip(chunks, refs):
                 sq_err_accumulate(ref, parent(wq, xc), acc[i:i + 1])
-        acc[n_grid] = float(numel)
+        acc[n_grid:].fill_(float(numel))  # fill_ takes the scalar by value: `acc[i] = python_float` stages a host copy and blocks
     if dist_on:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=process_group)
     return scales, acc, ratios

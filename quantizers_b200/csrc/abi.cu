@@ -286,15 +286,7 @@ int b200q_awq_scales(const float* x_mean, const float* w_mean, int64_t k, const 
                      int32_t duo, float* scales, void* stream) {
     REQ_PTR(x_mean); REQ_PTR(ratios_host); REQ_PTR(scales);
     B200Q_REQUIRE(n_ratios >= 0 && n_ratios <= 256, "n_ratios out of range");
-    // ratios travel as kernel-visible memory: stage them at the tail of the output (row n_ratios-1 is written last)
-    cudaStream_t st = (cudaStream_t)stream;
-    float* d_ratios = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&d_ratios, sizeof(float) * n_ratios, st);
-    if (e != cudaSuccess) { set_error("cudaMallocAsync: %s", cudaGetErrorString(e)); return B200Q_ECUDA; }
-    cudaMemcpyAsync(d_ratios, ratios_host, sizeof(float) * n_ratios, cudaMemcpyHostToDevice, st);
-    int rc = launch_awq_scales(x_mean, w_mean, k, d_ratios, n_ratios, duo, scales, st);
-    cudaFreeAsync(d_ratios, st);
-    return rc;
+    return launch_awq_scales(x_mean, w_mean, k, ratios_host, n_ratios, duo, scales, (cudaStream_t)stream);
 }
 int b200q_awq_scaled_fake_quantize(const void* weight, int64_t rows, int64_t cols, const b200q_scheme* sc, const float* scales,
                                    void* out, void* stream) {

@@ -103,12 +103,14 @@ int launch_wmean(int dt, const void* w, int64_t rows, int64_t cols, int group, d
     return B200Q_OK;
 }
 
-// one CTA per grid point
+// one CTA per grid point; the ratios travel by value in the kernel parameters (no staging allocation, no host copy to order)
+struct RatioPack { float r[64]; };
 __global__ void __launch_bounds__(256) awq_scales_kernel(const float* __restrict__ x_mean, const float* __restrict__ w_mean,
-                                                         int64_t k, const float* __restrict__ ratios, int duo,
+                                                         int64_t k, const RatioPack ratios, int first, int duo,
                                                          float* __restrict__ scales) {
     __shared__ float smx[8], smn[8];
-    const float r = ratios[blockIdx.x];
+    const float r = ratios.r[blockIdx.x];
+    scales += (int64_t)first * k;
     float* out = scales + (int64_t)blockIdx.x * k;
     float mx = -INFINITY, mn = INFINITY;
     for (int64_t i = threadIdx.x; i < k; i += blockDim.x) {
@@ -137,8 +139,13 @@ int launch_awq_scales(const float* x_mean, const float* w_mean, int64_t k, const
                       float* scales, cudaStream_t st) {
     if (k == 0 || n_ratios == 0) return B200Q_OK;
     B200Q_REQUIRE(!duo || w_mean != nullptr, "duo_scaling needs w_mean");
-    awq_scales_kernel<<<n_ratios, 256, 0, st>>>(x_mean, w_mean, k, ratios, duo, scales);
-    B200Q_CHECK_LAUNCH();
+    for (int first = 0; first < n_ratios; first += 64) {  // ratios: HOST pointer
+        RatioPack pack;
+        const int n = n_ratios - first < 64 ? n_ratios - first : 64;
+        for (int i = 0; i < n; i++) pack.r[i] = ratios[first + i];
+        awq_scales_kernel<<<n, 256, 0, st>>>(x_mean, w_mean, k, pack, first, duo, scales);
+        B200Q_CHECK_LAUNCH();
+    }
     return B200Q_OK;
 }
 

@@ -1,0 +1,183 @@
+"""GPU: the oneshot-shaped driver (recipe -> modifiers -> compressed state dict) on a tiny decoder, against the oracle:
+RTN outputs bit-exact per Linear, AWQ mappings resolved from the recipe with the same argmin / losses within 1e-3."""
+import pytest
+import torch
+
+from oracle import llmc_restated as R
+from oracle import oracle as O
+from tests.util import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+H, I, HEADS = 128, 256, 4
+
+RECIPE = """
+quant_stage:
+  quant_modifiers:
+    QuantizationModifier:
+      targets: "re:.*self_attn\\\\.(k|q|o|v)_proj.*"
+      scheme: FP8_BLOCK
+    AWQModifier:
+      mlp_projections:
+        group_0:
+          targets: ["re:.*(down|gate|up)_proj.*"]
+          weights: {num_bits: 4, type: int, symmetric: true, group_size: 32, strategy: group, observer: memoryless_minmax}
+      ignore: ["lm_head"]
+      duo_scaling: true
+      mappings:
+        - smooth_layer: re:.*post_attention_layernorm$
+          balance_layers: ["re:.*gate_proj$", "re:.*up_proj$"]
+        - smooth_layer: re:.*up_proj$
+          balance_layers: ["re:.*down_proj$"]
+"""
+
+NVFP4_RECIPE = """
+default_stage:
+  default_modifiers:
+    QuantizationModifier:
+      scheme: NVFP4
+      targets: ["Linear"]
+      ignore: ["lm_head"]
+"""
+
+
+class Attn(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            setattr(self, n, torch.nn.Linear(H, H, bias=False))
+
+    def forward(self, x):
+        B, S, _ = x.shape
+        q, k, v = (p(x).view(B, S, HEADS, H // HEADS).transpose(1, 2) for p in (self.q_proj, self.k_proj, self.v_proj))
+        o = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True)
+        return self.o_proj(o.transpose(1, 2).reshape(B, S, H))
+
+
+class MLP(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.gate_proj = torch.nn.Linear(H, I, bias=False)
+        self.up_proj = torch.nn.Linear(H, I, bias=False)
+        self.down_proj = torch.nn.Linear(I, H, bias=False)
+
+    def forward(self, x):
+        return self.down_proj(torch.nn.functional.silu(self.gate_proj(x)) * self.up_proj(x))
+
+
+class Block(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.input_layernorm = torch.nn.LayerNorm(H)
+        self.post_attention_layernorm = torch.nn.LayerNorm(H)
+        self.self_attn, self.mlp = Attn(), MLP()
+
+    def forward(self, x):
+        x = x + self.self_attn(self.input_layernorm(x))
+        return x + self.mlp(self.post_attention_layernorm(x))
+
+
+class TinyLM(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.model = torch.nn.Module()
+        self.model.layers = torch.nn.ModuleList([Block(), Block()])
+        self.lm_head = torch.nn.Linear(H, 64, bias=False)
+
+    def forward(self, x):
+        for b in self.model.layers:
+            x = b(x)
+        return self.lm_head(x)
+
+
+def _model(seed=0):
+    torch.manual_seed(seed)
+    m = TinyLM()
+    for p in m.parameters():
+        if p.ndim == 2:
+            p.data.normal_(0, 0.05)
+            p.data[:, 3] *= 8
+    return m.to(torch.bfloat16).cuda()
+
+
+def _batches(n=4, S=96, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    spread = 1 + 3 * torch.rand(H, generator=g)
+    return [(torch.randn(1, S, H, generator=g) * spread).to(torch.bfloat16).cuda() for _ in range(n)]
+
+
+def test_oneshot_rtn_nvfp4_fused_siblings():
+    """QuantizationModifier NVFP4 on every Linear: q/k/v and gate/up share min(global_scale); every tensor equals the oracle."""
+    from quantizers_b200.oneshot import oneshot
+
+    m = _model(3)
+    sd, cfg = oneshot(m, NVFP4_RECIPE)
+    assert cfg["format"] == "nvfp4-pack-quantized" and cfg["ignore"] == ["lm_head"]
+    assert not any(k.startswith("lm_head") for k in sd)
+    mods = dict(m.named_modules())
+    geom = O.Geom(O.GROUP, 16)
+    for layer in range(2):
+        for parent, sibs in ((f"model.layers.{layer}.self_attn", ("q_proj", "k_proj", "v_proj")), (f"model.layers.{layer}.mlp", ("gate_proj", "up_proj")),
+                             (f"model.layers.{layer}.self_attn", ("o_proj",)), (f"model.layers.{layer}.mlp", ("down_proj",))):
+            ws = [mods[f"{parent}.{s}"].weight.detach().cpu() for s in sibs]
+            gs = min(float(O.generate_gparam(float(w.float().min()), float(w.float().max()), torch.bfloat16)) for w in ws)
+            for s, w in zip(sibs, ws):
+                want = O.compress(w, "nvfp4-pack-quantized", geom, 4, True, torch.tensor([gs]))
+                for k, v in want.items():
+                    assert_bits_equal(sd[f"{parent}.{s}.{k}"].reshape(v.shape), v, f"{parent}.{s}.{k}")
+
+
+def test_oneshot_mixed_fp8_block_and_awq_int4():
+    """The reference's mixed recipe shape (REF:configs/recipes/recipe_mixed_fp8_int4.yaml): FP8_BLOCK RTN on attention, AWQ INT4 g32
+    on the MLP with explicit mappings.  Mapping resolution, search results and the final packed tensors are checked."""
+    from quantizers_b200 import recipe as RC
+    from quantizers_b200.oneshot import _Capture, awq_model, quantize_model
+
+    m = _model(5)
+    batches = _batches()
+    rec = RC.parse_recipe(RECIPE)
+    # what the search sees: inputs of the balance layers on the un-smoothed model
+    names = [f"model.layers.{l}.mlp.{p}" for l in range(2) for p in ("gate_proj", "down_proj")]
+    cap = _Capture(m, names, [])
+    with torch.no_grad():
+        for b in batches:
+            m(b)
+    cap.close()
+    x_cpu = {n: [t.cpu() for t in v] for n, v in cap.inputs.items()}
+    w0 = {n: p.detach().cpu().clone() for n, p in m.named_parameters()}
+
+    sd_a, cfg_a, results = awq_model(m, rec, batches)
+    sd_q, cfg_q = quantize_model(m, rec)
+    assert cfg_q["format"] == "float-quantized" and cfg_a["format"] == "pack-quantized"
+    assert len(results) == 4
+    geom = O.Geom(O.GROUP, 32)
+    for l in range(2):
+        pre = f"model.layers.{l}.mlp"
+        s_ref, r_ref, l_ref = R.compute_best_scale(x_cpu[f"{pre}.gate_proj"], [w0[f"{pre}.gate_proj.weight"], w0[f"{pre}.up_proj.weight"]],
+                                                   R.mlp_parent(w0[f"{pre}.down_proj.weight"]), geom, O.INT, 4, True)
+        s, r, losses = results[f"model.layers.{l}.post_attention_layernorm -> {pre}.gate_proj,{pre}.up_proj"]
+        assert r == r_ref and max(abs(a - b) / b for a, b in zip(losses, l_ref)) < 1e-3
+        assert torch.allclose(s, s_ref, rtol=1e-5)
+        # up -> down runs on the smoothed up_proj's output; check the fold-in of the first mapping and the final RTN tensors
+        new_w, new_ln = R.smooth([w0[f"{pre}.gate_proj.weight"]], w0[f"model.layers.{l}.post_attention_layernorm.weight"], s)
+        s2, _, _ = results[f"{pre}.up_proj -> {pre}.down_proj"]
+        assert_bits_equal(dict(m.named_parameters())[f"{pre}.gate_proj.weight"].detach(), new_w[0], "gate smoothed")
+        assert_bits_equal(dict(m.named_parameters())[f"model.layers.{l}.post_attention_layernorm.weight"].detach(), new_ln, "ln smoothed")
+        for p in ("gate_proj", "up_proj", "down_proj"):
+            w = dict(m.named_parameters())[f"{pre}.{p}.weight"].detach().cpu()
+            want = O.compress(w, "pack-quantized", geom, 4, True)
+            for k, v in want.items():
+                assert_bits_equal(sd_a[f"{pre}.{p}.{k}"].reshape(v.shape), v, f"{pre}.{p}.{k}")
+        for p in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            w = w0[f"model.layers.{l}.self_attn.{p}.weight"]
+            want = O.compress(w, "float-quantized", O.Geom(O.BLOCK, 0, 128, 128), 8, True)
+            for k, v in want.items():
+                assert_bits_equal(sd_q[f"model.layers.{l}.self_attn.{p}.{k}"].reshape(v.shape), v, f"attn {p}.{k}")
+
+
+def test_oneshot_refuses_cpu_weights():
+    from quantizers_b200.oneshot import oneshot
+
+    m = TinyLM().to(torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        oneshot(m, NVFP4_RECIPE)

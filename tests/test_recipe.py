@@ -1,0 +1,136 @@
+"""CPU: recipe (YAML) parsing and target / mapping resolution -- host logic behind the reference's recipe schema
+(REF:configs/recipes/*.yaml; the YAML below is typed here in that schema, not copied)."""
+import pytest
+import torch
+
+from quantizers_b200 import recipe as R
+
+AWQ_LIST_FORM = """
+quantization_scheme:
+  type: W4A16
+  targets: ["Linear"]
+modifiers:
+  - name: AWQModifier
+    config_groups:
+      group_0:
+        targets: ["Linear"]
+        weights: {num_bits: 4, type: int, symmetric: true, group_size: 32, strategy: group, dynamic: false, observer: memoryless_minmax}
+    ignore: ["lm_head"]
+    duo_scaling: true
+"""
+
+MIXED_STAGE_FORM = """
+quant_stage:
+  quant_modifiers:
+    QuantizationModifier:
+      targets: r"re:.*self_attn\\.(k|q|o|v)_proj.*"
+      scheme: FP8_BLOCK
+    AWQModifier:
+      mlp_projections:
+        group_0:
+          targets: ["re:.*(down|gate|up)_proj.*"]
+          weights: {num_bits: 4, type: int, symmetric: true, group_size: 32, strategy: group}
+      ignore: ["lm_head"]
+      duo_scaling: true
+      mappings:
+        - smooth_layer: re:.*post_attention_layernorm$
+          balance_layers: ["re:.*gate_proj$", "re:.*up_proj$"]
+        - smooth_layer: re:.*up_proj$
+          balance_layers: ["re:.*down_proj$"]
+"""
+
+MOE_NVFP4 = """
+default_stage:
+  default_modifiers:
+    QuantizationModifier:
+      scheme: NVFP4
+      targets:
+        - "re:.*mlp\\\\.experts\\\\.\\\\d+\\\\.(down_proj|gate_proj|up_proj)$"
+"""
+
+
+class Block(torch.nn.Module):
+    def __init__(self, h=32, i=64):
+        super().__init__()
+        self.input_layernorm = torch.nn.LayerNorm(h)
+        self.post_attention_layernorm = torch.nn.LayerNorm(h)
+        self.self_attn = torch.nn.Module()
+        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            setattr(self.self_attn, n, torch.nn.Linear(h, h, bias=False))
+        self.mlp = torch.nn.Module()
+        self.mlp.gate_proj = torch.nn.Linear(h, i, bias=False)
+        self.mlp.up_proj = torch.nn.Linear(h, i, bias=False)
+        self.mlp.down_proj = torch.nn.Linear(i, h, bias=False)
+
+
+class Tiny(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.model = torch.nn.Module()
+        self.model.layers = torch.nn.ModuleList([Block(), Block()])
+        self.lm_head = torch.nn.Linear(32, 100, bias=False)
+
+
+def test_list_form_and_ignore():
+    rec = R.parse_recipe(AWQ_LIST_FORM)
+    assert [m.kind for m in rec.modifiers] == ["AWQModifier"]
+    spec = rec.modifier("AWQModifier")
+    a = spec.config_groups[0].weights
+    assert (a.num_bits, a.type, a.symmetric, a.strategy, a.group_size, a.format) == (4, "int", True, "group", 32, "pack-quantized")
+    assert spec.ignore == ["lm_head"] and spec.duo_scaling is True and spec.n_grid == 20
+    m = Tiny()
+    lin = [(n, x) for n, x in m.named_modules() if isinstance(x, torch.nn.Linear)]
+    got = R.resolve_targets(lin, spec)
+    assert "lm_head" not in got and len(got) == 14
+
+
+def test_stage_form_mixed_and_mappings():
+    rec = R.parse_recipe(MIXED_STAGE_FORM)
+    assert [m.kind for m in rec.modifiers] == ["QuantizationModifier", "AWQModifier"]
+    q, a = rec.modifiers
+    assert q.config_groups[0].preset == "FP8_BLOCK" and q.config_groups[0].weights.block_structure == [128, 128]
+    assert q.config_groups[0].targets == ["re:.*self_attn\\.(k|q|o|v)_proj.*"]   # python-literal debris stripped
+    assert a.config_groups[0].weights.group_size == 32 and len(a.mappings) == 2
+    m = Tiny()
+    lin = [(n, x) for n, x in m.named_modules() if isinstance(x, torch.nn.Linear)]
+    assert sorted(R.resolve_targets(lin, q)) == sorted(n for n, _ in lin if "self_attn" in n)
+    assert sorted(R.resolve_targets(lin, a)) == sorted(n for n, _ in lin if "mlp" in n)
+    names = [n for n, _ in m.named_modules()]
+    maps = R.resolve_mappings(names, a)
+    assert ("model.layers.0.post_attention_layernorm", ["model.layers.0.mlp.gate_proj", "model.layers.0.mlp.up_proj"],
+            "model.layers.0.mlp") in maps
+    assert ("model.layers.1.mlp.up_proj", ["model.layers.1.mlp.down_proj"], "model.layers.1.mlp.down_proj") in maps
+    assert len(maps) == 4
+
+
+def test_moe_regex_targets_and_presets():
+    spec = R.parse_recipe(MOE_NVFP4).modifier("QuantizationModifier")
+    g = spec.config_groups[0]
+    assert g.weights.format == "nvfp4-pack-quantized" and g.input_activations.observer == "static_minmax"
+    lin = torch.nn.Linear(4, 4)
+    named = [("model.layers.3.mlp.experts.17.gate_proj", lin), ("model.layers.3.mlp.gate", lin),
+             ("model.layers.3.mlp.shared_expert.up_proj", lin), ("model.layers.3.self_attn.q_proj", lin)]
+    assert list(R.resolve_targets(named, spec)) == ["model.layers.3.mlp.experts.17.gate_proj"]
+
+
+def test_presets_match_compressed_tensors():
+    ct = pytest.importorskip("compressed_tensors.quantization.quant_scheme")
+    for name, kw in R._PRESET_WEIGHTS.items():
+        w = ct.PRESET_SCHEMES[name].get("weights")
+        if kw is None:
+            assert w is None
+            continue
+        val = lambda v: getattr(v, "value", v)
+        assert (w.num_bits, val(w.type), w.symmetric, val(w.strategy), w.group_size, w.block_structure) == (
+            kw["num_bits"], kw["type"], kw["symmetric"], kw["strategy"], kw.get("group_size"), kw.get("block_structure")), name
+
+
+def test_errors():
+    with pytest.raises(ValueError):
+        R.parse_recipe("foo: 1")
+    with pytest.raises(ValueError):
+        R.parse_recipe("modifiers:\n  - name: QuantizationModifier\n    scheme: W3A3\n")
+    with pytest.raises(ValueError):
+        R._args_from_dict(dict(num_bits=4, type="int", strategy="group"))
+    with pytest.raises(ValueError):
+        R._args_from_dict(dict(num_bits=4, type="int", strategy="group", group_size=128, actorder="group"))
