@@ -394,13 +394,70 @@ def run_moe_awq(args, dev, world, rank, peaks):
     flops = awq.expert_mapping_flops(T, 1536, 3072) * args.moe_awq_experts
     tf = awq.expert_mapping_flops(T, 1536, 3072) * len(experts) / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1500.0)))
-    return {"metric": "awq_expert_mappings_per_s", "value": args.moe_awq_experts / (ms * 1e-3), "unit": "experts/s", "ms_total": ms,
-            "scaling": "strong",
-            "config": {"workload": "minimax-m2.1 experts-only AWQ INT4 g32 sym, per-expert w3->w2 mappings, n_grid 20, duo_scaling",
-                       "experts": args.moe_awq_experts, "experts_per_gpu": len(experts), "tokens": T, "flops_total": flops,
-                       "best_ratios_first4": [r[1] for r in res[:4]]},
+    out = {"metric": "awq_expert_mappings_per_s", "value": args.moe_awq_experts / (ms * 1e-3), "unit": "experts/s", "ms_total": ms,
+           "scaling": "strong",
+           "config": {"workload": "minimax-m2.1 experts-only AWQ INT4 g32 sym, per-expert w3->w2 mappings, n_grid 20, duo_scaling",
+                      "experts": args.moe_awq_experts, "experts_per_gpu": len(experts), "tokens": T, "flops_total": flops,
+                      "best_ratios_first4": [r[1] for r in res[:4]]},
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+                        "kernel": "awq_gemm_loss_kernel (tcgen05, TMEM)", "note": "per-GPU figure of the slowest rank"}}
+    del xs, copies, w2, w3
+    awq.workspace.release()
+    torch.cuda.empty_cache()
+    if args.moe_block_experts > 0:
+        out["layer_mapping"] = run_moe_block(args, dev, world, rank, peak)
+    return out
+
+
+def run_moe_block(args, dev, world, rank, peak):
+    """configs[4] kind (i): the layer-wide mapping post_attention_layernorm -> every expert's w1, w3 (one scale vector, parent =
+    the routed sparse-MoE block, top-8 routing) on a reduced layer of ``--moe-block-experts`` experts.  All experts live on every
+    rank; the T calibration tokens are sharded across the ranks (strong scaling) and the |x| sums / [n_grid] loss accumulators
+    are all-reduced over NCCL -- the one real exchange step of the path."""
+    import torch.distributed as dist
+
+    from quantizers_b200 import awq
+    from quantizers_b200 import scheduler as S
+
+    E, H, I, K = args.moe_block_experts, 3072, 1536, 8
+    T = args.awq_tokens
+    qargs = S.PRESETS["INT4_G32_SYM"]
+    units = list(range(E))
+    w1 = S.synth_stack(units, I, H, 0, dev)
+    w3 = S.synth_stack(units, I, H, 1, dev)
+    w2 = S.synth_stack(units, H, I, 2, dev)
+    g = torch.Generator(device=dev).manual_seed(4321)
+    x_all = (torch.randn(T, H, generator=g, device=dev) * (1 + 3 * torch.rand(H, generator=g, device=dev))).to(torch.bfloat16)
+    router = torch.randn(E, H, generator=g, device=dev) * 0.02
+    tok = S.partition(T, world, rank)
+    x = x_all[tok.start:tok.stop].contiguous()
+    p = torch.softmax(x.float() @ router.t(), dim=-1)
+    topk_w, topk_idx = torch.topk(p, K, dim=-1)
+    topk_w = topk_w / topk_w.sum(-1, keepdim=True)
+    del x_all
+    pg = dist.group.WORLD if world > 1 else None
+    awq.search_moe_block_mapping(x, w1, w3, w2, topk_idx, topk_w, qargs, process_group=pg)   # warm-up pass
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    s, ratio, losses = awq.search_moe_block_mapping(x, w1, w3, w2, topk_idx, topk_w, qargs, process_group=pg)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    tf = awq.moe_block_flops(len(tok), K, H, I) / (ms * 1e-3) / 1e12
+    awq.workspace.release()
+    return {"metric": "awq_layer_mappings_per_s", "value": 1e3 / ms, "unit": "mappings/s", "ms": ms, "scaling": "strong",
+            "config": {"workload": "minimax-m2.1 layer-wide mapping (post_attention_layernorm -> all experts' w1/w3), routed block parent",
+                       "experts": E, "top_k": K, "tokens": T, "tokens_per_gpu": len(tok), "best_ratio": ratio,
+                       "collective": "all-reduce(SUM) of |x| sums and [n_grid] loss accumulators" if world > 1 else None},
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
-                         "kernel": "awq_gemm_loss_kernel (tcgen05, TMEM)", "note": "per-GPU figure of the slowest rank"}}
+                         "kernel": "awq_gemm_project_kernel (tcgen05, TMEM), one small launch per expert and stage",
+                         "note": "T * k / E routed tokens per expert and launch; gather / index_add_ / squared error run beside the GEMMs; per-GPU figure of the slowest rank"}}
 
 
 # ----------------------------------------------------------------------------- main arm
@@ -418,6 +475,7 @@ def main():
     ap.add_argument("--moe-layers", type=int, default=8, help="layers of the Qwen3-30B-A3B NVFP4 expert-sharded leg (0 disables it)")
     ap.add_argument("--moe-steps", type=int, default=20)
     ap.add_argument("--moe-awq-experts", type=int, default=16, help="experts of the MiniMax-M2.1 per-expert AWQ leg (0 disables it)")
+    ap.add_argument("--moe-block-experts", type=int, default=32, help="experts of the reduced layer of the layer-wide MoE mapping leg (0 disables it)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -195,6 +195,28 @@ def mlp_parent(down: torch.Tensor):
     return f
 
 
+def moe_block_parent(w2: Sequence[torch.Tensor], topk_idx: torch.Tensor, topk_w: torch.Tensor):
+    """parent of the layer-wide MoE mapping (post_attention_layernorm -> every expert's w1, w3): the routed sparse-MoE block as
+    transformers writes it (Mixtral / Qwen3-MoE style): per expert, gather its routed tokens, ``w2(silu(w1 x) * (w3 x))``, scale
+    by the routing weight (cast to the hidden dtype) and ``index_add_`` into the bf16 output, experts in index order.
+    ``weights = [w1_0, w3_0, w1_1, w3_1, ...]``; ``x`` holds ALL calibration tokens (routing rows line up with it)."""
+
+    def f(weights: List[torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+        lin = torch.nn.functional.linear
+        out = torch.zeros_like(x[:, : w2[0].shape[0]])
+        for e in range(len(w2)):
+            tok, slot = torch.where(topk_idx == e)
+            if tok.numel() == 0:
+                continue
+            xe = x[tok]
+            h = torch.nn.functional.silu(lin(xe, weights[2 * e])) * lin(xe, weights[2 * e + 1])
+            y = lin(h, w2[e]) * topk_w[tok, slot, None].to(x.dtype)
+            out.index_add_(0, tok, y.to(x.dtype))
+        return out
+
+    return f
+
+
 def attention_parent(o_proj: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, q_norm: torch.Tensor, k_norm: torch.Tensor,
                      rope_theta: float = 1e6, eps: float = 1e-6):
     """parent of q/k/v: transformers ``Qwen3Attention.forward`` on one calibration sample ``x [S, K]`` (batch 1, causal mask,

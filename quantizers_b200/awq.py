@@ -481,3 +481,93 @@ def search_expert_mappings(x_in: Sequence[torch.Tensor], balance: torch.Tensor, 
         n = all_acc.shape[1] - 1
         out.append((all_scales[e], ratios[bi], (all_acc[e, :n] / all_acc[e, n]).tolist()))
     return out
+
+
+def moe_block_flops(T: int, top_k: int, hidden: int, inter: int, n_grid: int = 20) -> float:
+    """ALGORITHMIC FLOPs of the layer-wide MoE mapping search: (n_grid + 1) evaluations of the routed block, 3 GEMMs of
+    2 * hidden * inter per routed (token, expert) pair (un-routed pairs do not reach the block output)."""
+    return (n_grid + 1) * 3 * 2.0 * T * top_k * hidden * inter
+
+
+class RoutedMoE:
+    """The routed sparse-MoE block as an AWQ parent: ``out[t] = sum_{j < k} p[t, j] * w2_e( act(w1_e x_t) * (w3_e x_t) )`` with
+    ``e = topk_idx[t, j]``, accumulated expert by expert with ``index_add_`` in the activation dtype like the transformers
+    Mixtral / Qwen3-MoE / MiniMax blocks do.  Routing depends on x and the (un-quantized) router only, so it is computed once by
+    the caller.  Under ``moe_calibrate_all_experts`` every expert additionally runs on all tokens, but only routed pairs reach
+    the block output that the loss is taken on, so only those are evaluated here (same output, 1 / (E / k) of the FLOPs)."""
+
+    def __init__(self, x: torch.Tensor, w2: torch.Tensor, topk_idx: torch.Tensor, topk_w: torch.Tensor):
+        L.require_cuda(x, w2, topk_idx, topk_w)
+        T, k = topk_idx.shape
+        E = w2.shape[0]
+        flat = topk_idx.reshape(-1).to(torch.int64)
+        order = torch.argsort(flat, stable=True)
+        self.tok = (order // k).contiguous()
+        self.pw = topk_w.reshape(-1)[order].to(x.dtype).unsqueeze(1).contiguous()
+        counts = torch.bincount(flat, minlength=E)
+        self.off = [0] + torch.cumsum(counts, 0).tolist()   # the one host round trip of the mapping
+        self.xs = x.index_select(0, self.tok)                # routed inputs, expert-major
+        self.w2, self.T, self.H = w2, T, x.shape[1]
+
+    def __call__(self, w13: torch.Tensor) -> torch.Tensor:
+        """w13 ``[E, 2 * I, H]`` (w1 rows, then w3 rows) -> block output ``[T, H]``."""
+        out = torch.zeros((self.T, self.H), dtype=self.xs.dtype, device=self.xs.device)
+        for e in range(self.w2.shape[0]):
+            a, b = self.off[e], self.off[e + 1]
+            if a == b:
+                continue
+            h = gemm_project(self.xs[a:b], w13[e:e + 1], swiglu=True)[0]
+            y = gemm_project(h, self.w2[e:e + 1], swiglu=False)[0]
+            out.index_add_(0, self.tok[a:b], y * self.pw[a:b])
+        return out
+
+
+@torch.no_grad()
+def search_moe_block_mapping(x: torch.Tensor, w1: torch.Tensor, w3: torch.Tensor, w2: torch.Tensor, topk_idx: torch.Tensor,
+                             topk_w: torch.Tensor, args, n_grid: int = 20, duo_scaling: bool = True, process_group=None,
+                             max_variant_bytes: int = 16 << 30) -> Tuple[torch.Tensor, float, List[float]]:
+    """The layer-wide MoE mapping ``post_attention_layernorm -> every expert's w1, w3`` (REF:configs/recipes/
+    recipe_Minimax-M2.1-Experts-only-AWQ.yaml:29-31; Qwen3-MoE's ``post_attention_layernorm -> experts.*.gate/up``): ONE scale
+    vector ``s[H]`` shared by all 2E balance matrices, ``w_mean`` over all their rows, ``x_mean`` over all tokens (the hook sits on
+    expert 0's w1, which sees every token under calibrate-all-experts), parent = the routed block (``RoutedMoE``), loss on its
+    output.
+
+    x [T, H] bf16, w1 / w3 [E, I, H], w2 [E, H, I], topk_idx / topk_w [T, k].  The weight variants of a ratio are 2 * E * I * H
+    elements, so ratios are processed in chunks of at most ``max_variant_bytes``.  With ``process_group`` the ranks hold token
+    shards of the same layer (all experts on every rank): |x| sums and the loss accumulators are all-reduced.
+    Returns (best_scales cpu fp32 [H], best_ratio, losses[n_grid]); the caller applies ``smooth`` to w1 / w3 / the norm."""
+    import torch.distributed as dist
+
+    L.require_cuda(x, w1, w3, w2)
+    if x.dtype != torch.bfloat16:
+        raise L.B200QError("search_moe_block_mapping runs on the bf16 tensor-core path")
+    E, I, H = w1.shape
+    dev = x.device
+    dist_on = process_group is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+    w13 = torch.cat([w1, w3], dim=1).contiguous()              # [E, 2I, H]
+    xsum = abs_sum_cols(x)
+    if dist_on:
+        x_mean = reduce_token_stats(xsum, torch.full((1,), float(x.shape[0]), dtype=torch.float64, device=dev), process_group)
+    else:
+        x_mean = xsum / float(x.shape[0])
+    rows_per_call = 262144  # launch limit of the row-tiled kernels
+    flat = w13.view(-1, H)
+    w_mean = compute_layer_means([flat[r0:r0 + rows_per_call] for r0 in range(0, flat.shape[0], rows_per_call)], args.group_size) if duo_scaling else None
+    ratios = [i / n_grid for i in range(n_grid)]
+    scales = awq_scales(x_mean, w_mean, ratios, duo_scaling)
+    parent = RoutedMoE(x, w2, topk_idx, topk_w)
+    ref = parent(w13)
+    acc = torch.zeros(n_grid + 1, dtype=torch.float32, device=dev)
+    per_ratio = w13.numel() * w13.element_size()
+    chunk = max(1, min(n_grid, int(max_variant_bytes // max(per_ratio, 1))))
+    for r0 in range(0, n_grid, chunk):
+        r1 = min(n_grid, r0 + chunk)
+        variants = workspace.get("moe_w13", (r1 - r0, E, 2 * I, H), w13.dtype, dev)
+        vflat = variants.view(r1 - r0, E * 2 * I, H)
+        for q0 in range(0, flat.shape[0], rows_per_call):
+            scaled_fake_quantize_grid(flat[q0:q0 + rows_per_call], scales[r0:r1], args, vflat[:, q0:q0 + rows_per_call])
+        for r in range(r0, r1):
+            sq_err_accumulate(ref, parent(variants[r - r0]), acc[r:r + 1])
+    acc[n_grid:].fill_(float(ref.numel()))
+    best_i, losses = reduce_and_select(acc, process_group if dist_on else None, dist_on)
+    return scales[best_i].cpu(), ratios[best_i], losses

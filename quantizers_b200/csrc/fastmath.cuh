@@ -35,6 +35,33 @@ __device__ __forceinline__ f32x2 mul2_plus0(f32x2 a, f32x2 b) {
 // the two bf16 halves of a 32-bit word as an fp32 pair (lo element first)
 __device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t w) { return pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
 
+// ---- ALU-pipe relief.  ncu on every bf16 fast kernel shows the half-rate ALU pipe (LOP3 / PRMT / F2FP / HMNMX2 / VIMNMX) at
+// 60-70 % with the FMA pipe at 20-35 %: the kernels are bound by ALU issue, not by HBM.  These variants move work across:
+// bf16 -> fp32 through the mixed-precision FMA (FHFMA.BF16 reads either half of the word directly: x * 1 + (-0.0) is exact for
+// every x including -0.0), instead of IMAD.SHL + LOP3
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2_fma(uint32_t w) {
+    float lo, hi;
+    asm("{ .reg .b16 l, h; mov.b32 {l, h}, %2; fma.rn.f32.bf16 %0, l, %3, %4; fma.rn.f32.bf16 %1, h, %3, %4; }"
+        : "=f"(lo), "=f"(hi) : "r"(w), "h"((unsigned short)0x3f80), "f"(-0.0f));
+    return pack2(lo, hi);
+}
+// "do the two bracket ends round to the same bf16?" accumulated on the FMA pipe: acc += (a - b)^2 per half (HFMA2.BF16); a zero
+// accumulator means every pair was equal.  (a - b)^2 can only underflow to zero for |a| < ~1e-17, where both ends quantize to
+// the same code anyway; inf - inf gives NaN, which reads as "different".
+__device__ __forceinline__ uint32_t hdiff2_acc(uint32_t a, uint32_t b, uint32_t acc) {
+    uint32_t d;
+    asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    asm("fma.rn.bf16x2 %0, %1, %1, %2;" : "=r"(acc) : "r"(d), "r"(acc));
+    return acc;
+}
+__device__ __forceinline__ bool hdiff2_any(uint32_t acc) { return (acc & 0x7fff7fffu) != 0; }
+// x + (x >> 4) in one instruction (mad.hi -> LEA.HI): merges neighbouring nibbles-in-bytes
+__device__ __forceinline__ uint32_t fold_nibbles(uint32_t x) {
+    uint32_t r;
+    asm("mad.hi.u32 %0, %1, %2, %1;" : "=r"(r) : "r"(x), "r"(0x10000000u));
+    return r;
+}
+
 struct Bracket {
     f32x2 lo, hi;  // (r_lo, r_lo), (r_hi, r_hi)
     __device__ __forceinline__ void init(float s) {

@@ -92,7 +92,9 @@ __device__ __noinline__ uint2 repair_chunk(const uint4 raw, float s, float z, bo
 }
 
 // LOG2N: log2(chunks per group): 1 (g16) 2 (g32) 3 (g64) 4 (g128)
-template <int QT, bool SYM, int LOG2N>
+// FMA: ALU-pipe relief variants (fastmath.cuh): FHFMA unpack, DPX 3-input max for the asymmetric statistics, bracket agreement
+// accumulated with HFMA2, nibble folding with LEA.HI
+template <int QT, bool SYM, int LOG2N, bool FMA>
 __global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(const TmaParams p) {
     constexpr int kWarps = WarpsFor<QT>::value;
     constexpr int N = 1 << LOG2N;          // chunks per group
@@ -192,6 +194,26 @@ __global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(
                 }
                 st_a = hmaxabs2(a0, a1);
                 st_a = hmaxabs2(st_a, prmt(st_a, st_a, 0x1032));
+            } else if (FMA) {
+                // max(max, 0) and min(min, 0) are all the asymmetric qparams need (helpers.py:72-73), and both are MAX reductions on
+                // the raw bf16 bits: as s16 the largest positive float wins (RELU clamps an all-negative group to +0), as u16 the
+                // negative float of largest magnitude wins (a result below 0x8000 means "no negative element").  DPX 3-input
+                // VIMNMX3 halves the op count of the HMNMX2 max + min chains.
+                uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+#pragma unroll
+                for (int i = 0; i < N; i += 2) {
+                    const uint4 v0 = lds128(gaddr + (((i + rot) & (N - 1)) << 4));
+                    const uint4 v1 = lds128(gaddr + (((i + 1 + rot) & (N - 1)) << 4));
+                    a0 = __vimax3_s16x2_relu(__vimax3_s16x2_relu(v0.x, v0.y, v0.z), v0.w, a0);
+                    b0 = __vimax3_u16x2(__vimax3_u16x2(v0.x, v0.y, v0.z), v0.w, b0);
+                    a1 = __vimax3_s16x2_relu(__vimax3_s16x2_relu(v1.x, v1.y, v1.z), v1.w, a1);
+                    b1 = __vimax3_u16x2(__vimax3_u16x2(v1.x, v1.y, v1.z), v1.w, b1);
+                }
+                st_a = __vimax3_s16x2_relu(a0, a1, prmt(a0, a1, 0x1032));   // low half: max over both halves of a0 and a1's high
+                st_a = __vmaxs2(st_a, prmt(st_a, st_a, 0x1032));
+                st_b = __vimax3_u16x2(b0, b1, prmt(b0, b1, 0x1032));
+                st_b = __vmaxu2(st_b, prmt(st_b, st_b, 0x1032));
+                if ((st_b & 0x8000u) == 0) st_b = 0;                         // no negative element: min(min, 0) = 0
             } else {
                 uint32_t a0 = 0xff80ff80u, a1 = 0xff80ff80u, b0 = 0x7f807f80u, b1 = 0x7f807f80u;  // -inf / +inf
 #pragma unroll
@@ -277,21 +299,29 @@ __global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(
                 uint32_t h[4], diff = 0;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const f32x2 x = bf16x2_to_f32x2(w[k]);
+                    const f32x2 x = FMA ? bf16x2_to_f32x2_fma(w[k]) : bf16x2_to_f32x2(w[k]);
                     float al, ah, bl, bh;
                     if (QT == QT_INT) {
                         unpack2(mul2(x, br.lo), al, ah);
                         unpack2(mul2(x, br.hi), bl, bh);
                         uint32_t u = cvt_bf16x2(ah, al);
-                        diff |= u ^ cvt_bf16x2(bh, bl);
+                        if (FMA) diff = hdiff2_acc(u, cvt_bf16x2(bh, bl), diff);
+                        else diff |= u ^ cvt_bf16x2(bh, bl);
                         if (!SYM) u = hadd2(u, z2);
                         h[k] = __viaddmin_s16x2_relu(hadd2(u, kMagic), kUnbias, 0x000f000fu);
                     } else if (QT == QT_FP8) {
                         unpack2(add_zp ? mul2_plus0(x, br.lo) : mul2(x, br.lo), al, ah);
                         unpack2(add_zp ? mul2_plus0(x, br.hi) : mul2(x, br.hi), bl, bh);
                         const uint32_t u = cvt_bf16x2(ah, al);
-                        diff |= u ^ cvt_bf16x2(bh, bl);
-                        h[k] = cvt_e4m3x2(__uint_as_float(u & 0xffff0000u), __uint_as_float(u << 16));
+                        if (FMA) diff = hdiff2_acc(u, cvt_bf16x2(bh, bl), diff);
+                        else diff |= u ^ cvt_bf16x2(bh, bl);
+                        if (FMA) {
+                            float ul, uh;
+                            unpack2(bf16x2_to_f32x2_fma(u), ul, uh);
+                            h[k] = cvt_e4m3x2(uh, ul);
+                        } else {
+                            h[k] = cvt_e4m3x2(__uint_as_float(u & 0xffff0000u), __uint_as_float(u << 16));
+                        }
                     } else {
                         unpack2(mul2_plus0(x, br.lo), al, ah);
                         unpack2(mul2_plus0(x, br.hi), bl, bh);
@@ -302,13 +332,15 @@ __global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(
                 uint2 packed;
                 if (QT == QT_INT) {
                     const uint32_t x01 = prmt(h[0], h[1], 0x6420), x23 = prmt(h[2], h[3], 0x6420);
-                    packed = make_uint2(prmt(x01 | (x01 >> 4), x23 | (x23 >> 4), 0x6420), 0u);
+                    if (FMA) packed = make_uint2(prmt(fold_nibbles(x01), fold_nibbles(x23), 0x6420), 0u);
+                    else packed = make_uint2(prmt(x01 | (x01 >> 4), x23 | (x23 >> 4), 0x6420), 0u);
                 } else if (QT == QT_FP8) {
                     packed = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
                 } else {
                     packed = make_uint2(h[0] | (h[1] << 8) | (h[2] << 16) | (h[3] << 24), 0u);
                 }
-                if (diff != 0 || unsafe) packed = repair_chunk<QT, SYM>(v, s, z, add_zp, unsafe, packed);
+                const bool differ = (FMA && QT != QT_FP4) ? hdiff2_any(diff) : diff != 0;
+                if (differ || unsafe) packed = repair_chunk<QT, SYM>(v, s, z, add_zp, unsafe, packed);
                 if (QT == QT_FP8) sts64(oaddr + c * 8, packed);
                 else sts32(oaddr + c * 4, packed.x);
             }
@@ -326,22 +358,28 @@ __global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(
     if (lane == 0) bulk_wait0();
 }
 
-template <int QT, bool SYM, int LOG2N>
-int launch_tma(const TmaParams& p, cudaStream_t st) {
+template <int QT, bool SYM, int LOG2N, bool FMA>
+int launch_tma_v(const TmaParams& p, cudaStream_t st) {
     constexpr int OUT_BYTES = 512 * ((QT == QT_FP8) ? 8 : 4);
     constexpr int kWarps = WarpsFor<QT>::value;
     const size_t smem = (size_t)kWarps * (kStages * kTileBytes + OUT_BYTES + 64);
     static bool configured = false;  // benign race: idempotent attribute
     if (!configured) {
-        cudaFuncSetAttribute(group_tma_kernel<QT, SYM, LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(group_tma_kernel<QT, SYM, LOG2N, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     constexpr int GPT = 32 * (16 >> LOG2N);
     const int64_t n_tiles = (p.n_groups + GPT - 1) / GPT;
     const int64_t ctas = max((int64_t)1, min((int64_t)kNumSMs, (n_tiles + kWarps - 1) / kWarps));
-    group_tma_kernel<QT, SYM, LOG2N><<<(unsigned)ctas, kWarps * 32, smem, st>>>(p);
+    group_tma_kernel<QT, SYM, LOG2N, FMA><<<(unsigned)ctas, kWarps * 32, smem, st>>>(p);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
+}
+
+template <int QT, bool SYM, int LOG2N>
+int launch_tma(const TmaParams& p, cudaStream_t st) {
+    static const bool legacy = getenv("B200Q_TMA_LEGACY_ALU") != nullptr;  // A/B switch for the ALU-pipe relief variants
+    return legacy ? launch_tma_v<QT, SYM, LOG2N, false>(p, st) : launch_tma_v<QT, SYM, LOG2N, true>(p, st);
 }
 
 }  // namespace

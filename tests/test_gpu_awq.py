@@ -292,3 +292,30 @@ def test_search_expert_mappings_matches_oracle():
         assert_bits_equal(w3_dev[e], new_s, f"w3[{e}] smoothed")
     with pytest.raises(ValueError):
         awq.search_expert_mappings([xs[0].cuda()], w2_dev, Args("int4_g32_sym"))
+
+
+def test_search_moe_block_mapping_matches_oracle():
+    """config 5 (i): ONE scale vector for all experts' w1 / w3, parent = the routed sparse-MoE block, loss on its output.
+    Routing (top-2 of 6 experts, one expert never routed) is computed once and handed to both sides."""
+    from quantizers_b200 import awq
+
+    E, T, H, I, K = 6, 640, 256, 384, 2
+    g = torch.Generator().manual_seed(23)
+    x = (torch.randn(T, H, generator=g) * (1 + 3 * torch.rand(H, generator=g))).to(torch.bfloat16)
+    w1 = (torch.randn(E, I, H, generator=g) * 0.05).to(torch.bfloat16)
+    w3 = (torch.randn(E, I, H, generator=g) * 0.05).to(torch.bfloat16)
+    w2 = (torch.randn(E, H, I, generator=g) * 0.05).to(torch.bfloat16)
+    logits = torch.randn(T, E, generator=g)
+    logits[:, 4] = -1e9                                           # expert 4 is never routed
+    p = torch.softmax(logits, dim=-1)
+    topk_w, topk_idx = torch.topk(p, K, dim=-1)
+    topk_w = (topk_w / topk_w.sum(-1, keepdim=True))
+    geom = O.Geom(O.GROUP, 32)
+    weights = [w for e in range(E) for w in (w1[e], w3[e])]
+    s_ref, r_ref, l_ref = R.compute_best_scale([x], weights, R.moe_block_parent([w2[e] for e in range(E)], topk_idx, topk_w), geom, O.INT, 4, True)
+    for budget in (16 << 30, 3 * 2 * E * I * H * 2):   # all ratios at once / three per chunk
+        s, r, l = awq.search_moe_block_mapping(x.cuda(), w1.cuda(), w3.cuda(), w2.cuda(), topk_idx.cuda(), topk_w.cuda(), Args("int4_g32_sym"),
+                                               max_variant_bytes=budget)
+        assert max(abs(a - b) / b for a, b in zip(l, l_ref)) < 1e-3, [abs(a - b) / b for a, b in zip(l, l_ref)]
+        assert r == r_ref
+        assert torch.allclose(s, s_ref, rtol=1e-5)
