@@ -25,11 +25,12 @@ namespace {
 using namespace fast;
 
 constexpr int kStages = 2;
-constexpr int kTileElems = 4096;
-// warps per CTA (one CTA per SM): as many as shared memory allows -- ncu showed 8 warps/SM leave the issue slots
-// half idle (serial qparam chains, LDS/MUFU latency)
-template <int QT> struct WarpsFor { static constexpr int value = (QT == QT_FP8) ? 10 : 12; };
-constexpr int kTileBytes = kTileElems * 2;
+// warps per CTA (one CTA per SM): as many as shared memory allows.  ncu: with 8 KB tiles (12 warps = 3 per scheduler) neither the
+// ALU nor the FMA pipe is saturated (51 % / 31 %), issue slots are 65 % busy and the stalls are fixed-latency waits -- too few
+// warps to hide them.  4 KB tiles double the warps per SM; a group of 128 is then shared by a pair of lanes.
+template <int QT, int TILE> struct WarpsFor {
+    static constexpr int value = TILE == 4096 ? ((QT == QT_FP8) ? 10 : 12) : ((QT == QT_FP8) ? 20 : 24);
+};
 
 using namespace async;
 
@@ -94,16 +95,20 @@ __device__ __noinline__ uint2 repair_chunk(const uint4 raw, float s, float z, bo
 // LOG2N: log2(chunks per group): 1 (g16) 2 (g32) 3 (g64) 4 (g128)
 // FMA: ALU-pipe relief variants (fastmath.cuh): FHFMA unpack, DPX 3-input max for the asymmetric statistics, bracket agreement
 // accumulated with HFMA2, nibble folding with LEA.HI
-template <int QT, bool SYM, int LOG2N, bool FMA>
-__global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(const TmaParams p) {
-    constexpr int kWarps = WarpsFor<QT>::value;
-    constexpr int N = 1 << LOG2N;          // chunks per group
-    constexpr int GPL = 16 / N;            // groups per lane per tile
+template <int QT, bool SYM, int LOG2N, bool FMA, int TILE>
+__global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_kernel(const TmaParams p) {
+    constexpr int kWarps = WarpsFor<QT, TILE>::value;
+    constexpr int kTileBytes = TILE * 2;
+    constexpr int N = 1 << LOG2N;          // chunks (8 elements, 16 bytes) per group
     constexpr int G = 8 * N;               // group size
-    constexpr int GPT = 32 * GPL;          // groups per tile
+    constexpr int GPT = TILE / G;          // groups per tile
+    constexpr int LPG = GPT >= 32 ? 1 : 32 / GPT;   // lanes sharing one group (2 for g128 in a 4 KB tile)
+    constexpr int GPL = GPT >= 32 ? GPT / 32 : 1;   // groups per lane per tile
+    constexpr int NL = N / LPG;            // chunks of a group per lane
     constexpr int OUT_CHUNK = (QT == QT_FP8) ? 8 : 4;  // output bytes per 8-element chunk
-    constexpr int OUT_BYTES = 512 * OUT_CHUNK;         // per tile
-    constexpr int ROT_SHIFT = (LOG2N >= 3) ? 0 : (3 - LOG2N);
+    constexpr int OUT_BYTES = (TILE / 8) * OUT_CHUNK;  // per tile
+    constexpr int ROT_SHIFT = (LPG > 1 || LOG2N >= 3) ? 0 : (3 - LOG2N);
+    static_assert(LPG <= 2 && NL >= 2, "tile / group geometry");
 
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -178,17 +183,19 @@ __global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(
 
 #pragma unroll (GPL >= 4 ? 2 : 1)
         for (int gi = 0; gi < GPL; gi++) {
-            const int gl = gi * 32 + lane;           // group index inside the tile
+            const int gl = LPG == 1 ? gi * 32 + lane : lane / LPG;   // group index inside the tile
+            const int half = LPG == 1 ? 0 : lane % LPG;                // which part of the group this lane owns
             const bool act = gl < n_here;            // partial last tile: inactive lanes compute on stale smem, store nothing
-            const uint32_t gaddr = tin + (uint32_t)gl * (G * 2);
+            const bool owner = act && half == 0;     // writes the group's qparams
+            const uint32_t gaddr = tin + (uint32_t)gl * (G * 2) + (uint32_t)half * (NL * 16);
             // ---- A. statistics (two independent chains for ILP)
             uint32_t st_a, st_b = 0;
             if (SYM) {
                 uint32_t a0 = 0, a1 = 0;
 #pragma unroll
-                for (int i = 0; i < N; i += 2) {
-                    const uint4 v0 = lds128(gaddr + (((i + rot) & (N - 1)) << 4));
-                    const uint4 v1 = lds128(gaddr + (((i + 1 + rot) & (N - 1)) << 4));
+                for (int i = 0; i < NL; i += 2) {
+                    const uint4 v0 = lds128(gaddr + (((i + rot) & (NL - 1)) << 4));
+                    const uint4 v1 = lds128(gaddr + (((i + 1 + rot) & (NL - 1)) << 4));
                     a0 = hmaxabs2(a0, hmaxabs2(hmaxabs2(v0.x, v0.y), hmaxabs2(v0.z, v0.w)));
                     a1 = hmaxabs2(a1, hmaxabs2(hmaxabs2(v1.x, v1.y), hmaxabs2(v1.z, v1.w)));
                 }
@@ -201,9 +208,9 @@ __global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(
                 // VIMNMX3 halves the op count of the HMNMX2 max + min chains.
                 uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
 #pragma unroll
-                for (int i = 0; i < N; i += 2) {
-                    const uint4 v0 = lds128(gaddr + (((i + rot) & (N - 1)) << 4));
-                    const uint4 v1 = lds128(gaddr + (((i + 1 + rot) & (N - 1)) << 4));
+                for (int i = 0; i < NL; i += 2) {
+                    const uint4 v0 = lds128(gaddr + (((i + rot) & (NL - 1)) << 4));
+                    const uint4 v1 = lds128(gaddr + (((i + 1 + rot) & (NL - 1)) << 4));
                     a0 = __vimax3_s16x2_relu(__vimax3_s16x2_relu(v0.x, v0.y, v0.z), v0.w, a0);
                     b0 = __vimax3_u16x2(__vimax3_u16x2(v0.x, v0.y, v0.z), v0.w, b0);
                     a1 = __vimax3_s16x2_relu(__vimax3_s16x2_relu(v1.x, v1.y, v1.z), v1.w, a1);
@@ -213,13 +220,12 @@ __global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(
                 st_a = __vmaxs2(st_a, prmt(st_a, st_a, 0x1032));
                 st_b = __vimax3_u16x2(b0, b1, prmt(b0, b1, 0x1032));
                 st_b = __vmaxu2(st_b, prmt(st_b, st_b, 0x1032));
-                if ((st_b & 0x8000u) == 0) st_b = 0;                         // no negative element: min(min, 0) = 0
             } else {
                 uint32_t a0 = 0xff80ff80u, a1 = 0xff80ff80u, b0 = 0x7f807f80u, b1 = 0x7f807f80u;  // -inf / +inf
 #pragma unroll
-                for (int i = 0; i < N; i += 2) {
-                    const uint4 v0 = lds128(gaddr + (((i + rot) & (N - 1)) << 4));
-                    const uint4 v1 = lds128(gaddr + (((i + 1 + rot) & (N - 1)) << 4));
+                for (int i = 0; i < NL; i += 2) {
+                    const uint4 v0 = lds128(gaddr + (((i + rot) & (NL - 1)) << 4));
+                    const uint4 v1 = lds128(gaddr + (((i + 1 + rot) & (NL - 1)) << 4));
                     a0 = hmax2(a0, hmax2(hmax2(v0.x, v0.y), hmax2(v0.z, v0.w)));
                     b0 = hmin2(b0, hmin2(hmin2(v0.x, v0.y), hmin2(v0.z, v0.w)));
                     a1 = hmax2(a1, hmax2(hmax2(v1.x, v1.y), hmax2(v1.z, v1.w)));
@@ -230,7 +236,14 @@ __global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(
                 st_a = hmax2(st_a, prmt(st_a, st_a, 0x1032));
                 st_b = hmin2(st_b, prmt(st_b, st_b, 0x1032));
             }
-            // ---- B. qparams (once per group, by the lane that uses them; same rounding chain as qmath.cuh)
+            if (LPG == 2) {  // the other half of the group lives in the neighbouring lane
+                const uint32_t oa = __shfl_xor_sync(0xffffffffu, st_a, 1), ob = __shfl_xor_sync(0xffffffffu, st_b, 1);
+                if (SYM) st_a = hmaxabs2(st_a, oa);
+                else if (FMA) { st_a = __vmaxs2(st_a, oa); st_b = __vmaxu2(st_b, ob); }
+                else { st_a = hmax2(st_a, oa); st_b = hmin2(st_b, ob); }
+            }
+            if (!SYM && FMA && (st_b & 0x8000u) == 0) st_b = 0;               // no negative element: min(min, 0) = 0
+            // ---- B. qparams (once per group, by the lanes that use them; same rounding chain as qmath.cuh)
             float s, z = 0.0f;
             Bracket br;
             const int64_t gidx = g0 + gl;
@@ -248,7 +261,7 @@ __global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(
                 const float t = __shfl_sync(0xffffffffu, tab, (int)M);
                 if (gs_tab_ok) s = __fmul_rn(t, __uint_as_float((uint32_t)(E + 127) << 23));
                 else s = __fdiv_rn(e4m3_decode((uint8_t)code), gsv);
-                if (act) ((uint8_t*)p.scale)[gidx] = (uint8_t)code;
+                if (owner) ((uint8_t*)p.scale)[gidx] = (uint8_t)code;
                 br.init(s);
             } else if (SYM) {
                 s = div_const_bf16(__uint_as_float((st_a << 16) & 0x7fff0000u), QT == QT_INT ? 7.5f : 448.0f);
@@ -275,8 +288,8 @@ __global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(
                 if (s0 == 0.0f) { s = eps_of<DT_BF16>(); br.init(s); }
             }
             if (QT != QT_FP4) {
-                if (act) ((uint16_t*)p.scale)[gidx] = (uint16_t)(__float_as_uint(s) >> 16);
-                if (QT == QT_INT && !SYM && act) {
+                if (owner) ((uint16_t*)p.scale)[gidx] = (uint16_t)(__float_as_uint(s) >> 16);
+                if (QT == QT_INT && !SYM && owner) {
                     const uint32_t gpr = (uint32_t)p.groups_per_row;  // launcher guarantees < 2^31
                     const uint32_t t = k0 + (uint32_t)gl, dr = t / gpr, k = t - dr * gpr;
                     int64_t b = b0, r = (int64_t)r0 + dr;
@@ -290,10 +303,10 @@ __global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(
             const bool unsafe = (QT == QT_FP4) ? !fp4_scale_is_safe(s) : !scale_is_safe(__float_as_uint(s));
             const bool add_zp = (QT == QT_FP8) ? (p.has_zp != 0) : true;
             const uint32_t z2 = (__float_as_uint(z) >> 16) * 0x10001u;
-            const uint32_t oaddr = out_base + (uint32_t)gl * (N * OUT_CHUNK);
+            const uint32_t oaddr = out_base + (uint32_t)gl * (N * OUT_CHUNK) + (uint32_t)half * (NL * OUT_CHUNK);
 #pragma unroll
-            for (int i = 0; i < N; i++) {
-                const int c = (i + rot) & (N - 1);
+            for (int i = 0; i < NL; i++) {
+                const int c = (i + rot) & (NL - 1);
                 const uint4 v = lds128(gaddr + (c << 4));
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
                 uint32_t h[4], diff = 0;
@@ -358,28 +371,39 @@ __global__ void __launch_bounds__(WarpsFor<QT>::value * 32, 1) group_tma_kernel(
     if (lane == 0) bulk_wait0();
 }
 
-template <int QT, bool SYM, int LOG2N, bool FMA>
+template <int QT, bool SYM, int LOG2N, bool FMA, int TILE>
 int launch_tma_v(const TmaParams& p, cudaStream_t st) {
-    constexpr int OUT_BYTES = 512 * ((QT == QT_FP8) ? 8 : 4);
-    constexpr int kWarps = WarpsFor<QT>::value;
-    const size_t smem = (size_t)kWarps * (kStages * kTileBytes + OUT_BYTES + 64);
+    constexpr int OUT_BYTES = (TILE / 8) * ((QT == QT_FP8) ? 8 : 4);
+    constexpr int kWarps = WarpsFor<QT, TILE>::value;
+    const size_t smem = (size_t)kWarps * (kStages * TILE * 2 + OUT_BYTES + 64);
     static bool configured = false;  // benign race: idempotent attribute
     if (!configured) {
-        cudaFuncSetAttribute(group_tma_kernel<QT, SYM, LOG2N, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(group_tma_kernel<QT, SYM, LOG2N, FMA, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    constexpr int GPT = 32 * (16 >> LOG2N);
+    constexpr int GPT = TILE / (8 << LOG2N);
     const int64_t n_tiles = (p.n_groups + GPT - 1) / GPT;
     const int64_t ctas = max((int64_t)1, min((int64_t)kNumSMs, (n_tiles + kWarps - 1) / kWarps));
-    group_tma_kernel<QT, SYM, LOG2N, FMA><<<(unsigned)ctas, kWarps * 32, smem, st>>>(p);
+    group_tma_kernel<QT, SYM, LOG2N, FMA, TILE><<<(unsigned)ctas, kWarps * 32, smem, st>>>(p);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }
 
+// Measured on B200 (scripts/ab_tma.py, 16 x [9728, 2560] bf16, fraction of the 6.55 TB/s copy bandwidth):
+//                        8 KB tiles, 12 warps          4 KB tiles, 24 warps
+//   INT4 g128 asym       0.668 -> 0.680 (FMA mix)      0.680
+//   INT4 g128 sym        0.819 -> 0.836                0.748
+//   INT4 g32  sym        0.776 -> 0.793                0.781
+//   FP8  g32             0.950 -> 0.913                0.839
+// More warps do not help (the kernel is bound by its instruction count, ~10.8 issued per element, not by latency), the
+// FMA-pipe instruction mix helps INT4 by ~2 % and costs FP8 4 %.  Defaults follow the table; B200Q_TMA_TILE=2048 and
+// B200Q_TMA_LEGACY_ALU=1 / B200Q_TMA_FMA=1 select the other variants for experiments (read once per process).
 template <int QT, bool SYM, int LOG2N>
 int launch_tma(const TmaParams& p, cudaStream_t st) {
-    static const bool legacy = getenv("B200Q_TMA_LEGACY_ALU") != nullptr;  // A/B switch for the ALU-pipe relief variants
-    return legacy ? launch_tma_v<QT, SYM, LOG2N, false>(p, st) : launch_tma_v<QT, SYM, LOG2N, true>(p, st);
+    static const int tile = getenv("B200Q_TMA_TILE") ? atoi(getenv("B200Q_TMA_TILE")) : 4096;
+    static const bool fma = getenv("B200Q_TMA_LEGACY_ALU") ? false : (getenv("B200Q_TMA_FMA") ? true : QT == QT_INT);
+    if (QT != QT_FP4 && tile == 2048) return launch_tma_v<QT, SYM, LOG2N, true, 2048>(p, st);
+    return fma ? launch_tma_v<QT, SYM, LOG2N, true, 4096>(p, st) : launch_tma_v<QT, SYM, LOG2N, false, 4096>(p, st);
 }
 
 }  // namespace
