@@ -180,13 +180,14 @@ __device__ __forceinline__ void fp4_build_table(Fp4Entry* table, float gs) {
     }
 }
 
-__device__ __forceinline__ void fp4_load_tile(uint4 (&raw)[FP4_UF][2], const uint4* wbase, int64_t g0, int64_t groups_per_mat) {
+template <bool KEEP = false>
+__device__ __forceinline__ void fp4_load_tile(uint4 (&raw)[FP4_UF][2], const uint4* wbase, int64_t g0, int64_t groups_per_mat, uint64_t policy = 0) {
 #pragma unroll
     for (int u = 0; u < FP4_UF; u++) {
         const int64_t g = g0 + u * FP4_THREADS;
         if (g < groups_per_mat) {
-            raw[u][0] = ldg_stream(wbase + 2 * g);
-            raw[u][1] = ldg_stream(wbase + 2 * g + 1);
+            raw[u][0] = KEEP ? ldg_keep(wbase + 2 * g, policy) : ldg_stream(wbase + 2 * g);
+            raw[u][1] = KEEP ? ldg_keep(wbase + 2 * g + 1, policy) : ldg_stream(wbase + 2 * g + 1);
         } else {
             raw[u][0] = raw[u][1] = make_uint4(0, 0, 0, 0);
         }
@@ -197,6 +198,7 @@ __device__ __forceinline__ uint32_t fp4_group_absmax2(const uint4 (&r)[2]) {  //
 }
 
 // one 1024-group tile of one matrix, already in registers: scale codes + packed e2m1 out
+template <bool FMA>
 __device__ __forceinline__ void fp4_compress_regs(const uint4 (&raw)[FP4_UF][2], const Fp4Entry* table, float gs, uint8_t* sbase, uint2* obase,
                                                   int64_t g0, int64_t groups_per_mat) {
 #pragma unroll
@@ -217,8 +219,10 @@ __device__ __forceinline__ void fp4_compress_regs(const uint4 (&raw)[FP4_UF][2],
         for (int h = 0; h < 2; h++) {
             // x * r + 0.0: exact -0.0 inputs carry no sign nibble (torch.sign(-0.) == 0); satfinite == clamp to +-6; the sign
             // bit of a value that rounds to zero comes from the pre-round sign, like the reference's sign(x) * |q|
-            const f32x2 x0 = bf16x2_to_f32x2(raw[u][h].x), x1 = bf16x2_to_f32x2(raw[u][h].y);
-            const f32x2 x2 = bf16x2_to_f32x2(raw[u][h].z), x3 = bf16x2_to_f32x2(raw[u][h].w);
+            const f32x2 x0 = FMA ? bf16x2_to_f32x2_fma(raw[u][h].x) : bf16x2_to_f32x2(raw[u][h].x);
+            const f32x2 x1 = FMA ? bf16x2_to_f32x2_fma(raw[u][h].y) : bf16x2_to_f32x2(raw[u][h].y);
+            const f32x2 x2 = FMA ? bf16x2_to_f32x2_fma(raw[u][h].z) : bf16x2_to_f32x2(raw[u][h].z);
+            const f32x2 x3 = FMA ? bf16x2_to_f32x2_fma(raw[u][h].w) : bf16x2_to_f32x2(raw[u][h].w);
             uint32_t packed = cvt_e2m1x8(mul2_plus0(x0, rl), mul2_plus0(x1, rl), mul2_plus0(x2, rl), mul2_plus0(x3, rl));
             const uint32_t diff = packed ^ cvt_e2m1x8(mul2_plus0(x0, rh), mul2_plus0(x1, rh), mul2_plus0(x2, rh), mul2_plus0(x3, rh));
             if (diff != 0 || e.unsafe != 0.0f) packed = fix_group_fp4(raw[u][h], e.s_eff, packed);
@@ -227,11 +231,12 @@ __device__ __forceinline__ void fp4_compress_regs(const uint4 (&raw)[FP4_UF][2],
         stg_stream(obase + g, make_uint2(out[0], out[1]));
     }
 }
+template <bool FMA>
 __device__ __forceinline__ void fp4_compress_tile(const Fp4Entry* table, float gs, const uint4* wbase, uint8_t* sbase, uint2* obase, int64_t g0,
                                                   int64_t groups_per_mat) {
     uint4 raw[FP4_UF][2];
     fp4_load_tile(raw, wbase, g0, groups_per_mat);
-    fp4_compress_regs(raw, table, gs, sbase, obase, g0, groups_per_mat);
+    fp4_compress_regs<FMA>(raw, table, gs, sbase, obase, g0, groups_per_mat);
 }
 
 // caller-supplied global scales (fused q/k/v siblings, decompress round trips): one pass
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(FP4_THREADS) nvfp4_flat_kernel(const GroupPara
     uint8_t* sbase = (uint8_t*)p.scale + b * groups_per_mat;
     uint2* obase = reinterpret_cast<uint2*>((uint8_t*)p.out + b * groups_per_mat * 8);
     for (int tile = blockIdx.x; tile < tiles_per_mat; tile += gridDim.x)
-        fp4_compress_tile(table, gs, wbase, sbase, obase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, groups_per_mat);
+        fp4_compress_tile<false>(table, gs, wbase, sbase, obase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, groups_per_mat);
 }
 
 // Global scale computed here: the whole-matrix |max| must be known before the first code is emitted, i.e. two passes over the
@@ -268,9 +273,10 @@ struct Fp4FusedParams {
 // |max| bits of tiles [tile0, tile1) of one matrix, reduced over the CTA (valid in thread 0)
 __device__ __forceinline__ uint32_t fp4_absmax_tiles(const uint4* wbase, int tile0, int tile1, int64_t groups_per_mat, uint32_t* s_red) {
     uint32_t mm = 0;
+    const uint64_t keep = l2_policy_evict_last();  // the compress pass re-reads these lines
     for (int tile = tile0; tile < tile1; tile++) {
         uint4 raw[FP4_UF][2];
-        fp4_load_tile(raw, wbase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, groups_per_mat);
+        fp4_load_tile<true>(raw, wbase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, groups_per_mat, keep);
         mm = hmaxabs2(mm, hmaxabs2(hmaxabs2(fp4_group_absmax2(raw[0]), fp4_group_absmax2(raw[1])),
                                    hmaxabs2(fp4_group_absmax2(raw[2]), fp4_group_absmax2(raw[3]))));
     }
@@ -287,6 +293,7 @@ __device__ __forceinline__ uint32_t fp4_absmax_tiles(const uint4* wbase, int til
     return bits;
 }
 
+template <bool FMA>
 __global__ void __launch_bounds__(FP4_THREADS, 4) nvfp4_fused_kernel(const GroupParams p, const Fp4FusedParams f) {
     __shared__ Fp4Entry table[128];
     __shared__ float s_gs;
@@ -343,9 +350,9 @@ __global__ void __launch_bounds__(FP4_THREADS, 4) nvfp4_fused_kernel(const Group
     __syncthreads();
     uint8_t* sbase = (uint8_t*)p.scale + m * f.groups_per_mat;
     uint2* obase = reinterpret_cast<uint2*>((uint8_t*)p.out + m * f.groups_per_mat * 8);
-    fp4_compress_regs(raw, table, gs, sbase, obase, (int64_t)tile0 * FP4_TILE_GROUPS + threadIdx.x, f.groups_per_mat);
+    fp4_compress_regs<FMA>(raw, table, gs, sbase, obase, (int64_t)tile0 * FP4_TILE_GROUPS + threadIdx.x, f.groups_per_mat);
     for (int tile = tile0 + 1; tile < tile1; tile++)
-        fp4_compress_tile(table, gs, wbase, sbase, obase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, f.groups_per_mat);
+        fp4_compress_tile<FMA>(table, gs, wbase, sbase, obase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, f.groups_per_mat);
 }
 
 
@@ -401,11 +408,13 @@ int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_
     f.n_spans = (int)n_spans;
     const int64_t span_bytes = groups_per_mat * 32 * span;
     f.nt = nt;
-    f.lookahead = (int)max((int64_t)1, min(n_spans, ((int64_t)tune_env("B200Q_FP4_LOOKAHEAD_MB", 14) << 20) / max(span_bytes, (int64_t)1)));
+    f.lookahead = (int)max((int64_t)1, min(n_spans, ((int64_t)tune_env("B200Q_FP4_LOOKAHEAD_MB", 40) << 20) / max(span_bytes, (int64_t)1)));
     f.sync = sync;
     f.gs_out = gs_out;
     cudaMemsetAsync(sync, 0, sizeof(uint32_t) * 2 * n_spans, st);
-    nvfp4_fused_kernel<<<(unsigned)grid, FP4_THREADS, 0, st>>>(p, f);
+    static const bool fma = getenv("B200Q_FP4_FMA") != nullptr;  // FHFMA unpack (ALU-pipe relief), A/B switch
+    if (fma) nvfp4_fused_kernel<true><<<(unsigned)grid, FP4_THREADS, 0, st>>>(p, f);
+    else nvfp4_fused_kernel<false><<<(unsigned)grid, FP4_THREADS, 0, st>>>(p, f);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }
