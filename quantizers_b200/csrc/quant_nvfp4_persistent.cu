@@ -31,18 +31,19 @@ using namespace fast;
 using namespace fp4;
 using namespace async;
 
-constexpr int RS_Q = 16;                                 // per-step sync slots (ring); must exceed the distance D
+constexpr int RS_Q = 8;                                  // per-step sync slots (ring); must exceed the distance D
 constexpr int RS_NPOLL = 3;
 constexpr int RS_CTRL = 2 + RS_NPOLL;                    // producer, publisher, pollers
 constexpr int RS_MIN_TILE_GROUPS = 512;                  // every configuration's tile holds at least this many groups
 
-template <int NW, int GPT, int S> struct RsCfg {
+template <int NW, int GPT, int S, int CPS = 1> struct RsCfg {
+    static constexpr int kCtasPerSm = CPS;
     static constexpr int kTileGroups = NW * 32 * GPT;
     static constexpr int kTileBytes = kTileGroups * 32;
     static constexpr int kThreads = (RS_CTRL + NW) * 32;
     static constexpr int kSmem = S * kTileBytes + RS_Q * 128 * (int)sizeof(Fp4Entry) + (2 * S + 2 * RS_Q) * 8 + RS_Q * 8;
     static_assert(kTileGroups >= RS_MIN_TILE_GROUPS, "workspace sizing assumes tiles of >= 512 groups");
-    static_assert(kSmem <= 232448, "shared memory budget");
+    static_assert(CPS * (kSmem + 1024) <= 233472, "shared memory budget");
 };
 
 struct Fp4PersistentParams {
@@ -76,9 +77,9 @@ __device__ __forceinline__ uint32_t absmax2_16(const uint4 a, const uint4 b) {  
     return hmaxabs2(hmaxabs2(hmaxabs2(a.x, a.y), hmaxabs2(a.z, a.w)), hmaxabs2(hmaxabs2(b.x, b.y), hmaxabs2(b.z, b.w)));
 }
 
-template <int NW, int GPT, int S>
-__global__ void __launch_bounds__(RsCfg<NW, GPT, S>::kThreads, 1) nvfp4_persistent_kernel(const GroupParams p, const Fp4PersistentParams f) {
-    using C = RsCfg<NW, GPT, S>;
+template <int NW, int GPT, int S, int CPS>
+__global__ void __launch_bounds__(RsCfg<NW, GPT, S, CPS>::kThreads, CPS) nvfp4_persistent_kernel(const GroupParams p, const Fp4PersistentParams f) {
+    using C = RsCfg<NW, GPT, S, CPS>;
     extern __shared__ __align__(128) uint8_t smem[];
     Fp4Entry* tables = reinterpret_cast<Fp4Entry*>(smem + S * C::kTileBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(tables + RS_Q * 128);
@@ -293,20 +294,20 @@ int tune_env(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-template <int NW, int GPT, int S>
+template <int NW, int GPT, int S, int CPS = 1>
 int launch_cfg(const GroupParams& p, int64_t batch, int span, float* gs_out, uint32_t* sync, cudaStream_t st, int sms) {
-    using C = RsCfg<NW, GPT, S>;
+    using C = RsCfg<NW, GPT, S, CPS>;
     const int64_t groups_per_mat = p.rows * (p.cols >> 4);
     const int64_t tiles = (groups_per_mat + C::kTileGroups - 1) / C::kTileGroups;
     const int64_t total = tiles * batch, span_tiles = tiles * span;
     if (tiles >= (1ll << 30) || span_tiles >= (1ll << 30)) return B200Q_ENOSYS;
-    const int64_t grid = min((int64_t)sms, total);
+    const int64_t grid = min((int64_t)sms * CPS, total);
     // D: steps a span can stretch over + slack for the publish -> poll -> table chain
     const int64_t D = (span_tiles + grid - 2) / grid + tune_env("B200Q_FP4_SLACK", 4);
     if (D >= RS_Q) return B200Q_ENOSYS;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(nvfp4_persistent_kernel<NW, GPT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem) != cudaSuccess) {
+        if (cudaFuncSetAttribute(nvfp4_persistent_kernel<NW, GPT, S, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem) != cudaSuccess) {
             cudaGetLastError();
             return B200Q_ENOSYS;
         }
@@ -323,7 +324,7 @@ int launch_cfg(const GroupParams& p, int64_t batch, int span, float* gs_out, uin
     cudaMemsetAsync(sync, 0, sizeof(uint32_t) * total, st);
     GroupParams pp = p;
     void* args[] = {(void*)&pp, (void*)&f};
-    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)nvfp4_persistent_kernel<NW, GPT, S>, dim3((unsigned)grid), dim3(C::kThreads), args,
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)nvfp4_persistent_kernel<NW, GPT, S, CPS>, dim3((unsigned)grid), dim3(C::kThreads), args,
                                                       C::kSmem, st);
     if (e != cudaSuccess) {
         set_error("nvfp4 persistent launch failed: %s", cudaGetErrorString(e));
@@ -353,6 +354,8 @@ int launch_nvfp4_resident(const GroupParams& p, int64_t batch, int span, float* 
     switch (tune_env("B200Q_FP4_CFG", 1)) {
     case 0: return launch_cfg<16, 2, 6>(p, batch, span, gs_out, sync, st, sms);
     case 3: return launch_cfg<20, 2, 4>(p, batch, span, gs_out, sync, st, sms);
+    case 4: return launch_cfg<12, 2, 3, 2>(p, batch, span, gs_out, sync, st, sms);  // two desynchronised CTAs per SM
+    case 5: return launch_cfg<12, 2, 4, 2>(p, batch, span, gs_out, sync, st, sms);
     default: return launch_cfg<24, 2, 4>(p, batch, span, gs_out, sync, st, sms);
     }
 }

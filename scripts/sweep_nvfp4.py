@@ -13,7 +13,7 @@ shapes = [(256, 768, 2048, 2), (128, 2048, 768, 1), (64, 1536, 3072, 2), (6, 100
 for (E, R, C, span) in shapes:
     w = synth_stack(list(range(E)), R, C, 0, dev)
     outs = {}
-    for mode in ("1c0s4", "1c1s4", "1c3s4", "0"):
+    for mode in ("1c1s4", "1c4s3", "1c4s5", "1c5s3", "1c5s5", "0"):
         os.environ["B200Q_FP4_PERSISTENT"] = mode[0]
         if len(mode) > 1:
             os.environ["B200Q_FP4_CFG"] = mode[2]
