@@ -470,6 +470,7 @@ def main():
     ap.add_argument("--layers", type=int, default=36, help="decoder layers per rank (36 = full Qwen3-4B)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-layers", type=int, default=36, help="decoder layers the CPU baseline quantizes (36 = the whole workload once)")
     ap.add_argument("--awq-layers", type=int, default=3, help="decoder layers of the AWQ search leg per rank (0 disables it)")
     ap.add_argument("--awq-tokens", type=int, default=64 * 512, help="calibration tokens per layer (64 samples x 512)")
     ap.add_argument("--moe-layers", type=int, default=8, help="layers of the Qwen3-30B-A3B NVFP4 expert-sharded leg (0 disables it)")
@@ -611,12 +612,19 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             kind = cpu_kind()
             torch.set_num_threads(os.cpu_count() or 1)
-            layer = cpu_layer(0)
-            t0 = time.perf_counter()
-            nb = cpu_quantize_layer(layer, kind)
-            dt = time.perf_counter() - t0
+            n_layers = max(1, args.cpu_layers)
+            nb, dt = 0, 0.0
+            for li in range(n_layers):          # generation is outside the timed region, the reference path inside
+                layer = cpu_layer(li)
+                t0 = time.perf_counter()
+                nb += cpu_quantize_layer(layer, kind)
+                dt += time.perf_counter() - t0
+                del layer
             line["cpu_baseline"] = {"value": nb / dt / 1e9, "unit": UNIT, "cores": torch.get_num_threads() if kind == "reference" else 1,
-                                    "kind": kind, "sample": "one Qwen3-4B decoder layer (7 matrices, 201.9 MB bf16), single cold pass"}
+                                    "kind": kind, "seconds": dt,
+                                    "sample": f"{n_layers} of 36 Qwen3-4B decoder layers ({nb / 1e9:.2f} GB bf16) through "
+                                              + ("live compressed-tensors (observer amin/amax -> calculate_qparams -> Compressor.compress)"
+                                                 if kind == "reference" else "the C oracle")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
