@@ -419,7 +419,8 @@ def run_moe_block(args, dev, world, rank, peak):
     from quantizers_b200 import awq
     from quantizers_b200 import scheduler as S
 
-    E, H, I, K = args.moe_block_experts, 3072, 1536, 8
+    E, H, I = args.moe_block_experts, 3072, 1536
+    K = min(8, E)
     T = args.awq_tokens
     qargs = S.PRESETS["INT4_G32_SYM"]
     units = list(range(E))
