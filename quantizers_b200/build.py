@@ -24,7 +24,7 @@ HEADERS = ["qmath.cuh", "common.cuh", "kernels.cuh", "fastmath.cuh", "async.cuh"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # no --use_fast_math: IEEE division / no FMA contraction is part of the parity contract (qmath.cuh)
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--fmad=false", "-Xptxas", "-v"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--fmad=false", "-Xptxas", "-v"] + os.environ.get("B200Q_NVCC_DEFS", "").split()
 
 
 def _newer(target: str, deps) -> bool:

@@ -41,6 +41,16 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
     return r;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v)); }
 __device__ __forceinline__ void sts64(uint32_t addr, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(v.x), "r"(v.y)); }
 

@@ -304,12 +304,36 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_k
             const bool add_zp = (QT == QT_FP8) ? (p.has_zp != 0) : true;
             const uint32_t z2 = (__float_as_uint(z) >> 16) * 0x10001u;
             const uint32_t oaddr = out_base + (uint32_t)gl * (N * OUT_CHUNK) + (uint32_t)half * (NL * OUT_CHUNK);
+            uint32_t diff = 0;
+            // Measured (scripts/ab_tma.py, fraction of the HBM roofline; asym g128 / sym g128 / sym g32 / fp8 g32):
+            //   bracket check by HFMA2, repair in the loop     0.67 / 0.84 / 0.79 / 0.95
+            //   bracket check by XOR,   repair in the loop       -  / 0.74 / 0.84 / 0.95
+            //   bracket check by XOR,   repair deferred        0.72 / 0.74 / 0.80 / 0.95
+            //   bracket check by HFMA2, repair deferred        0.69 / 0.77 / 0.83 / 0.95
+            // -> per-format choice below (overridable at build time: B200Q_NVCC_DEFS="-DB200Q_TMA_DEFER=... -DB200Q_TMA_HDIFF=...").
+            // DEFER (asymmetric INT4, the longest per-element chain): the exact repair runs once per group after the loop, which
+            // keeps the loop call-free straight-line code (no per-chunk branch / BSSY / constant re-materialisation): +9 % measured.
+            // The other formats are faster with the repair inside the loop (a group-wide flag fires for ~0.2 % of the groups, i.e.
+            // for ~6 % of the warp iterations, and the divergent repair pass then costs more than the branches saved).
+            // Batches of QB chunks: enough independent chains to hide the conversion latencies without letting the compiler hoist
+            // all 16 loads of a group (which drove the kernel to the 168-register cap).
+#ifndef B200Q_TMA_DEFER
+#define B200Q_TMA_DEFER (QT == QT_INT && !SYM)
+#endif
+#ifndef B200Q_TMA_HDIFF
+#define B200Q_TMA_HDIFF (QT == QT_INT && SYM && LOG2N == 4)
+#endif
+            constexpr bool DEFER = B200Q_TMA_DEFER;
+            constexpr bool HDIFF = FMA && QT != QT_FP4 && (B200Q_TMA_HDIFF);
+            constexpr int QB = !DEFER ? NL : (NL < 4 ? NL : 4);
+#pragma unroll 1
+            for (int i0 = 0; i0 < NL; i0 += QB)
 #pragma unroll
-            for (int i = 0; i < NL; i++) {
+            for (int i = i0; i < i0 + QB; i++) {
                 const int c = (i + rot) & (NL - 1);
                 const uint4 v = lds128(gaddr + (c << 4));
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                uint32_t h[4], diff = 0;
+                uint32_t h[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const f32x2 x = FMA ? bf16x2_to_f32x2_fma(w[k]) : bf16x2_to_f32x2(w[k]);
@@ -318,7 +342,7 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_k
                         unpack2(mul2(x, br.lo), al, ah);
                         unpack2(mul2(x, br.hi), bl, bh);
                         uint32_t u = cvt_bf16x2(ah, al);
-                        if (FMA) diff = hdiff2_acc(u, cvt_bf16x2(bh, bl), diff);
+                        if (HDIFF) diff = hdiff2_acc(u, cvt_bf16x2(bh, bl), diff);
                         else diff |= u ^ cvt_bf16x2(bh, bl);
                         if (!SYM) u = hadd2(u, z2);
                         h[k] = __viaddmin_s16x2_relu(hadd2(u, kMagic), kUnbias, 0x000f000fu);
@@ -326,7 +350,7 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_k
                         unpack2(add_zp ? mul2_plus0(x, br.lo) : mul2(x, br.lo), al, ah);
                         unpack2(add_zp ? mul2_plus0(x, br.hi) : mul2(x, br.hi), bl, bh);
                         const uint32_t u = cvt_bf16x2(ah, al);
-                        if (FMA) diff = hdiff2_acc(u, cvt_bf16x2(bh, bl), diff);
+                        if (HDIFF) diff = hdiff2_acc(u, cvt_bf16x2(bh, bl), diff);
                         else diff |= u ^ cvt_bf16x2(bh, bl);
                         if (FMA) {
                             float ul, uh;
@@ -352,10 +376,27 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_k
                 } else {
                     packed = make_uint2(h[0] | (h[1] << 8) | (h[2] << 16) | (h[3] << 24), 0u);
                 }
-                const bool differ = (FMA && QT != QT_FP4) ? hdiff2_any(diff) : diff != 0;
-                if (differ || unsafe) packed = repair_chunk<QT, SYM>(v, s, z, add_zp, unsafe, packed);
+                if (!DEFER) {
+                    if ((HDIFF ? hdiff2_any(diff) : diff != 0) || unsafe) packed = repair_chunk<QT, SYM>(v, s, z, add_zp, unsafe, packed);
+                    diff = 0;
+                }
                 if (QT == QT_FP8) sts64(oaddr + c * 8, packed);
                 else sts32(oaddr + c * 4, packed.x);
+            }
+            // ---- C'. exact repair, once per group and out of the hot loop (rare: p ~ 1e-4 per element).  `diff` collected every
+            // disagreement of the two bracket ends over the lane's chunks; the loop above is call-free straight-line code, so the
+            // compiler interleaves chunks and keeps its constants in registers.  The inputs are still in the stage.
+            if (DEFER && ((HDIFF ? hdiff2_any(diff) : diff != 0) || unsafe)) {
+#pragma unroll 1
+                for (int c = 0; c < NL; c++) {
+                    const uint4 v = lds128(gaddr + (c << 4));
+                    uint2 packed;
+                    if (QT == QT_FP8) packed = lds64(oaddr + c * 8);
+                    else packed = make_uint2(lds32(oaddr + c * 4), 0u);
+                    packed = repair_chunk<QT, SYM>(v, s, z, add_zp, unsafe, packed);
+                    if (QT == QT_FP8) sts64(oaddr + c * 8, packed);
+                    else sts32(oaddr + c * 4, packed.x);
+                }
             }
         }
         // ---- D. hand the packed tile to the TMA engine, refill this input stage
