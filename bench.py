@@ -457,8 +457,8 @@ def run_moe_block(args, dev, world, rank, peak):
                        "experts": E, "top_k": K, "tokens": T, "tokens_per_gpu": len(tok), "best_ratio": ratio,
                        "collective": "all-reduce(SUM) of |x| sums and [n_grid] loss accumulators" if world > 1 else None},
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
-                         "kernel": "awq_gemm_project_kernel (tcgen05, TMEM), one small launch per expert and stage",
-                         "note": "T * k / E routed tokens per expert and launch; gather / index_add_ / squared error run beside the GEMMs; per-GPU figure of the slowest rank"}}
+                         "kernel": "awq_gemm_project_kernel, grouped mode (tcgen05, TMEM): one launch per stage over all experts + bf16 combine kernel",
+                         "note": "routed pairs sorted expert-major, rows padded to 128-row tiles; per-GPU figure of the slowest rank"}}
 
 
 # ----------------------------------------------------------------------------- main arm

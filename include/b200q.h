@@ -196,6 +196,19 @@ int b200q_awq_gemm_loss_pairs(const void* a_ref, const void* a_q, int64_t tokens
 int b200q_awq_gemm_project(const void* x, int64_t tokens, int64_t k, const void* w, int64_t n_variants, int64_t n_out, int32_t swiglu,
                            void* out, void* stream);
 
+/* W2 of the layer-wide MoE mapping (post_attention_layernorm -> every expert's w1 / w3; parent = the routed sparse-MoE block of
+ * transformers' Mixtral / Qwen3-MoE / MiniMax modules): the same projection with one weight PER 128-ROW TILE of x.  The caller
+ * sorts the routed (token, expert) pairs expert-major and pads every expert's rows to whole tiles; tile_expert int32
+ * [tokens / 128] (device) names the expert of each tile (< 0: padding tile, skipped).  w: T [n_experts, rows, k] with rows = n_out
+ * (swiglu == 0) or 2 * n_out (gate rows, then up rows); out: T [tokens, n_out].  One launch replaces n_experts launches. */
+int b200q_awq_gemm_project_grouped(const void* x, int64_t tokens, int64_t k, const void* w, int64_t n_experts, int64_t n_out, int32_t swiglu,
+                                   const int32_t* tile_expert, void* out, void* stream);
+/* ... and its combine step: out[t] = sum_j bf16(y[row[t, j]] * weight[t, j]), accumulated in bf16 with j in ascending expert
+ * order (the rounding sequence of the reference's per-expert index_add_); row int32 [tokens, top_k] (< 0: skip), weight T
+ * [tokens, top_k], y T [padded rows, hidden], out T [tokens, hidden].  bf16 only. */
+int b200q_moe_combine(const void* y, const int32_t* row, const void* weight, int64_t tokens, int32_t top_k, int64_t hidden, void* out,
+                      void* stream);
+
 /* W2, attention parent (input_layernorm -> q/k/v mapping; transformers Qwen3Attention.forward between the projections and
  * SDPA): in-place per-head RMSNorm (weights T [head_dim]) + rotary embedding of the q and k columns of
  * qkv T [tokens, (n_heads + 2 n_kv) * head_dim]; position = token index % seq_len; cos/sin T [seq_len, head_dim].  bf16 only. */

@@ -491,34 +491,65 @@ def moe_block_flops(T: int, top_k: int, hidden: int, inter: int, n_grid: int = 2
 
 class RoutedMoE:
     """The routed sparse-MoE block as an AWQ parent: ``out[t] = sum_{j < k} p[t, j] * w2_e( act(w1_e x_t) * (w3_e x_t) )`` with
-    ``e = topk_idx[t, j]``, accumulated expert by expert with ``index_add_`` in the activation dtype like the transformers
-    Mixtral / Qwen3-MoE / MiniMax blocks do.  Routing depends on x and the (un-quantized) router only, so it is computed once by
-    the caller.  Under ``moe_calibrate_all_experts`` every expert additionally runs on all tokens, but only routed pairs reach
-    the block output that the loss is taken on, so only those are evaluated here (same output, 1 / (E / k) of the FLOPs)."""
+    ``e = topk_idx[t, j]``, accumulated expert by expert in the activation dtype like the transformers Mixtral / Qwen3-MoE /
+    MiniMax blocks do (``index_add_`` per expert, ascending).  Routing depends on x and the (un-quantized) router only, so it is
+    computed once by the caller.  Under ``moe_calibrate_all_experts`` every expert additionally runs on all tokens, but only
+    routed pairs reach the block output that the loss is taken on, so only those are evaluated here (same output, 1 / (E / k) of
+    the FLOPs).
+
+    Layout: the routed (token, expert) pairs are sorted expert-major and every expert's rows are padded to whole 128-row tiles,
+    so ONE grouped tcgen05 launch per stage serves all experts (``b200q_awq_gemm_project_grouped``: tile -> expert table); the
+    combine kernel then sums each token's k rows in ascending expert order with bf16 rounding after every step."""
+
+    TILE = 128
 
     def __init__(self, x: torch.Tensor, w2: torch.Tensor, topk_idx: torch.Tensor, topk_w: torch.Tensor):
         L.require_cuda(x, w2, topk_idx, topk_w)
         T, k = topk_idx.shape
         E = w2.shape[0]
+        dev = x.device
         flat = topk_idx.reshape(-1).to(torch.int64)
-        order = torch.argsort(flat, stable=True)
-        self.tok = (order // k).contiguous()
-        self.pw = topk_w.reshape(-1)[order].to(x.dtype).unsqueeze(1).contiguous()
+        order = torch.argsort(flat, stable=True)                      # pairs expert-major, token order inside an expert
         counts = torch.bincount(flat, minlength=E)
-        self.off = [0] + torch.cumsum(counts, 0).tolist()   # the one host round trip of the mapping
-        self.xs = x.index_select(0, self.tok)                # routed inputs, expert-major
-        self.w2, self.T, self.H = w2, T, x.shape[1]
+        padded = (counts + self.TILE - 1) // self.TILE * self.TILE
+        starts = torch.cumsum(padded, 0) - padded                     # first padded row of each expert
+        rows_total = int(padded.sum().item())                         # the one host round trip of the mapping
+        rows_total = max(rows_total, self.TILE)
+        excl = torch.cumsum(counts, 0) - counts
+        sorted_e = flat[order]
+        prow = starts[sorted_e] + (torch.arange(order.numel(), device=dev) - excl[sorted_e])   # padded row of each sorted pair
+        gather = torch.zeros(rows_total, dtype=torch.int64, device=dev)                          # padding rows read token 0
+        gather[prow] = order // k
+        self.xs = x.index_select(0, gather)                            # [rows_total, H] routed inputs
+        tile_e = torch.full((rows_total // self.TILE,), -1, dtype=torch.int32, device=dev)
+        tile_ids = torch.arange(rows_total // self.TILE, device=dev) * self.TILE
+        owner = torch.searchsorted(starts + padded, tile_ids, right=True).clamp(max=E - 1)
+        valid = tile_ids < (starts + counts)[owner]                     # tiles that hold at least one real row
+        tile_e[valid] = owner[valid].to(torch.int32)
+        self.tile_expert = tile_e
+        # per token: its k padded rows and routing weights in ascending expert order
+        row_of_pair = torch.empty(order.numel(), dtype=torch.int64, device=dev)
+        row_of_pair[order] = prow
+        row_tk = row_of_pair.view(T, k)
+        by_expert = torch.argsort(topk_idx.to(torch.int64), dim=1, stable=True)
+        self.rows = row_tk.gather(1, by_expert).to(torch.int32).contiguous()
+        self.pw = topk_w.to(x.dtype).gather(1, by_expert).contiguous()
+        self.w2, self.T, self.H, self.k = w2.contiguous(), T, x.shape[1], k
 
     def __call__(self, w13: torch.Tensor) -> torch.Tensor:
         """w13 ``[E, 2 * I, H]`` (w1 rows, then w3 rows) -> block output ``[T, H]``."""
-        out = torch.zeros((self.T, self.H), dtype=self.xs.dtype, device=self.xs.device)
-        for e in range(self.w2.shape[0]):
-            a, b = self.off[e], self.off[e + 1]
-            if a == b:
-                continue
-            h = gemm_project(self.xs[a:b], w13[e:e + 1], swiglu=True)[0]
-            y = gemm_project(h, self.w2[e:e + 1], swiglu=False)[0]
-            out.index_add_(0, self.tok[a:b], y * self.pw[a:b])
+        lib = L.lib()
+        dev = self.xs.device
+        st = L.stream_ptr(dev)
+        E, two_i, H = w13.shape
+        I = two_i // 2
+        R = self.xs.shape[0]
+        h = workspace.get("moe_h", (R, I), self.xs.dtype, dev)
+        y = workspace.get("moe_y", (R, self.H), self.xs.dtype, dev)
+        L.check(lib.b200q_awq_gemm_project_grouped(L.ptr(self.xs), R, H, L.ptr(w13), E, I, 1, L.ptr(self.tile_expert), L.ptr(h), st))
+        L.check(lib.b200q_awq_gemm_project_grouped(L.ptr(h), R, I, L.ptr(self.w2), E, self.H, 0, L.ptr(self.tile_expert), L.ptr(y), st))
+        out = torch.empty((self.T, self.H), dtype=self.xs.dtype, device=dev)
+        L.check(lib.b200q_moe_combine(L.ptr(y), L.ptr(self.rows), L.ptr(self.pw), self.T, self.k, self.H, L.ptr(out), st))
         return out
 
 

@@ -242,6 +242,9 @@ struct ProjParams {
     int32_t n_m_tiles, n_n_tiles, n_k_blocks, n_variants, group_m;
     int32_t tokens, n_out, up_row_offset;
     uint16_t* out;  // bf16 [n_variants, tokens, n_out]
+    // grouped mode (MoE experts): non-null -> one weight variant PER M TILE (tile_variant[mt] = expert owning the tile's rows, < 0 =
+    // padding tile, skipped) and a single [tokens, n_out] output; the rows of an expert are padded to whole tiles by the caller
+    const int32_t* tile_variant;
 };
 
 // grouped rasterisation: consecutive items cover group_m m-tiles x all n-tiles column by column, so one wave of 148
@@ -288,7 +291,8 @@ awq_gemm_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int n_items = p.n_variants * p.n_m_tiles * p.n_n_tiles;
+    const bool grouped = p.tile_variant != nullptr;
+    const int n_items = (grouped ? 1 : p.n_variants) * p.n_m_tiles * p.n_n_tiles;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -296,6 +300,7 @@ awq_gemm_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int v, mt, nt;
                 decode_item(p, item, v, mt, nt);
+                if (grouped) { v = p.tile_variant[mt]; if (v < 0) continue; }
                 for (int kb = 0; kb < p.n_k_blocks; kb++, it++) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1u);
@@ -314,8 +319,14 @@ awq_gemm_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     } else if (warp == 1) {
         if (lane == 0) {
             uint32_t it = 0, n_done = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                if (grouped) {
+                    int v, mt, nt;
+                    decode_item(p, item, v, mt, nt);
+                    if (p.tile_variant[mt] < 0) continue;
+                }
                 const uint32_t slot = n_done & 1u, use = n_done >> 1;
+                n_done++;
                 mbar_wait(bar_tempty + 8 * slot, (use & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d = tmem_base + slot * BN;
@@ -335,10 +346,12 @@ awq_gemm_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     } else {
         const uint32_t quad = (uint32_t)warp & 3u;
         uint32_t n_done = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int v, mt, nt;
             decode_item(p, item, v, mt, nt);
+            if (grouped) { if (p.tile_variant[mt] < 0) continue; v = 0; }
             const uint32_t slot = n_done & 1u, use = n_done >> 1;
+            n_done++;
             const uint32_t t_lane = tmem_base + ((quad * 32u) << 16) + slot * BN;
             const int row = mt * BM + (int)quad * 32 + lane;
             const int col0 = nt * TN;
@@ -487,8 +500,8 @@ int b200q_awq_gemm_loss(const void* x, int64_t tokens, int64_t k, const void* w_
     return b200q_awq_gemm_loss_pairs(x, nullptr, tokens, k, w_ref, w_q, n, n_ratios, loss, workspace, workspace_bytes, stream);
 }
 
-int b200q_awq_gemm_project(const void* x, int64_t tokens, int64_t k, const void* w, int64_t n_variants, int64_t n_out, int32_t swiglu,
-                           void* out, void* stream) {
+static int gemm_project_impl(const void* x, int64_t tokens, int64_t k, const void* w, int64_t n_variants, int64_t n_out, int32_t swiglu,
+                             const void* tile_variant, void* out, void* stream) {
     B200Q_REQUIRE(x && w && out, "b200q_awq_gemm_project: NULL pointer");
     B200Q_REQUIRE(k % 8 == 0 && k >= 8, "K must be a multiple of 8 (16-byte rows for the tensor maps), got %lld", (long long)k);
     B200Q_REQUIRE(n_out % 8 == 0, "n_out must be a multiple of 8 (16-byte output vectors), got %lld", (long long)n_out);
@@ -511,7 +524,8 @@ int b200q_awq_gemm_project(const void* x, int64_t tokens, int64_t k, const void*
     p.n_out = (int)n_out;
     p.up_row_offset = (int)n_out;
     p.out = (uint16_t*)out;
-    const int64_t items = (int64_t)p.n_variants * p.n_m_tiles * p.n_n_tiles;
+    p.tile_variant = (const int32_t*)tile_variant;
+    const int64_t items = (int64_t)(tile_variant ? 1 : p.n_variants) * p.n_m_tiles * p.n_n_tiles;
     B200Q_REQUIRE(items < (1ll << 31), "too many tiles");
     const int grid = (int)min((int64_t)kNumSMs, items);
     if (swiglu) {
@@ -523,6 +537,18 @@ int b200q_awq_gemm_project(const void* x, int64_t tokens, int64_t k, const void*
     }
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
+}
+
+int b200q_awq_gemm_project(const void* x, int64_t tokens, int64_t k, const void* w, int64_t n_variants, int64_t n_out, int32_t swiglu,
+                           void* out, void* stream) {
+    return gemm_project_impl(x, tokens, k, w, n_variants, n_out, swiglu, nullptr, out, stream);
+}
+
+int b200q_awq_gemm_project_grouped(const void* x, int64_t tokens, int64_t k, const void* w, int64_t n_experts, int64_t n_out, int32_t swiglu,
+                                   const int32_t* tile_expert, void* out, void* stream) {
+    B200Q_REQUIRE(tile_expert, "b200q_awq_gemm_project_grouped: NULL tile table");
+    B200Q_REQUIRE(tokens % BM == 0, "grouped projection: the rows of every expert are padded to whole %d-row tiles by the caller", BM);
+    return gemm_project_impl(x, tokens, k, w, n_experts, n_out, swiglu, tile_expert, out, stream);
 }
 
 }  // extern "C"
