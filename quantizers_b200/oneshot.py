@@ -196,7 +196,14 @@ def awq_model(model: torch.nn.Module, recipe: Union[str, dict, Recipe], calibrat
     for s_name, balance, parent in resolve_mappings(names, spec):
         balance = [b for b in balance if b in targets]
         if balance:
-            resolved.append((s_name, balance, parent if len(balance) > 1 else balance[0]))
+            if len(balance) == 1:
+                parent = balance[0]
+            else:
+                # containers have no forward of their own: climb to the first real module (llmcompressor avoids ModuleList
+                # ancestors the same way -- for "every expert's w1 / w3" the parent is the sparse-MoE block, not `experts`)
+                while parent and isinstance(mods[parent], (torch.nn.ModuleList, torch.nn.ModuleDict)):
+                    parent = parent.rpartition(".")[0]
+            resolved.append((s_name, balance, parent))
     cap = _Capture(model, {b for _, bl, _ in resolved for b in bl[:1]}, {p for _, bl, p in resolved if len(bl) > 1})
     try:
         for batch in calibration:

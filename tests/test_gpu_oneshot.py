@@ -181,3 +181,129 @@ def test_oneshot_refuses_cpu_weights():
     m = TinyLM().to(torch.bfloat16)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         oneshot(m, NVFP4_RECIPE)
+
+
+# ----------------------------------------------------------------------------- MoE recipe (config 5 shape) through awq_model
+MOE_RECIPE = """
+default_stage:
+  default_modifiers:
+    AWQModifier:
+      config_groups:
+        mlp_experts_projections:
+          targets: ["re:.*block_sparse_moe\\\\.experts\\\\.\\\\d+\\\\.(w1|w2|w3)$"]
+          weights: {num_bits: 4, type: int, symmetric: true, group_size: 32, strategy: group, dynamic: false, observer: memoryless_minmax}
+      mappings:
+        - smooth_layer: re:.*post_attention_layernorm$
+          balance_layers: ["re:.*w1$", "re:.*w3$"]
+        - smooth_layer: re:.*w3$
+          balance_layers: ["re:.*w2$"]
+      duo_scaling: true
+"""
+
+
+class Expert(torch.nn.Module):
+    def __init__(self, h, i):
+        super().__init__()
+        self.w1, self.w3, self.w2 = torch.nn.Linear(h, i, bias=False), torch.nn.Linear(h, i, bias=False), torch.nn.Linear(i, h, bias=False)
+
+    def forward(self, x):
+        return self.w2(torch.nn.functional.silu(self.w1(x)) * self.w3(x))
+
+
+class SparseMoE(torch.nn.Module):
+    """Routed block in "calibrate all experts" form (what llmcompressor swaps in, REF:scripts/do_oneshot.py:186): every expert
+    runs on ALL tokens, only the routed rows reach the output (index_add_ per expert, ascending)."""
+
+    def __init__(self, h=128, i=256, e=4, k=2):
+        super().__init__()
+        self.gate = torch.nn.Linear(h, e, bias=False)
+        self.experts = torch.nn.ModuleList([Expert(h, i) for _ in range(e)])
+        self.k = k
+
+    def forward(self, x):
+        B, S, H = x.shape
+        xf = x.reshape(-1, H)
+        p = torch.softmax(self.gate(xf).float(), dim=-1)
+        w, idx = torch.topk(p, self.k, dim=-1)
+        w = (w / w.sum(-1, keepdim=True)).to(x.dtype)
+        out = torch.zeros_like(xf)
+        for e, ex in enumerate(self.experts):
+            y = ex(xf)
+            tok, slot = torch.where(idx == e)
+            if tok.numel():
+                out.index_add_(0, tok, y[tok] * w[tok, slot, None])
+        return out.view(B, S, H)
+
+
+class MoELayer(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.post_attention_layernorm = torch.nn.LayerNorm(128)
+        self.block_sparse_moe = SparseMoE()
+
+    def forward(self, x):
+        return x + self.block_sparse_moe(self.post_attention_layernorm(x))
+
+
+class TinyMoELM(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.model = torch.nn.Module()
+        self.model.layers = torch.nn.ModuleList([MoELayer()])
+
+    def forward(self, x):
+        return self.model.layers[0](x)
+
+
+def test_awq_moe_recipe_through_oneshot():
+    """MiniMax-style experts-only AWQ recipe (REF:configs/recipes/recipe_Minimax-M2.1-Experts-only-AWQ.yaml shape): the layer-wide
+    mapping resolves to all experts' w1 + w3 with the sparse-MoE block as parent, the per-expert mappings to w3 -> w2; results
+    against the restated search replaying the same block on the CPU."""
+    import copy
+
+    from torch.func import functional_call
+
+    from quantizers_b200 import recipe as RC
+    from quantizers_b200.oneshot import _Capture, awq_model
+
+    torch.manual_seed(11)
+    m = TinyMoELM()
+    for p in m.parameters():
+        if p.ndim == 2:
+            p.data.normal_(0, 0.05)
+    m.model.layers[0].block_sparse_moe.gate.weight.data.normal_(0, 1.0)
+    m = m.to(torch.bfloat16).cuda()
+    cpu = copy.deepcopy(m).cpu()
+    batches = _batches(n=3, S=64, seed=5)
+    pre = "model.layers.0.block_sparse_moe"
+    names = [f"{pre}.experts.0.w1"] + [f"{pre}.experts.{e}.w2" for e in range(4)]
+    cap = _Capture(m, names, [pre])
+    with torch.no_grad():
+        for b in batches:
+            m(b)
+    cap.close()
+    w0 = {n: p.detach().cpu().clone() for n, p in m.named_parameters()}
+    sd, cfg, results = awq_model(m, RC.parse_recipe(MOE_RECIPE), batches)
+    assert len(results) == 1 + 4 and cfg["format"] == "pack-quantized"
+    # layer-wide mapping: balance = w1 of every expert, then w3 of every expert; parent = the MoE block
+    balance = [f"{pre}.experts.{e}.w1" for e in range(4)] + [f"{pre}.experts.{e}.w3" for e in range(4)]
+    key = "model.layers.0.post_attention_layernorm -> " + ",".join(balance)
+    assert key in results
+    block = cpu.model.layers[0].block_sparse_moe
+    calls = [a[0].cpu() for a, _ in cap.parent_args[pre]]
+    rel = [b[len(pre) + 1:] + ".weight" for b in balance]
+
+    def parent(weights, _x):
+        outs = [functional_call(block, dict(zip(rel, weights)), (c,)) for c in calls]
+        return torch.cat([o.reshape(-1, o.shape[-1]) for o in outs])
+
+    x_cpu = torch.cat([t.cpu() for t in cap.inputs[f"{pre}.experts.0.w1"]])
+    s_ref, r_ref, l_ref = R.compute_best_scale([x_cpu], [w0[b + ".weight"] for b in balance], parent, O.Geom(O.GROUP, 32), O.INT, 4, True)
+    s, r, losses = results[key]
+    assert r == r_ref and max(abs(a - b) / b for a, b in zip(losses, l_ref)) < 1e-3
+    assert torch.allclose(s, s_ref, rtol=1e-5)
+    # every target got packed tensors
+    for e in range(4):
+        for wn in ("w1", "w2", "w3"):
+            assert f"{pre}.experts.{e}.{wn}.weight_packed" in sd and f"{pre}.experts.{e}.{wn}.weight_scale" in sd
+    assert not any(k.startswith(f"{pre}.gate") for k in sd)
