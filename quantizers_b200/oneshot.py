@@ -112,6 +112,70 @@ def quantize_model(model: torch.nn.Module, recipe: Union[str, dict, Recipe], mod
     return sd, cfg
 
 
+# ----------------------------------------------------------------------------- activation calibration (O3)
+@torch.no_grad()
+def calibrate_activations(model: torch.nn.Module, spec: ModifierSpec, dataset: Sequence, forward: Optional[Callable] = None) -> Dict[str, torch.Tensor]:
+    """LLMC ``calibrate_activations(module, x, "input")`` for every target whose scheme quantizes its inputs statically:
+    forward pre-hooks feed each Linear's input to a CUDA observer (state stays on the device, one kernel per call);
+      TENSOR_GROUP (NVFP4, ``static_minmax``)  -> ``<module>.input_global_scale`` fp32 [1] = generate_gparam(running min / max)
+      TENSOR static (FP8)                      -> ``<module>.input_scale`` = calculate_qparams(min, max) in the activation dtype
+    Dynamic schemes (token / group activations) calibrate nothing.  Empty inputs (an expert no token reached) are skipped."""
+    from .observers import Observer
+
+    lin = _linears(model)
+    targets = resolve_targets(lin, spec)
+    observers: Dict[str, Observer] = {}
+    handles = []
+    for name, mod in lin:
+        g = targets.get(name)
+        ia = None if g is None else g.input_activations
+        if ia is None:
+            continue
+        strat = ia.strategy
+        dyn = getattr(ia, "dynamic", False)
+        if not ((strat == "tensor_group") or (strat == "tensor" and dyn in (False, None))):
+            continue
+        obs = Observer.load_from_registry(getattr(ia, "observer", None) or "static_minmax", base_name="input", args=ia)
+        observers[name] = obs
+
+        def hook(m, args, _obs=obs, _tg=(strat == "tensor_group")):
+            x = args[0]
+            if x.numel() == 0:
+                return
+            if _tg:
+                _obs.get_global_scale(x.detach())
+            else:
+                _obs(x.detach())
+
+        handles.append(mod.register_forward_pre_hook(hook))
+    if not observers:
+        return {}
+    try:
+        for batch in dataset:
+            if forward is not None:
+                forward(model, batch)
+            elif isinstance(batch, dict):
+                model(**batch)
+            else:
+                model(batch)
+    finally:
+        for h in handles:
+            h.remove()
+    out: Dict[str, torch.Tensor] = {}
+    for name, obs in observers.items():
+        if _strategy_of(obs.args) == "tensor_group":
+            if obs.global_min is not None:
+                out[f"{name}.input_global_scale"] = ops.generate_gparam(obs.global_min, obs.global_max)
+        elif obs.min_val is not None:
+            scale, _ = ops.calculate_qparams(obs.min_val, obs.max_val, obs.args)
+            out[f"{name}.input_scale"] = scale
+    return out
+
+
+def _strategy_of(args) -> str:
+    return getattr(args.strategy, "value", args.strategy)
+
+
 # ----------------------------------------------------------------------------- AWQ over a module tree
 class _Capture:
     """Forward pre-hooks that keep the inputs of the balance layers (first positional argument, flattened to [tokens, K]) and
@@ -255,6 +319,8 @@ def oneshot(model: torch.nn.Module, recipe: Union[str, dict, Recipe], dataset: O
             if spec.kind == "GPTQModifier":
                 raise NotImplementedError("GPTQ is outside the hot path this package accelerates (SURVEY.md §8f)")
             part, cfg = quantize_model(model, rec, spec=spec)
+            if dataset is not None:
+                part.update(calibrate_activations(model, spec, dataset, forward))
         else:
             raise NotImplementedError(f"modifier {spec.kind} is not part of the quantization hot path")
         sd.update(part)

@@ -307,3 +307,24 @@ def test_awq_moe_recipe_through_oneshot():
         for wn in ("w1", "w2", "w3"):
             assert f"{pre}.experts.{e}.{wn}.weight_packed" in sd and f"{pre}.experts.{e}.{wn}.weight_scale" in sd
     assert not any(k.startswith(f"{pre}.gate") for k in sd)
+
+
+def test_oneshot_nvfp4_input_global_scales():
+    """NVFP4 scheme with calibration data: every target also gets ``input_global_scale`` from the static_minmax observer over
+    all batches (LLMC calibrate_activations; CT:quantization/quant_scheme.py:170-180)."""
+    from quantizers_b200.oneshot import _Capture, oneshot
+
+    m = _model(7)
+    batches = _batches(n=3, S=48, seed=9)
+    names = [n for n, mod in m.named_modules() if isinstance(mod, torch.nn.Linear) and n != "lm_head"]
+    cap = _Capture(m, names, [])
+    with torch.no_grad():
+        for b in batches:
+            m(b)
+    cap.close()
+    sd, cfg = oneshot(m, NVFP4_RECIPE, dataset=batches)
+    for n in names:
+        want = R.activation_global_scale([t.cpu() for t in cap.inputs[n]])
+        got = sd[f"{n}.input_global_scale"]
+        assert got.dtype == torch.float32 and got.numel() == 1 and got.item() == want.item(), n
+    assert "lm_head.input_global_scale" not in sd
