@@ -144,6 +144,14 @@ int b200q_fake_quantize(const void* x, int64_t rows, int64_t cols, const b200q_s
 int b200q_dequantize(const void* codes, int64_t rows, int64_t cols, const b200q_scheme* scheme, const void* scale,
                      const int8_t* zp, const float* global_scale, void* out, void* stream);
 
+/* Compressor.decompress in one pass (CT:compressors/pack_quantized/base.py:79-113, nvfp4/base.py:74-96): packed codes + qparams
+ * -> T weights [batch, rows, cols], without the unpacked int8 / T intermediates.  Same layouts as the b200q_compress_* outputs;
+ * zp_packed NULL for symmetric schemes (nothing is subtracted, like dequantize(zero_point=None)); global_scale fp32 [batch]. */
+int b200q_decompress_int_packed(const int32_t* packed, const void* scale, const int32_t* zp_packed, int64_t batch, int64_t rows, int64_t cols,
+                                const b200q_scheme* scheme, void* out, void* stream);
+int b200q_decompress_nvfp4(const uint8_t* packed, const uint8_t* scale_e4m3, const float* global_scale, int64_t batch, int64_t rows, int64_t cols,
+                           int32_t dtype, void* out, void* stream);
+
 /* Q7/Q9: pack_to_int32 / unpack_from_int32  CT:compressors/pack_quantized/helpers.py:20-161 */
 int b200q_pack_int32(const int8_t* value, int64_t rows, int64_t cols, int32_t num_bits, int32_t packed_dim,
                      int32_t* packed, void* stream);

@@ -64,6 +64,8 @@ _SIGS = {
     "b200q_compress_nvfp4_workspace": (c_int64, [c_int64, c_int64, c_int64, c_int32]),
     "b200q_awq_gemm_project_grouped": (_I, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int32, _P, _P, _P]),
     "b200q_moe_combine": (_I, [_P, _P, _P, c_int64, c_int32, c_int64, _P, _P]),
+    "b200q_decompress_int_packed": (_I, [_P, _P, _P, c_int64, c_int64, c_int64, _S, _P, _P]),
+    "b200q_decompress_nvfp4": (_I, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P]),
     "b200q_pipeline_create": (_I, [POINTER(c_void_p), c_int64, c_int32]),
     "b200q_pipeline_destroy": (_I, [_P]),
     "b200q_pipeline_compress_host": (_I, [_P, _P, c_int64, c_int64, c_int64, _S, _P, _P, _P, _P]),

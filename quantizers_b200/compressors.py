@@ -56,8 +56,19 @@ class B200PackedQuantizationCompressor(PackedQuantizationCompressor):
         zero_point = state_dict.get("weight_zero_point", None)
         original_shape = state_dict.get("weight_shape")
         weights = scheme.weights
-        if not weights.symmetric and weights.strategy in PACK_ZP_STRATS:
+        asym = not weights.symmetric and weights.strategy in PACK_ZP_STRATS
+        if asym:
             assert zero_point is not None, "Asymmetric quant requires zero-point values"
+        strat = getattr(weights.strategy, "value", weights.strategy)
+        if packed.is_cuda and strat in ("group", "channel") and scale.dtype in (torch.bfloat16, torch.float16, torch.float32):
+            # fused unpack + dequantize: one pass, no int8 intermediate
+            state_dict["weight"] = ops.decompress_int_packed(packed, scale, zero_point if asym else None, tuple(int(v) for v in original_shape),
+                                                             weights)
+            if asym:
+                state_dict["weight_zero_point"] = ops.unpack_from_int32(zero_point, weights.num_bits, (*original_shape[:-1], scale.shape[-1]),
+                                                                        packed_dim=0)
+            return state_dict
+        if asym:
             zero_point = ops.unpack_from_int32(zero_point, weights.num_bits, (*original_shape[:-1], scale.shape[-1]), packed_dim=0)
             state_dict["weight_zero_point"] = zero_point
         unpacked = ops.unpack_from_int32(packed, weights.num_bits, original_shape)
@@ -89,6 +100,10 @@ class B200NVFP4PackedCompressor(NVFP4PackedCompressor):
         scale = state_dict.get("weight_scale")
         global_scale = state_dict.get("weight_global_scale", None)
         m, n = packed.shape
+        if packed.is_cuda and global_scale is not None and scale.dtype == torch.float8_e4m3fn:
+            state_dict["weight"] = ops.decompress_nvfp4(packed, scale, global_scale, torch.bfloat16)  # fused unpack + dequantize
+            state_dict["weight_scale"] = torch.nn.Parameter(scale.to(torch.bfloat16), requires_grad=False)
+            return state_dict
         unpacked = ops.unpack_fp4_from_uint8(packed, m, n * 2)
         scale_float = scale.to(unpacked.dtype)
         state_dict["weight"] = ops.dequantize(x_q=unpacked, scale=scale_float, global_scale=global_scale, dtype=unpacked.dtype)

@@ -252,6 +252,19 @@ int b200q_dequantize(const void* codes, int64_t rows, int64_t cols, const b200q_
     return elementwise(EW_DEQUANT, codes, rows, cols, sc, scale, zp, gs, out, stream);
 }
 
+int b200q_decompress_int_packed(const int32_t* packed, const void* scale, const int32_t* zp_packed, int64_t batch, int64_t rows, int64_t cols,
+                                const b200q_scheme* sc, void* out, void* stream) {
+    if (int rc = check_scheme(sc)) return rc;
+    REQ_PTR(packed); REQ_PTR(scale); REQ_PTR(out);
+    B200Q_REQUIRE(sc->qtype == B200Q_INT && (sc->strategy == B200Q_GROUP || sc->strategy == B200Q_CHANNEL), "pack-quantized decompress: INT, group or channel");
+    return launch_decompress_int_packed(sc->dtype, packed, scale, zp_packed, batch, rows, cols, sc->strategy == B200Q_GROUP ? sc->group_size : 0,
+                                        sc->num_bits, out, (cudaStream_t)stream);
+}
+int b200q_decompress_nvfp4(const uint8_t* packed, const uint8_t* scale_e4m3, const float* global_scale, int64_t batch, int64_t rows, int64_t cols,
+                           int32_t dtype, void* out, void* stream) {
+    REQ_PTR(packed); REQ_PTR(scale_e4m3); REQ_PTR(global_scale); REQ_PTR(out);
+    return launch_decompress_nvfp4(dtype, packed, scale_e4m3, global_scale, 1, batch, rows, cols, out, (cudaStream_t)stream);
+}
 int b200q_pack_int32(const int8_t* value, int64_t rows, int64_t cols, int32_t num_bits, int32_t packed_dim, int32_t* packed,
                      void* stream) {
     REQ_PTR(value); REQ_PTR(packed);

@@ -70,6 +70,11 @@ int launch_unpack_int32(const int32_t* p, int64_t rows, int64_t cols, int nbits,
 int launch_pack_fp4(int dt, const void* x, int64_t rows, int64_t cols, uint8_t* out, cudaStream_t st);
 int launch_unpack_fp4(int dt, const uint8_t* p, int64_t rows, int64_t cols, void* out, cudaStream_t st);
 
+int launch_decompress_int_packed(int dt, const int32_t* packed, const void* scale, const int32_t* zp_packed, int64_t batch, int64_t rows,
+                                 int64_t cols, int group, int nbits, void* out, cudaStream_t st);
+int launch_decompress_nvfp4(int dt, const uint8_t* packed, const uint8_t* scale, const float* gs, int gs_stride, int64_t batch, int64_t rows,
+                            int64_t cols, void* out, cudaStream_t st);
+
 // ---- fused CHANNEL / BLOCK / TENSOR compress (quant_tile.cu)
 struct TileParams {
     const void* w;

@@ -66,6 +66,67 @@ __global__ void __launch_bounds__(256) unpack_fp4_kernel(const uint8_t* __restri
     }
 }
 
+// ---- fused decompress: packed codes + qparams -> T weights in one pass (CT Compressor.decompress =
+// unpack_from_int32 / unpack_fp4_from_uint8 followed by dequantize, compressors/pack_quantized/base.py:79-113, nvfp4/base.py:74-96).
+// One thread per output chunk of 8 elements (16-byte store); reads 0.5 B + qparams per element instead of the int8 / T
+// intermediates of the two-step path (1 B resp. 2 B written and read back per element).
+template <int DT>
+__global__ void __launch_bounds__(256) decompress_int_packed_kernel(const int32_t* __restrict__ packed, const void* __restrict__ scale,
+                                                                    const int32_t* __restrict__ zp_packed, int64_t batch, int64_t rows,
+                                                                    int64_t cols, int group, int nbits, void* __restrict__ out) {
+    const int pf = 32 / nbits, off = 1 << (nbits - 1);
+    const uint32_t mask = (1u << nbits) - 1u;
+    const int64_t pcols = (cols + pf - 1) / pf, chunks_per_row = (cols + 7) / 8;
+    const int64_t gtot = group > 0 ? cols / group : 1, zrows = (rows + pf - 1) / pf;
+    const int64_t total = batch * rows * chunks_per_row;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t br = t / chunks_per_row, ch = t - br * chunks_per_row;  // br = b * rows + r
+        const int64_t b = br / rows, r = br - b * rows, c0 = ch * 8;
+        float y[8];
+        uint32_t w = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int64_t c = c0 + i;
+            if (c >= cols) { y[i] = 0.0f; continue; }
+            if (i % pf == 0 || i == 0) w = (uint32_t)packed[br * pcols + c / pf];
+            const float q = (float)((int)((w >> (nbits * (int)(c % pf))) & mask) - off);
+            const int64_t g = group > 0 ? c / group : 0;
+            const float s = load_T<DT>(scale, br * gtot + g);
+            float z = 0.0f;
+            if (zp_packed) {
+                const uint32_t zw = (uint32_t)zp_packed[(b * zrows + r / pf) * gtot + g];
+                z = (float)((int)((zw >> (nbits * (int)(r % pf))) & mask) - off);
+            }
+            y[i] = dequant_val<DT>(q, s, z, zp_packed != nullptr);
+        }
+        if (c0 + 8 <= cols) store_chunk_T<DT>(out, br * cols + c0, y);
+        else for (int i = 0; c0 + i < cols; i++) store_T<DT>(out, br * cols + c0 + i, y[i]);
+    }
+}
+// NVFP4: one thread per group of 16 (8 bytes of codes, one e4m3 scale): value * (fp32(scale) / gs), fp32 product cast to T
+template <int DT>
+__global__ void __launch_bounds__(256) decompress_nvfp4_kernel(const uint2* __restrict__ packed, const uint8_t* __restrict__ scale,
+                                                               const float* __restrict__ gs, int gs_stride, int64_t groups_per_mat,
+                                                               int64_t n_groups, void* __restrict__ out) {
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 cw = packed[g];
+        // the module holds the e4m3 scale as T (exact) and dequantize() promotes scale / global_scale to fp32
+        const float se = fdiv(round_to<DT>(e4m3_decode(scale[g])), gs[gs_stride ? g / groups_per_mat : 0]);
+        const uint32_t words[2] = {cw.x, cw.y};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t nib = (words[h] >> (4 * i)) & 0xfu;
+                const float v = e2m1_value(nib & 7u);
+                y[i] = round_to<DT>(fmul((nib & 8u) ? -v : v, se));
+            }
+            store_chunk_T<DT>(out, g * 16 + h * 8, y);
+        }
+    }
+}
+
 static int nblocks(int64_t work) { return (int)max((int64_t)1, min((int64_t)kNumSMs * 16, (work + 255) / 256)); }
 
 int launch_pack_int32(const int8_t* v, int64_t rows, int64_t cols, int nbits, int packed_dim, int32_t* out, cudaStream_t st) {
@@ -93,6 +154,29 @@ int launch_pack_fp4(int dt, const void* x, int64_t rows, int64_t cols, uint8_t* 
 int launch_unpack_fp4(int dt, const uint8_t* p, int64_t rows, int64_t cols, void* out, cudaStream_t st) {
     if (rows * cols == 0) return B200Q_OK;
     B200Q_DISPATCH_DT(dt, { unpack_fp4_kernel<DT><<<nblocks(rows * cols), 256, 0, st>>>(p, rows * cols, out); });
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+int launch_decompress_int_packed(int dt, const int32_t* packed, const void* scale, const int32_t* zp_packed, int64_t batch, int64_t rows,
+                                 int64_t cols, int group, int nbits, void* out, cudaStream_t st) {
+    B200Q_REQUIRE(nbits == 4 || nbits == 8, "pack-quantized decompress supports 4 and 8 bits");
+    B200Q_REQUIRE(group == 0 || cols % group == 0, "tensor column shape must be divisible by the given group_size %d but got %lld", group,
+                  (long long)cols);
+    B200Q_REQUIRE(cols % 8 == 0 || (dt == DT_F32), "columns must be a multiple of 8 for the 16-byte stores");
+    if (batch * rows * cols == 0) return B200Q_OK;
+    B200Q_DISPATCH_DT(dt, { decompress_int_packed_kernel<DT><<<nblocks(batch * rows * ((cols + 7) / 8)), 256, 0, st>>>(packed, scale, zp_packed, batch,
+                                                                                                                rows, cols, group, nbits, out); });
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+int launch_decompress_nvfp4(int dt, const uint8_t* packed, const uint8_t* scale, const float* gs, int gs_stride, int64_t batch, int64_t rows,
+                            int64_t cols, void* out, cudaStream_t st) {
+    B200Q_REQUIRE(cols % 16 == 0, "tensor column shape must be divisible by the given group_size 16 but got %lld", (long long)cols);
+    B200Q_REQUIRE((((uintptr_t)packed) & 7) == 0 && (((uintptr_t)out) & 15) == 0, "packed / out must be 8 / 16-byte aligned");
+    if (batch * rows * cols == 0) return B200Q_OK;
+    const int64_t gpm = rows * (cols / 16), n = batch * gpm;
+    B200Q_DISPATCH_DT(dt, { decompress_nvfp4_kernel<DT><<<nblocks(n), 256, 0, st>>>((const uint2*)packed, scale, gs, gs_stride, gpm, n, out); });
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }

@@ -334,6 +334,47 @@ def observe_mse_minmax(weight: torch.Tensor, args, global_scale: Optional[torch.
     return mn, mx
 
 
+# ----------------------------------------------------------------------------- fused decompress
+@torch.no_grad()
+def decompress_int_packed(packed: torch.Tensor, scale: torch.Tensor, zp_packed: Optional[torch.Tensor], shape, args) -> torch.Tensor:
+    """pack-quantized ``Compressor.decompress`` in one pass: ``weight_packed`` int32 + ``weight_scale`` (+ row-packed
+    ``weight_zero_point``) -> weight ``[*lead, rows, cols]`` in the scale dtype (unpack_from_int32 + dequantize fused)."""
+    L.require_cuda(packed, scale, zp_packed)
+    rows, cols = int(shape[-2]), int(shape[-1])
+    lead = tuple(packed.shape[:-2])
+    batch = 1
+    for d in lead:
+        batch *= int(d)
+    if scale.dtype not in L.DTYPE_CODE:
+        raise B200QError(f"unsupported scale dtype {scale.dtype}")
+    sc = scheme_from_args(args, scale.dtype, zp_packed is not None)
+    out = torch.empty(lead + (rows, cols), dtype=scale.dtype, device=packed.device)
+    L.check(L.lib().b200q_decompress_int_packed(L.ptr(packed.contiguous()), L.ptr(scale.contiguous()),
+                                                L.ptr(zp_packed.contiguous() if zp_packed is not None else None), batch, rows, cols,
+                                                ctypes.byref(sc), L.ptr(out), L.stream_ptr(packed.device)))
+    return out
+
+
+@torch.no_grad()
+def decompress_nvfp4(packed: torch.Tensor, scale: torch.Tensor, global_scale: torch.Tensor, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """nvfp4-pack-quantized ``decompress`` in one pass: u8 code pairs + e4m3 group scales + fp32 global scale -> weight."""
+    L.require_cuda(packed, scale, global_scale)
+    rows, half = int(packed.shape[-2]), int(packed.shape[-1])
+    lead = tuple(packed.shape[:-2])
+    batch = 1
+    for d in lead:
+        batch *= int(d)
+    gs = global_scale.to(torch.float32).reshape(-1).contiguous()
+    if gs.numel() == 1 and batch > 1:
+        gs = gs.expand(batch).contiguous()
+    if gs.numel() != batch:
+        raise B200QError(f"global_scale must have one entry per stacked weight, got {gs.numel()} for {batch}")
+    out = torch.empty(lead + (rows, half * 2), dtype=dtype, device=packed.device)
+    L.check(L.lib().b200q_decompress_nvfp4(L.ptr(packed.contiguous()), L.ptr(scale.contiguous().view(torch.uint8)), L.ptr(gs), batch, rows, half * 2,
+                                           L.DTYPE_CODE[dtype], L.ptr(out), L.stream_ptr(packed.device)))
+    return out
+
+
 # ----------------------------------------------------------------------------- pack / unpack
 @torch.no_grad()
 def pack_to_int32(value: torch.Tensor, num_bits: int, packed_dim: int = 1) -> torch.Tensor:

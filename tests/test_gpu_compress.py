@@ -288,3 +288,31 @@ def test_fast_int4_boundary_cases():
     want = O.compress(w2, "nvfp4-pack-quantized", geom_of("nvfp4"), 4, True)
     got = ops.compress_weight(w2.cuda(), Args("nvfp4"))
     _cmp_sd(got, want, "nvfp4 thresholds")
+
+
+@pytest.mark.parametrize("name", ["int4_g128_asym", "int4_g32_sym", "int4_channel_asym", "int4_channel_sym", "int8_g128_sym", "nvfp4"])
+def test_fused_decompress_matches_two_step_oracle(name):
+    """§8f rank 1: packed codes + qparams -> weights in one pass == the oracle's unpack followed by dequantize (which the CPU
+    suite pins against live compressed-tensors' Compressor.decompress), incl. a stacked [E, rows, cols] launch."""
+    from quantizers_b200 import ops
+
+    fmt, qtype, nb, sym, *_ = FORMATS[name]
+    geom = geom_of(name)
+    ws = [synth_weight(72, 256, torch.bfloat16, 60 + e) for e in range(3)]
+    sds = [O.compress(w, fmt, geom, nb, sym) for w in ws]
+    wants = []
+    for w, sd in zip(ws, sds):
+        if fmt == "pack-quantized":
+            q = O.unpack_from_int32(sd["weight_packed"], nb, w.shape)
+            zp = None if sym else O.unpack_from_int32(sd["weight_zero_point"], nb, sd["weight_scale"].shape, 0)
+            wants.append(O.dequantize(q, sd["weight_scale"], zp, geom, qtype))
+        else:
+            vals = O.unpack_fp4_from_uint8(sd["weight_packed"], *w.shape)
+            wants.append(O.dequantize(vals, sd["weight_scale"].to(torch.bfloat16), None, geom, qtype, sd["weight_global_scale"], out_dtype=torch.bfloat16))
+    stack = lambda k: torch.stack([sd[k] for sd in sds]).cuda()
+    if fmt == "pack-quantized":
+        got = ops.decompress_int_packed(stack("weight_packed"), stack("weight_scale"), None if sym else stack("weight_zero_point"), (72, 256), Args(name))
+    else:
+        got = ops.decompress_nvfp4(stack("weight_packed"), stack("weight_scale"), stack("weight_global_scale"))
+    for e, want in enumerate(wants):
+        assert_bits_equal(got[e], want, f"{name}[{e}]")
