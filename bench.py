@@ -541,6 +541,12 @@ def main():
         d["ms"] += a.elapsed_time(b)
         d["elems"] += elems
         d["n"] += 1
+    by_name = {}
+    for name, preset, elems, a, b in timings:
+        d = by_name.setdefault(name, [0.0, 0, preset])
+        d[0] += a.elapsed_time(b)
+        d[1] += elems
+    log("per-launch GB/s (algorithmic):", {k: round(S.PRESETS[v[2]].bytes_per_element() * v[1] / (v[0] * 1e-3) / 1e9) for k, v in by_name.items()})
     dom = max(per, key=lambda k: per[k]["ms"])
     dargs = S.PRESETS[dom]
     alg_bytes = dargs.bytes_per_element() * per[dom]["elems"]
