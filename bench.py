@@ -632,6 +632,26 @@ def main():
                                     "sample": f"{n_layers} of 36 Qwen3-4B decoder layers ({nb / 1e9:.2f} GB bf16) through "
                                               + ("live compressed-tensors (observer amin/amax -> calculate_qparams -> Compressor.compress)"
                                                  if kind == "reference" else "the C oracle")}
+            if kind == "reference":
+                # the same compressed-tensors eager ops on this GPU (SURVEY.md §8d "reference on this box"): like-for-like hardware
+                try:
+                    from oracle import ct_live as LCT
+
+                    layer = [(n, f, w.to(dev)) for n, f, w in cpu_layer(0)]
+                    for rep in range(2):  # first pass warms cuBLAS / allocator
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        nbc = 0
+                        for _, fmt_name, w in layer:
+                            fmt, a = LCT.format_args(fmt_name)
+                            LCT.compress(w, fmt, a)
+                            nbc += w.numel() * 2
+                        torch.cuda.synchronize()
+                        dtc = time.perf_counter() - t0
+                    line["ct_eager_cuda"] = {"value": nbc / dtc / 1e9, "unit": UNIT,
+                                             "sample": "one decoder layer through live compressed-tensors with the tensors on this GPU (eager ATen kernels)"}
+                except Exception as e:  # noqa: BLE001 -- informational leg only
+                    line["ct_eager_cuda"] = {"unavailable": str(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

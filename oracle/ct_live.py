@@ -85,8 +85,8 @@ def weight_qparams(w: torch.Tensor, args, gs: torch.Tensor | None = None):
 
     mn, mx = observe_minmax(w, args)
     scale, zp = calculate_qparams(mn, mx, args, global_scale=gs)
-    scale_p = torch.empty(scale.shape, dtype=w.dtype).copy_(scale)
-    zp_p = torch.zeros(zp.shape, dtype=args.zp_dtype).copy_(zp)
+    scale_p = torch.empty(scale.shape, dtype=w.dtype, device=w.device).copy_(scale)
+    zp_p = torch.zeros(zp.shape, dtype=args.zp_dtype, device=w.device).copy_(zp)
     if args.strategy == "channel":
         scale_p, zp_p = scale_p.reshape(-1, 1), zp_p.reshape(-1, 1)
     return scale_p, zp_p
