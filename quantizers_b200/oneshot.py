@@ -333,3 +333,62 @@ def oneshot(model: torch.nn.Module, recipe: Union[str, dict, Recipe], dataset: O
         if extra["format"] != cfg["format"]:
             cfg["format"] = "mixed-precision"
     return sd, cfg
+
+
+# ----------------------------------------------------------------------------- save_pretrained(save_compressed=True)
+_TORCH_TO_ST = {torch.bfloat16: "BF16", torch.float16: "F16", torch.float32: "F32", torch.float64: "F64", torch.int64: "I64", torch.int32: "I32",
+                torch.int16: "I16", torch.int8: "I8", torch.uint8: "U8", torch.bool: "BOOL", torch.float8_e4m3fn: "F8_E4M3",
+                torch.float8_e5m2: "F8_E5M2"}
+
+
+def save_compressed(model: torch.nn.Module, state_dict: Dict[str, torch.Tensor], quantization_config: dict, save_directory: str,
+                    config: Optional[dict] = None, max_shard_bytes: int = 5 << 30) -> dict:
+    """``model.save_pretrained(save_directory, save_compressed=True)`` (REF:scripts/do_oneshot.py:197) for the result of
+    ``oneshot``: the compressed tensors replace the ``weight`` of every quantized module, every other parameter / buffer of the
+    model is written as is, shards of at most ``max_shard_bytes`` in safetensors format plus ``model.safetensors.index.json`` and
+    ``config.json`` with the ``quantization_config`` block.  Tensors leave the GPU one at a time (D2H into the shard file)."""
+    import json
+    import os
+
+    from .model_free import build_header
+
+    quantized = {k.rsplit(".", 1)[0] for k in state_dict if k.rsplit(".", 1)[-1] in ("weight_packed", "weight_scale")}
+    entries: List[Tuple[str, torch.Tensor]] = []
+    for name, t in model.state_dict().items():
+        mod, _, leaf = name.rpartition(".")
+        if mod in quantized and leaf == "weight":
+            continue
+        if name in state_dict:
+            continue
+        entries.append((name, t))
+    entries += list(state_dict.items())
+    entries.sort(key=lambda kv: kv[0])
+    shards: List[List[Tuple[str, torch.Tensor]]] = [[]]
+    size = 0
+    for name, t in entries:
+        nb = t.numel() * t.element_size()
+        if shards[-1] and size + nb > max_shard_bytes:
+            shards.append([])
+            size = 0
+        shards[-1].append((name, t))
+        size += nb
+    os.makedirs(save_directory, exist_ok=True)
+    weight_map, total = {}, 0
+    for i, shard in enumerate(shards):
+        fname = "model.safetensors" if len(shards) == 1 else f"model-{i + 1:05d}-of-{len(shards):05d}.safetensors"
+        head, offsets = build_header([(n, _TORCH_TO_ST[t.dtype], tuple(t.shape)) for n, t in shard], {"format": "pt"})
+        with open(os.path.join(save_directory, fname), "wb") as f:
+            f.write(head)
+            for n, t in shard:
+                host = t.detach().contiguous().cpu()
+                f.write(host.view(torch.uint8).numpy().tobytes() if host.numel() else b"")
+                weight_map[n] = fname
+                total += host.numel() * host.element_size()
+    if len(shards) > 1:
+        with open(os.path.join(save_directory, "model.safetensors.index.json"), "w") as f:
+            json.dump({"metadata": {"total_size": total}, "weight_map": weight_map}, f, indent=2)
+    cfg = dict(config or {})
+    cfg["quantization_config"] = quantization_config
+    with open(os.path.join(save_directory, "config.json"), "w") as f:
+        json.dump(cfg, f, indent=2)
+    return {"files": len(shards), "tensors": len(entries), "bytes": total}

@@ -328,3 +328,34 @@ def test_oneshot_nvfp4_input_global_scales():
         got = sd[f"{n}.input_global_scale"]
         assert got.dtype == torch.float32 and got.numel() == 1 and got.item() == want.item(), n
     assert "lm_head.input_global_scale" not in sd
+
+
+def test_save_compressed_roundtrip(tmp_path):
+    """oneshot -> save_compressed -> files load with the safetensors package: compressed tensors in place of the quantized
+    weights, untouched parameters as they were, sharded index and quantization_config present."""
+    import json
+    import os
+
+    st = pytest.importorskip("safetensors")
+    from quantizers_b200.oneshot import oneshot, save_compressed
+
+    m = _model(13)
+    sd, cfg = oneshot(m, NVFP4_RECIPE)
+    info = save_compressed(m, sd, cfg, str(tmp_path), config={"architectures": ["TinyLM"]}, max_shard_bytes=200_000)
+    assert info["files"] > 1
+    got = {}
+    for f in os.listdir(tmp_path):
+        if f.endswith(".safetensors"):
+            with st.safe_open(os.path.join(tmp_path, f), framework="pt") as h:
+                for k in h.keys():
+                    got[k] = h.get_tensor(k)
+    idx = json.load(open(tmp_path / "model.safetensors.index.json"))
+    assert set(idx["weight_map"]) == set(got)
+    for k, v in sd.items():
+        a, b = got[k], v.cpu()
+        assert a.dtype == b.dtype and torch.equal(a.view(torch.uint8), b.contiguous().view(torch.uint8)), k
+    assert "model.layers.0.self_attn.q_proj.weight" not in got and "model.layers.0.self_attn.q_proj.weight_packed" in got
+    assert torch.equal(got["lm_head.weight"], m.lm_head.weight.detach().cpu())
+    assert torch.equal(got["model.layers.1.input_layernorm.weight"], m.model.layers[1].input_layernorm.weight.detach().cpu())
+    c = json.load(open(tmp_path / "config.json"))
+    assert c["architectures"] == ["TinyLM"] and c["quantization_config"]["format"] == "nvfp4-pack-quantized"
