@@ -217,6 +217,12 @@ int b200q_awq_gemm_project_grouped(const void* x, int64_t tokens, int64_t k, con
 int b200q_moe_combine(const void* y, const int32_t* row, const void* weight, int64_t tokens, int32_t top_k, int64_t hidden, void* out,
                       void* stream);
 
+/* SURVEY.md §8f rank 4 -- GPTQ Hessian accumulation (LLMC modifiers/gptq: accumulate_hessian; the reference's GPTQ recipes,
+ * /root/reference/scripts/old_scripts/main_glm4-gptq.py:108-126): hessian fp32 [features, features] = alpha * hessian + beta * X^T X
+ * on the tensor cores (tcgen05, fp32 accumulate, fp32 read-modify-write epilogue).  xt: T = bf16 X^T [features, tokens], contiguous
+ * (tokens % 8 == 0).  With n the running sample count: alpha = n / (n + tokens), beta = 2 / (n + tokens). */
+int b200q_gptq_hessian_accumulate(const void* xt, int64_t features, int64_t tokens, float alpha, float beta, float* hessian, void* stream);
+
 /* W2, attention parent (input_layernorm -> q/k/v mapping; transformers Qwen3Attention.forward between the projections and
  * SDPA): in-place per-head RMSNorm (weights T [head_dim]) + rotary embedding of the q and k columns of
  * qkv T [tokens, (n_heads + 2 n_kv) * head_dim]; position = token index % seq_len; cos/sin T [seq_len, head_dim].  bf16 only. */

@@ -96,6 +96,18 @@ def mse_minmax(w: torch.Tensor, geom: O.Geom, qtype: int, num_bits: int, symmetr
     return bmn, bmx
 
 
+def accumulate_hessian(x: torch.Tensor, hessian: torch.Tensor, num_samples: int):
+    """modifiers/gptq ``accumulate_hessian``: H *= n/(n+t); n += t; inp = sqrt(2/n) * x.float().T; H += inp @ inp.T  (fp32)."""
+    import math
+
+    inp = x.reshape(-1, x.shape[-1]).t()
+    t = inp.shape[1]
+    hessian = hessian * (num_samples / (num_samples + t))
+    num_samples += t
+    inp = inp.to(torch.float32) * math.sqrt(2 / num_samples)
+    return hessian + inp.matmul(inp.t()), num_samples
+
+
 # ----------------------------------------------------------------------------- AWQ (O5, W1-W5)
 def accumulate_abs_mean(batches: Sequence[torch.Tensor]):
     """_accumulate_mean: per-input-channel mean of |x| over all tokens (running sum / count)."""

@@ -245,6 +245,7 @@ struct ProjParams {
     // grouped mode (MoE experts): non-null -> one weight variant PER M TILE (tile_variant[mt] = expert owning the tile's rows, < 0 =
     // padding tile, skipped) and a single [tokens, n_out] output; the rows of an expert are padded to whole tiles by the caller
     const int32_t* tile_variant;
+    float alpha, beta;  // EPI_F32_ACC: out(fp32) = alpha * out + beta * acc
 };
 
 // grouped rasterisation: consecutive items cover group_m m-tiles x all n-tiles column by column, so one wave of 148
@@ -266,9 +267,12 @@ __device__ __forceinline__ void decode_item(const ProjParams& p, int item, int& 
 __device__ __forceinline__ float silu_f32(float x) { return __fdiv_rn(x, __fadd_rn(1.0f, expf(-x))); }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-template <bool SWIGLU>
+enum : int { EPI_BF16 = 0, EPI_SWIGLU = 1, EPI_F32_ACC = 2 };
+
+template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 awq_gemm_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ProjParams p) {
+    constexpr bool SWIGLU = EPI == EPI_SWIGLU;
     constexpr int TN = SWIGLU ? BN / 2 : BN;  // output columns per tile
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -362,6 +366,15 @@ awq_gemm_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             for (int c = 0; c < TN / 32; c++) {
                 uint32_t g[32], o[16];
                 tc_ld32(t_lane + c * 32, g);
+                if (EPI == EPI_F32_ACC) {  // fp32 read-modify-write of the caller's matrix (GPTQ Hessian accumulation)
+                    if (row < p.tokens) {
+                        float* hrow = reinterpret_cast<float*>(p.out) + (size_t)row * (size_t)p.n_out + col0 + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (col0 + c * 32 + j < p.n_out) hrow[j] = __fmaf_rn(p.alpha, hrow[j], __fmul_rn(p.beta, __uint_as_float(g[j])));
+                    }
+                    continue;
+                }
                 if (SWIGLU) {
                     uint32_t u[32];
                     tc_ld32(t_lane + TN + c * 32, u);
@@ -501,7 +514,7 @@ int b200q_awq_gemm_loss(const void* x, int64_t tokens, int64_t k, const void* w_
 }
 
 static int gemm_project_impl(const void* x, int64_t tokens, int64_t k, const void* w, int64_t n_variants, int64_t n_out, int32_t swiglu,
-                             const void* tile_variant, void* out, void* stream) {
+                             const void* tile_variant, void* out, void* stream, int epi_f32 = 0, float alpha = 0.0f, float beta = 1.0f) {
     B200Q_REQUIRE(x && w && out, "b200q_awq_gemm_project: NULL pointer");
     B200Q_REQUIRE(k % 8 == 0 && k >= 8, "K must be a multiple of 8 (16-byte rows for the tensor maps), got %lld", (long long)k);
     B200Q_REQUIRE(n_out % 8 == 0, "n_out must be a multiple of 8 (16-byte output vectors), got %lld", (long long)n_out);
@@ -525,15 +538,20 @@ static int gemm_project_impl(const void* x, int64_t tokens, int64_t k, const voi
     p.up_row_offset = (int)n_out;
     p.out = (uint16_t*)out;
     p.tile_variant = (const int32_t*)tile_variant;
+    p.alpha = alpha;
+    p.beta = beta;
     const int64_t items = (int64_t)(tile_variant ? 1 : p.n_variants) * p.n_m_tiles * p.n_n_tiles;
     B200Q_REQUIRE(items < (1ll << 31), "too many tiles");
     const int grid = (int)min((int64_t)kNumSMs, items);
-    if (swiglu) {
-        cudaFuncSetAttribute(awq_gemm_project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
-        awq_gemm_project_kernel<true><<<grid, kThreads, kGemmSmem, st>>>(mx, mw, p);
+    if (epi_f32) {
+        cudaFuncSetAttribute(awq_gemm_project_kernel<EPI_F32_ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+        awq_gemm_project_kernel<EPI_F32_ACC><<<grid, kThreads, kGemmSmem, st>>>(mx, mw, p);
+    } else if (swiglu) {
+        cudaFuncSetAttribute(awq_gemm_project_kernel<EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+        awq_gemm_project_kernel<EPI_SWIGLU><<<grid, kThreads, kGemmSmem, st>>>(mx, mw, p);
     } else {
-        cudaFuncSetAttribute(awq_gemm_project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
-        awq_gemm_project_kernel<false><<<grid, kThreads, kGemmSmem, st>>>(mx, mw, p);
+        cudaFuncSetAttribute(awq_gemm_project_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+        awq_gemm_project_kernel<EPI_BF16><<<grid, kThreads, kGemmSmem, st>>>(mx, mw, p);
     }
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
@@ -542,6 +560,13 @@ static int gemm_project_impl(const void* x, int64_t tokens, int64_t k, const voi
 int b200q_awq_gemm_project(const void* x, int64_t tokens, int64_t k, const void* w, int64_t n_variants, int64_t n_out, int32_t swiglu,
                            void* out, void* stream) {
     return gemm_project_impl(x, tokens, k, w, n_variants, n_out, swiglu, nullptr, out, stream);
+}
+
+int b200q_gptq_hessian_accumulate(const void* xt, int64_t features, int64_t tokens, float alpha, float beta, float* hessian, void* stream) {
+    B200Q_REQUIRE(hessian, "b200q_gptq_hessian_accumulate: NULL pointer");
+    B200Q_REQUIRE((((uintptr_t)hessian) & 15) == 0, "hessian must be 16-byte aligned");
+    // H = alpha * H + beta * (X^T X): both operands are X^T [features, tokens] (contraction over the tokens, which are contiguous)
+    return gemm_project_impl(xt, features, tokens, xt, 1, features, 0, nullptr, hessian, stream, 1, alpha, beta);
 }
 
 int b200q_awq_gemm_project_grouped(const void* x, int64_t tokens, int64_t k, const void* w, int64_t n_experts, int64_t n_out, int32_t swiglu,

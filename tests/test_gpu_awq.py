@@ -319,3 +319,24 @@ def test_search_moe_block_mapping_matches_oracle():
         assert max(abs(a - b) / b for a, b in zip(l, l_ref)) < 1e-3, [abs(a - b) / b for a, b in zip(l, l_ref)]
         assert r == r_ref
         assert torch.allclose(s, s_ref, rtol=1e-5)
+
+
+def test_gptq_hessian_accumulation():
+    """§8f rank 4: H = H n/(n+t) + (2/(n+t)) X^T X over three batches (one with a row count that is not a multiple of 8) on the
+    tcgen05 fp32-accumulate epilogue against the restated fp32 reference.  Floating point: 2e-5 of max|H| (fp32 summation order)."""
+    from quantizers_b200 import gptq
+
+    g = torch.Generator().manual_seed(31)
+    K = 384
+    H = torch.zeros(K, K, dtype=torch.float32, device="cuda")
+    H_ref, n, n_ref = torch.zeros(K, K), 0, 0
+    for t in (512, 203, 1024):
+        x = (torch.randn(1, t, K, generator=g) * (1 + 3 * torch.rand(K, generator=g))).to(torch.bfloat16)
+        H, n = gptq.accumulate_hessian(x.cuda(), H, n)
+        H_ref, n_ref = R.accumulate_hessian(x, H_ref, n_ref)
+    assert n == n_ref == 1739
+    err = (H.cpu() - H_ref).abs().max().item() / H_ref.abs().max().item()
+    assert err < 2e-5, err
+    assert torch.allclose(H.cpu(), H.cpu().t(), rtol=0, atol=2e-5 * H_ref.abs().max().item())
+    with pytest.raises(ValueError):
+        gptq.accumulate_hessian(torch.zeros(4, K, device="cuda"), H, n)
