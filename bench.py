@@ -558,7 +558,8 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": f"group_kernel<bf16,{dom}> (fused observe+qparams+quantize+pack)",
+                "kernel": ("group_tma_kernel<INT4, asym, g128> (TMA-staged fused observe+qparams+quantize+pack)" if dom == "W4A16_ASYM"
+                           else f"fused compress kernel of {dom}"),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
                 "alg_bytes_per_element": dargs.bytes_per_element(), "avg_launch_ms": per[dom]["ms"] / per[dom]["n"],
                 "per_class": {k: {"GBps_bf16_in": v["elems"] * 2 / (v["ms"] * 1e-3) / 1e9,
