@@ -177,7 +177,38 @@ def run_e2e(spec, arena, steps, warmup, device_index):
     from quantizers_b200 import ops
     from quantizers_b200.scheduler import PRESETS
 
+    from quantizers_b200 import numa
+
     lib = L.lib()
+    jobs = []
+    h2d = d2h = 0
+    max_bytes = 0
+    # pinned staging buffers on the GPU's own NUMA node (first touch happens inside the allocation): with 8 ranks the far-socket
+    # hop, not PCIe, is what limits the host pipeline otherwise
+    with numa.near_device(device_index) as bound:
+        jobs, h2d, d2h, max_bytes = _e2e_buffers(spec, arena, ops, PRESETS)
+    handle = ctypes.c_void_p()
+    L.check(lib.b200q_pipeline_create(ctypes.byref(handle), max_bytes, device_index))
+
+    def step():
+        for hw, rows, cols, sc, codes, scale, zp in jobs:
+            L.check(lib.b200q_pipeline_compress_host(handle, L.ptr(hw), 1, rows, cols, ctypes.byref(sc), L.ptr(codes), L.ptr(scale),
+                                                     L.ptr(zp), None))
+        L.check(lib.b200q_pipeline_sync(handle))
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    lib.b200q_pipeline_destroy(handle)
+    return h2d * steps / dt / 1e9, h2d, d2h, dt, bound
+
+
+def _e2e_buffers(spec, arena, ops, PRESETS):
     jobs = []
     h2d = d2h = 0
     max_bytes = 0
@@ -201,25 +232,7 @@ def run_e2e(spec, arena, steps, warmup, device_index):
             jobs.append((hw[i], rows, cols, sc, codes[i], scale[i], None if zp is None else zp[i]))
             h2d += hw[i].numel() * 2
             d2h += codes[i].numel() * codes.element_size() + scale[i].numel() * 2 + (0 if zp is None else zp[i].numel() * 4)
-    handle = ctypes.c_void_p()
-    L.check(lib.b200q_pipeline_create(ctypes.byref(handle), max_bytes, device_index))
-
-    def step():
-        for hw, rows, cols, sc, codes, scale, zp in jobs:
-            L.check(lib.b200q_pipeline_compress_host(handle, L.ptr(hw), 1, rows, cols, ctypes.byref(sc), L.ptr(codes), L.ptr(scale),
-                                                     L.ptr(zp), None))
-        L.check(lib.b200q_pipeline_sync(handle))
-
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    lib.b200q_pipeline_destroy(handle)
-    return h2d * steps / dt / 1e9, h2d, d2h, dt
+    return jobs, h2d, d2h, max_bytes
 
 
 # ----------------------------------------------------------------------------- AWQ search leg (BASELINE.json metric part 2)
@@ -578,7 +591,7 @@ def main():
     del out
 
     # ---- e2e through the host pipeline (same metric, host buffers, copies in the timed region)
-    e2e_v, h2d, d2h, _ = run_e2e(spec, arena, args.e2e_steps, 1, local)
+    e2e_v, h2d, d2h, _, numa_bound = run_e2e(spec, arena, args.e2e_steps, 1, local)
     ev = torch.tensor([e2e_v], device=dev)
     if world > 1:
         dist.all_reduce(ev, op=dist.ReduceOp.MIN)  # slowest rank bounds the job
@@ -606,7 +619,8 @@ def main():
                    "layers_per_gpu": spec.units, "matrices_per_step": 7 * spec.units, "bytes_per_step_per_gpu": step_bytes,
                    "l2": "inputs (7.27 GB/step) far larger than the 126 MB L2; no flush needed", "parallelism": f"layer-sharded x{world}"},
         "roofline": roofline,
-        "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
+        "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+                "host_buffers": "pinned, on the GPU's NUMA node" if numa_bound else "pinned"},
         "gpu_launches": S.launches_per_step(spec) * args.steps,
         "clocks": sampler.summary() if rank == 0 else None,
     }

@@ -33,7 +33,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from . import ops
+from . import numa, ops
 from .recipe import match_name, preset_args
 from .scheduler import SchemeArgs
 
@@ -141,7 +141,8 @@ class _Worker:
         # one pinned arena per worker (a single cudaHostAlloc: page-locking is the expensive part of start-up), carved into the rings
         sizes = [max_weight_bytes, max_weight_bytes // 2 + 256, max_weight_bytes // 16 + 4096, max_weight_bytes // 64 + 4096, 16]
         sizes = [(n + 255) // 256 * 256 for n in sizes]
-        self._arena = torch.empty(self.RING * sum(sizes), dtype=torch.uint8, pin_memory=True)
+        with numa.near_device(device_index):  # first touch on the GPU's own NUMA node
+            self._arena = torch.empty(self.RING * sum(sizes), dtype=torch.uint8, pin_memory=True)
         off = 0
         rings = []
         for n in sizes:
