@@ -304,9 +304,16 @@ def awq_model(model: torch.nn.Module, recipe: Union[str, dict, Recipe], calibrat
 
 
 def oneshot(model: torch.nn.Module, recipe: Union[str, dict, Recipe], dataset: Optional[Sequence] = None,
-            forward: Optional[Callable] = None, **_ignored) -> Tuple[Dict[str, torch.Tensor], dict]:
+            forward: Optional[Callable] = None, moe_calibrate_all_experts: bool = False, **_ignored) -> Tuple[Dict[str, torch.Tensor], dict]:
     """``llmcompressor.oneshot``-shaped entry (REF:scripts/do_oneshot.py:179-187): applies every modifier of the recipe in order
-    and returns (compressed state dict, quantization_config).  ``dataset`` = calibration batches (needed by AWQModifier)."""
+    and returns (compressed state dict, quantization_config).  ``dataset`` = calibration batches (needed by AWQModifier).
+    ``moe_calibrate_all_experts`` (REF:scripts/do_oneshot.py:186): sparse MoE blocks get per-expert Linears and, while the
+    modifiers run, every expert sees every calibration token (``moe_calibration.moe_calibrate_all_experts``)."""
+    if moe_calibrate_all_experts:
+        from .moe_calibration import moe_calibrate_all_experts as _ctx
+
+        with _ctx(model):
+            return oneshot(model, recipe, dataset, forward, moe_calibrate_all_experts=False)
     rec = _as_recipe(recipe)
     sd: Dict[str, torch.Tensor] = {}
     cfgs = []

@@ -359,3 +359,176 @@ def test_save_compressed_roundtrip(tmp_path):
     assert torch.equal(got["model.layers.1.input_layernorm.weight"], m.model.layers[1].input_layernorm.weight.detach().cpu())
     c = json.load(open(tmp_path / "config.json"))
     assert c["architectures"] == ["TinyLM"] and c["quantization_config"]["format"] == "nvfp4-pack-quantized"
+
+
+# ----------------------------------------------------------------------------- CompressedLinear: run from the compressed tensors
+MIXED_RTN_RECIPE = """
+default_stage:
+  default_modifiers:
+    QuantizationModifier:
+      config_groups:
+        attn:
+          targets: ["re:.*self_attn\\\\.(q|k|v|o)_proj$"]
+          weights: {num_bits: 8, type: float, symmetric: true, strategy: block, block_structure: [128, 128], observer: memoryless_minmax}
+        mlp:
+          targets: ["re:.*mlp\\\\.(gate|up|down)_proj$"]
+          weights: {num_bits: 4, type: int, symmetric: false, group_size: 128, strategy: group, observer: memoryless_minmax}
+      ignore: ["lm_head"]
+"""
+
+
+def _oracle_fake_quantized(w, geom, qtype, bits, sym, gs=None):
+    mn, mx = O.minmax(w, geom)
+    scale, zp = O.calculate_qparams(mn, mx, qtype, bits, sym, gs)
+    if gs is not None:
+        scale = scale.to(torch.float8_e4m3fn)
+    zp = None if sym and qtype == O.INT else zp
+    fq = O.fake_quantize(w, scale, zp, geom, qtype, bits, gs)
+    if qtype != O.INT:
+        return fq
+    # integer codes cannot carry the sign of a zero: fake_quantize keeps round(-0.3) = -0.0 through (q - 0) * s, the decode of
+    # the stored code 0 gives +0.0 -- equal as numbers, different as bits (live CT behaves the same way)
+    dq = O.dequantize(O.quantize(w, scale, zp, geom, qtype, bits), scale, zp, geom, qtype)
+    assert torch.equal(dq, fq)
+    return dq
+
+
+@pytest.mark.parametrize("recipe", ["mixed", "nvfp4"])
+def test_compressed_linear_decodes_to_fake_quantized_weight(recipe):
+    """oneshot -> apply_compressed: every swapped Linear decodes (per forward call) to exactly fake_quantize(original weight), so
+    the model output equals the output of the dense model carrying the oracle's fake-quantized weights."""
+    import copy
+
+    from quantizers_b200.compressed_linear import CompressedLinear, apply_compressed
+    from quantizers_b200.oneshot import oneshot
+
+    m = _model(9)
+    dense = copy.deepcopy(m)
+    text = MIXED_RTN_RECIPE if recipe == "mixed" else NVFP4_RECIPE
+    sd, _ = oneshot(m, text)
+    swapped = apply_compressed(m, text, sd)
+    assert len(swapped) == 14 and "lm_head" not in swapped
+    mods, dmods = dict(m.named_modules()), dict(dense.named_modules())
+    for name in swapped:
+        cl = mods[name]
+        assert isinstance(cl, CompressedLinear)
+        w = dmods[name].weight.detach().cpu()
+        if recipe == "nvfp4":
+            gs = sd[f"{name}.weight_global_scale"].reshape(1).cpu()
+            want = _oracle_fake_quantized(w, O.Geom(O.GROUP, 16), O.FP4, 4, True, gs)
+        elif "self_attn" in name:
+            want = _oracle_fake_quantized(w, O.Geom(O.BLOCK, 0, 128, 128), O.FP8, 8, True)
+        else:
+            want = _oracle_fake_quantized(w, O.Geom(O.GROUP, 128), O.INT, 4, False)
+        assert_bits_equal(cl.decompressed_weight(), want, name)
+        dmods[name].weight.data.copy_(want.cuda())
+    x = _batches(n=1, S=32, seed=3)[0]
+    with torch.no_grad():
+        assert_bits_equal(m(x), dense(x), "forward from compressed tensors")
+    # the dense weights are gone: only compressed buffers remain on the swapped modules
+    kept = sum(b.numel() * b.element_size() for n in swapped for b in mods[n].buffers())
+    full = sum(dmods[n].weight.numel() * 2 for n in swapped)
+    assert kept < 0.6 * full
+
+
+def test_compressed_linear_rejects_bad_entries():
+    from quantizers_b200.compressed_linear import CompressedLinear
+    from quantizers_b200.scheduler import PRESETS
+
+    with pytest.raises(ValueError):
+        CompressedLinear({"weight_scale": torch.zeros(1)}, PRESETS["W4A16"], 8, 8)
+    with pytest.raises(ValueError):
+        CompressedLinear({"weight_packed": torch.zeros(1), "weight_scale": torch.zeros(1), "bogus": torch.zeros(1)}, PRESETS["W4A16"], 8, 8)
+
+
+# ----------------------------------------------------------------------------- moe_calibrate_all_experts through oneshot
+HF_MOE_RECIPE = """
+default_stage:
+  default_modifiers:
+    AWQModifier:
+      config_groups:
+        experts:
+          targets: ["re:.*mlp\\\\.experts\\\\.\\\\d+\\\\.(gate|up|down)_proj$"]
+          weights: {num_bits: 4, type: int, symmetric: true, group_size: 32, strategy: group, dynamic: false, observer: memoryless_minmax}
+      mappings:
+        - smooth_layer: re:.*up_proj$
+          balance_layers: ["re:.*down_proj$"]
+      duo_scaling: true
+"""
+
+
+def test_oneshot_moe_calibrate_all_experts_on_fused_experts():
+    """transformers' Qwen3-MoE block stores its experts as fused 3-D parameters: invisible to Linear targets
+    (REF:docs/quantization_tips_and_tricks.md:77-80).  With ``moe_calibrate_all_experts=True`` (REF:scripts/do_oneshot.py:186) the
+    block is linearized, every expert's up -> down mapping is searched on ALL calibration tokens, and the result matches the
+    restated search on those inputs."""
+    qm = pytest.importorskip("transformers.models.qwen3_moe.modeling_qwen3_moe")
+    from transformers import Qwen3MoeConfig
+
+    from quantizers_b200 import recipe as RC
+    from quantizers_b200.oneshot import awq_model
+    from quantizers_b200.moe_calibration import moe_calibrate_all_experts
+
+    Hh, Ii, E = 128, 128, 4
+    cfg = Qwen3MoeConfig(hidden_size=Hh, moe_intermediate_size=Ii, num_experts=E, num_experts_per_tok=2, norm_topk_prob=True,
+                         num_hidden_layers=1, num_attention_heads=2, num_key_value_heads=2, vocab_size=32)
+
+    class Layer(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.post_attention_layernorm = torch.nn.LayerNorm(Hh)
+            self.mlp = qm.Qwen3MoeSparseMoeBlock(cfg)
+
+        def forward(self, x):
+            y = self.mlp(self.post_attention_layernorm(x))
+            return x + (y[0] if isinstance(y, tuple) else y)
+
+    class LM(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = torch.nn.Module()
+            self.model.layers = torch.nn.ModuleList([Layer()])
+
+        def forward(self, x):
+            return self.model.layers[0](x)
+
+    torch.manual_seed(21)
+    m = LM()
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.ndim >= 2:
+                p.normal_(0, 0.06)
+        m.model.layers[0].mlp.gate.weight.normal_(0, 1.0)
+    m = m.to(torch.bfloat16).cuda()
+    g = torch.Generator().manual_seed(2)
+    batches = [(torch.randn(1, 80, Hh, generator=g)).to(torch.bfloat16).cuda() for _ in range(3)]
+    rec = RC.parse_recipe(HF_MOE_RECIPE)
+    sd0, _, res0 = awq_model(m, rec, batches)            # fused experts: nothing for the recipe to bind to
+    assert not sd0 and not res0
+    with torch.no_grad():
+        before = m(batches[0]).clone()
+    with moe_calibrate_all_experts(m) as names:
+        assert names == ["model.layers.0.mlp"]
+        with torch.no_grad():
+            assert torch.allclose(m(batches[0]).float(), before.float(), rtol=2e-2, atol=2e-2)
+        pre = "model.layers.0.mlp.experts"
+        seen = {e: [] for e in range(E)}
+        hooks = [m.get_submodule(f"{pre}.{e}.down_proj").register_forward_pre_hook(lambda mod, a, e=e: seen[e].append(a[0].detach().cpu()))
+                 for e in range(E)]
+        with torch.no_grad():
+            for b in batches:
+                m(b)
+        for h in hooks:
+            h.remove()
+        w0 = {e: m.get_submodule(f"{pre}.{e}.down_proj").weight.detach().cpu().clone() for e in range(E)}
+        sd, qcfg, results = awq_model(m, rec, batches)
+    assert len(results) == E
+    for e in range(E):
+        x = torch.cat(seen[e])
+        assert x.shape[0] == 3 * 80                       # every expert saw every token
+        s_ref, r_ref, l_ref = R.compute_best_scale([x], [w0[e]], R.linear_parent, O.Geom(O.GROUP, 32), O.INT, 4, True)
+        s, r, losses = results[f"{pre}.{e}.up_proj -> {pre}.{e}.down_proj"]
+        assert r == r_ref and max(abs(a - b) / b for a, b in zip(losses, l_ref)) < 1e-3
+        assert torch.allclose(s, s_ref, rtol=1e-5)
+        for p in ("gate_proj", "up_proj", "down_proj"):
+            assert f"{pre}.{e}.{p}.weight_packed" in sd
