@@ -70,6 +70,10 @@ int b200q_compress_int_packed(const void* weight, int64_t batch, int64_t rows, i
         TileParams p{};
         p.w = weight; p.rows = rows; p.cols = cols; p.nbits = sc->num_bits; p.symmetric = sc->symmetric; p.has_zp = 1;
         p.scale = scale; p.zp_packed = zp_packed; p.out = packed;
+        if (sc->dtype == B200Q_BF16 && fast_paths_enabled()) {
+            const int rc = launch_channel_fast(QT_INT, p, batch, st);
+            if (rc != B200Q_ENOSYS) return rc;
+        }
         return launch_channel_compress(sc->dtype, QT_INT, p, batch, st);
     }
     set_error("pack-quantized fused compress supports GROUP and CHANNEL strategies (got %d)", sc->strategy);
@@ -96,7 +100,13 @@ int b200q_compress_fp8(const void* weight, int64_t batch, int64_t rows, int64_t 
     TileParams p{};
     p.w = weight; p.rows = rows; p.cols = cols; p.nbits = 8; p.symmetric = 1; p.has_zp = sc->has_zp; p.scale = scale;
     p.out = q; p.workspace = (float*)workspace;
-    if (sc->strategy == B200Q_CHANNEL) return launch_channel_compress(sc->dtype, QT_FP8, p, batch, st);
+    if (sc->strategy == B200Q_CHANNEL) {
+        if (sc->dtype == B200Q_BF16 && fast_paths_enabled()) {
+            const int rc = launch_channel_fast(QT_FP8, p, batch, st);
+            if (rc != B200Q_ENOSYS) return rc;
+        }
+        return launch_channel_compress(sc->dtype, QT_FP8, p, batch, st);
+    }
     if (sc->strategy == B200Q_BLOCK) {
         B200Q_REQUIRE(sc->block_h == 128 && sc->block_w == 128, "fused block compress supports block_structure [128,128], got [%d,%d]",
                       sc->block_h, sc->block_w);

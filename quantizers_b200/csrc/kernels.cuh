@@ -86,6 +86,8 @@ struct TileParams {
     float* workspace;     // TENSOR: fp32 absmax bits per batch
 };
 int launch_channel_compress(int dt, int qt, const TileParams& p, int64_t batch, cudaStream_t st);
+// bf16 issue-tuned CHANNEL compress (quant_channel_fast.cu): FP8 and INT4; B200Q_ENOSYS when the shape is not covered
+int launch_channel_fast(int qt, const TileParams& p, int64_t batch, cudaStream_t st);
 int launch_block_fp8_compress(int dt, const TileParams& p, int64_t batch, cudaStream_t st);
 int launch_tensor_fp8_compress(int dt, const TileParams& p, int64_t batch, cudaStream_t st);
 

@@ -1,0 +1,209 @@
+// quant_channel_fast.cu -- issue-tuned bf16 CHANNEL (one scale per row) fused compress: FP8 float-quantized (the FP8_DYNAMIC
+// preset's weights, CT:quantization/quant_scheme.py:367-382) and INT4 pack-quantized, symmetric or asymmetric.
+//
+// The generic kernel (quant_tile.cu) spends one 256-thread CTA, four block-wide barriers and an IEEE division per element on a
+// row; measured 0.23 of the HBM roofline on 2560-column rows.  Here a row belongs to a TEAM of TW warps (1, 2, 4 or 8, picked so
+// that the row fits the team's registers: 8 x 128-bit loads per lane = 2048 elements per warp), a CTA carries 8 / TW rows, and
+// the row stays in registers between the statistics and the conversion -> one HBM read, one barrier (none when TW == 1).  The
+// arithmetic is the same bit-exact chain as every other bf16 fast kernel: bracketed reciprocal (fastmath.cuh) with the IEEE
+// repair for the rare element whose bracket ends disagree, qparams as in quant_group_tma.cu.
+#include "common.cuh"
+#include "fastmath.cuh"
+#include "fp4.cuh"
+#include "kernels.cuh"
+
+namespace b200q {
+namespace {
+using namespace fast;
+using fp4::cvt_e4m3x2;
+
+constexpr int NC = 8;  // 16-byte chunks per lane
+
+template <int QT, bool SYM>
+__device__ __noinline__ uint2 repair_row_chunk(const uint4 raw, float s, float z, bool add_zp, bool all, uint2 packed) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    Bracket br;
+    br.init(s);
+    float rl, rh, dummy;
+    unpack2(br.lo, rl, dummy);
+    unpack2(br.hi, rh, dummy);
+    uint32_t o[2] = {packed.x, packed.y};
+#pragma unroll 1
+    for (int e = 0; e < 8; e++) {
+        const uint32_t half = (e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16);
+        const float x = __uint_as_float(half);
+        const bool differ = __float2bfloat16_rn(__fmul_rn(x, rl)) != __float2bfloat16_rn(__fmul_rn(x, rh));
+        if (all || differ) {
+            if (QT == QT_INT) {
+                const uint32_t c = (uint32_t)(quant_int<DT_BF16>(x, s, z, !SYM, -8.0f, 7.0f) + 8) & 0xfu;
+                o[0] = (o[0] & ~(0xfu << (4 * e))) | (c << (4 * e));
+            } else {
+                const uint32_t c = quant_fp8<DT_BF16>(x, s, add_zp);
+                o[e >> 2] = (o[e >> 2] & ~(0xffu << (8 * (e & 3)))) | (c << (8 * (e & 3)));
+            }
+        }
+    }
+    return make_uint2(o[0], o[1]);
+}
+
+template <int QT, bool SYM, int TW>
+__global__ void __launch_bounds__(256, 4) channel_fast_kernel(const TileParams p, const int64_t total_rows) {
+    constexpr int RPC = 8 / TW;  // rows per CTA
+    constexpr int TL = TW * 32;  // lanes per team
+    constexpr bool ABS = (QT == QT_FP8) || SYM;
+    __shared__ uint32_t sm_a[8], sm_b[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int team = warp / TW, tl = (warp % TW) * 32 + lane;
+    const int64_t row = (int64_t)blockIdx.x * RPC + team;
+    const bool live = row < total_rows;
+    const int nch = (int)(p.cols >> 3);
+    const char* src = (const char*)p.w + row * p.cols * 2;
+    uint4 raw[NC];
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        const int c = j * TL + tl;
+        raw[j] = (live && c < nch) ? ldg_stream(src + (int64_t)c * 16) : make_uint4(0, 0, 0, 0);
+    }
+    // ---- A. row statistics.  Zero padding is neutral for |max|, for max(max, 0) and for min(min, 0).
+    uint32_t st_a = 0, st_b = 0;
+    if (ABS) {
+#pragma unroll
+        for (int j = 0; j < NC; j++) st_a = hmaxabs2(st_a, hmaxabs2(hmaxabs2(raw[j].x, raw[j].y), hmaxabs2(raw[j].z, raw[j].w)));
+        st_a = hmaxabs2(st_a, prmt(st_a, st_a, 0x1032));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) st_a = hmaxabs2(st_a, __shfl_xor_sync(0xffffffffu, st_a, o));
+    } else {
+        // max(max, 0) as the s16 maximum with RELU, min(min, 0) as the u16 maximum of the raw bits (quant_group_tma.cu)
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            st_a = __vimax3_s16x2_relu(__vimax3_s16x2_relu(raw[j].x, raw[j].y, raw[j].z), raw[j].w, st_a);
+            st_b = __vimax3_u16x2(__vimax3_u16x2(raw[j].x, raw[j].y, raw[j].z), raw[j].w, st_b);
+        }
+        st_a = __vmaxs2(st_a, prmt(st_a, st_a, 0x1032));
+        st_b = __vmaxu2(st_b, prmt(st_b, st_b, 0x1032));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st_a = __vmaxs2(st_a, __shfl_xor_sync(0xffffffffu, st_a, o));
+            st_b = __vmaxu2(st_b, __shfl_xor_sync(0xffffffffu, st_b, o));
+        }
+    }
+    if (TW > 1) {
+        if (lane == 0) { sm_a[warp] = st_a; sm_b[warp] = st_b; }
+        __syncthreads();
+        st_a = sm_a[team * TW];
+        st_b = sm_b[team * TW];
+#pragma unroll
+        for (int i = 1; i < TW; i++) {
+            if (ABS) st_a = hmaxabs2(st_a, sm_a[team * TW + i]);
+            else { st_a = __vmaxs2(st_a, sm_a[team * TW + i]); st_b = __vmaxu2(st_b, sm_b[team * TW + i]); }
+        }
+    }
+    if (!live) return;
+    if (!ABS && (st_b & 0x8000u) == 0) st_b = 0;  // no negative element: min(min, 0) = 0
+    // ---- B. qparams (same rounding chain as qmath.cuh)
+    float s, z = 0.0f;
+    Bracket br;
+    if (ABS) {
+        s = div_const_bf16(__uint_as_float((st_a << 16) & 0x7fff0000u), QT == QT_INT ? 7.5f : 448.0f);
+        if (s == 0.0f) s = eps_of<DT_BF16>();
+        br.init(s);
+    } else {
+        const float mn = fminf(__uint_as_float(st_b << 16), 0.0f), mx = fmaxf(__uint_as_float(st_a << 16), 0.0f);
+        const float d = round_to<DT_BF16>(__fadd_rn(mx, -mn));
+        const float s0 = div_const_bf16(d, 15.0f);
+        br.init(s0);
+        float t;
+        {
+            float rl, rh, dummy;
+            unpack2(br.lo, rl, dummy);
+            unpack2(br.hi, rh, dummy);
+            const uint32_t u = cvt_bf16x2(__fmul_rn(mn, rh), __fmul_rn(mn, rl));
+            if (((u >> 16) == (u & 0xffffu)) && scale_is_safe(__float_as_uint(s0))) t = __uint_as_float(u << 16);
+            else t = round_to<DT_BF16>(__fdiv_rn(mn, s0));
+        }
+        z = round_to<DT_BF16>(__fadd_rn(-8.0f, -t));
+        z = (z == z) ? rintf(fminf(fmaxf(z, -8.0f), 7.0f)) : 0.0f;
+        s = s0;
+        if (s0 == 0.0f) { s = eps_of<DT_BF16>(); br.init(s); }
+    }
+    if (tl == 0) {
+        ((uint16_t*)p.scale)[row] = (uint16_t)(__float_as_uint(s) >> 16);
+        if (QT == QT_INT && !SYM) {  // pack_to_int32(zero_point, packed_dim=0): nibble (r % 8) of word (r / 8) of this matrix
+            const int64_t b = row / p.rows, r = row - b * p.rows;
+            atomicOr((unsigned int*)&p.zp_packed[b * ((p.rows + 7) >> 3) + (r >> 3)], ((uint32_t)((int)z + 8) & 0xfu) << (4 * (int)(r & 7)));
+        }
+    }
+    // ---- C. quantize + pack from the registers
+    const bool unsafe = !scale_is_safe(__float_as_uint(s));
+    const bool add_zp = (QT == QT_FP8) ? (p.has_zp != 0) : true;
+    const uint32_t z2 = (__float_as_uint(z) >> 16) * 0x10001u;
+    const uint32_t kMagic = 0x43484348u, kUnbias = 0xbcc0bcc0u;  // bf16x2 (200, 200) / s16x2 (-0x4340): RNE, clamp [-8, 7], + 8
+    uint8_t* out_row = (uint8_t*)p.out + (QT == QT_FP8 ? row * p.cols : row * (p.cols >> 1));
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        const int c = j * TL + tl;
+        if (c >= nch) continue;
+        const uint32_t w[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+        uint32_t h[4], diff = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const f32x2 x = bf16x2_to_f32x2_fma(w[k]);
+            float al, ah, bl, bh;
+            if (QT == QT_INT) {
+                unpack2(mul2(x, br.lo), al, ah);
+                unpack2(mul2(x, br.hi), bl, bh);
+                uint32_t u = cvt_bf16x2(ah, al);
+                diff |= u ^ cvt_bf16x2(bh, bl);
+                if (!SYM) u = hadd2(u, z2);
+                h[k] = __viaddmin_s16x2_relu(hadd2(u, kMagic), kUnbias, 0x000f000fu);
+            } else {
+                unpack2(add_zp ? mul2_plus0(x, br.lo) : mul2(x, br.lo), al, ah);
+                unpack2(add_zp ? mul2_plus0(x, br.hi) : mul2(x, br.hi), bl, bh);
+                const uint32_t u = cvt_bf16x2(ah, al);
+                diff |= u ^ cvt_bf16x2(bh, bl);
+                float ul, uh;
+                unpack2(bf16x2_to_f32x2_fma(u), ul, uh);
+                h[k] = cvt_e4m3x2(uh, ul);
+            }
+        }
+        uint2 packed;
+        if (QT == QT_INT) {
+            const uint32_t x01 = prmt(h[0], h[1], 0x6420), x23 = prmt(h[2], h[3], 0x6420);
+            packed = make_uint2(prmt(fold_nibbles(x01), fold_nibbles(x23), 0x6420), 0u);
+        } else {
+            packed = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+        }
+        if (diff != 0 || unsafe) packed = repair_row_chunk<QT, SYM>(raw[j], s, z, add_zp, unsafe, packed);
+        if (QT == QT_FP8) stg_stream(out_row + (int64_t)c * 8, packed);
+        else stg_stream(out_row + (int64_t)c * 4, packed.x);
+    }
+}
+
+template <int QT, bool SYM>
+int launch_rows(const TileParams& p, int64_t total_rows, cudaStream_t st) {
+    const int64_t cap = p.cols;
+    auto grid = [&](int rpc) { return (unsigned)((total_rows + rpc - 1) / rpc); };
+    if (cap <= 2048) channel_fast_kernel<QT, SYM, 1><<<grid(8), 256, 0, st>>>(p, total_rows);
+    else if (cap <= 4096) channel_fast_kernel<QT, SYM, 2><<<grid(4), 256, 0, st>>>(p, total_rows);
+    else if (cap <= 8192) channel_fast_kernel<QT, SYM, 4><<<grid(2), 256, 0, st>>>(p, total_rows);
+    else channel_fast_kernel<QT, SYM, 8><<<grid(1), 256, 0, st>>>(p, total_rows);
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+}  // namespace
+
+// bf16 only; FP8 or INT4.  Returns B200Q_ENOSYS when the scheme / shape is not covered (the generic kernel takes over).
+int launch_channel_fast(int qt, const TileParams& p, int64_t batch, cudaStream_t st) {
+    if (p.cols % 8 != 0 || p.cols > 8 * 2048 || (((uintptr_t)p.w) & 15) != 0 || (((uintptr_t)p.out) & 7) != 0) return B200Q_ENOSYS;
+    const int64_t total_rows = batch * p.rows;
+    if (total_rows * p.cols == 0 || total_rows >= (1ll << 31)) return B200Q_ENOSYS;
+    if (qt == QT_FP8) return launch_rows<QT_FP8, true>(p, total_rows, st);
+    if (qt != QT_INT || p.nbits != 4) return B200Q_ENOSYS;
+    if (p.symmetric) return launch_rows<QT_INT, true>(p, total_rows, st);
+    if (p.zp_packed == nullptr) return B200Q_ENOSYS;
+    cudaMemsetAsync(p.zp_packed, 0, sizeof(int32_t) * batch * ((p.rows + 7) / 8), st);
+    return launch_rows<QT_INT, false>(p, total_rows, st);
+}
+
+}  // namespace b200q

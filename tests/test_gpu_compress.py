@@ -290,6 +290,42 @@ def test_fast_int4_boundary_cases():
     _cmp_sd(got, want, "nvfp4 thresholds")
 
 
+@pytest.mark.parametrize("name", ["fp8_channel", "int4_channel_sym", "int4_channel_asym"])
+def test_fast_channel_kernel_team_sizes_and_boundaries(name):
+    """The bf16 CHANNEL kernel gives a row to a team of 1 / 2 / 4 / 8 warps depending on its length (rows longer than 16384
+    fall back to the generic kernel): every team size, ragged row counts (last CTA partly empty), stacked matrices (zero-point
+    words packed down the rows of EACH matrix), plus adversarial rows -- all bf16 magnitudes against scales from 1e-30 to 1e30,
+    all-zero / all-negative / all-positive rows, signed zeros."""
+    from quantizers_b200 import ops
+
+    fmt, qtype, nb, sym, strat, g, blk = FORMATS[name]
+    for R, C, seed in ((13, 2048, 1), (11, 2056, 2), (9, 4096, 3), (7, 4104, 4), (5, 8192, 5), (3, 8200, 6), (3, 16384, 7), (2, 16392, 8)):
+        w = synth_weight(R, C, torch.bfloat16, seed)
+        _cmp_sd(ops.compress_weight(w.cuda(), Args(name)), O.compress(w, fmt, geom_of(name), nb, sym), f"{name}/{R}x{C}")
+    # stacked launch: [3, 21, 2560] -> per-matrix results, zero-point rows do not bleed across matrices
+    ws = [synth_weight(21, 2560, torch.bfloat16, 40 + i) for i in range(3)]
+    got = ops.compress_weight(torch.stack(ws).cuda(), Args(name))
+    for i, w in enumerate(ws):
+        want = O.compress(w, fmt, geom_of(name), nb, sym)
+        for k, v in want.items():
+            if k != "weight_shape":
+                assert_bits_equal(got[k][i].reshape(v.shape), v, f"{name}: stacked[{i}].{k}")
+    allv = torch.arange(0x0001, 0x7F80, dtype=torch.int32).to(torch.int16).view(torch.bfloat16).float()
+    rows = []
+    for scale_max in (1.0, 0.0371, 7.5, 448.0, 3.0e-3, 1.0e30, 1.0e-30):
+        v = allv[(allv <= scale_max)][-(255 * 24):]
+        v = v[: (v.numel() // 255) * 255].reshape(-1, 255)
+        rows.append(torch.cat([torch.full((v.shape[0], 1), scale_max), v * torch.where(torch.arange(255) % 2 == 0, 1.0, -1.0)], dim=1))
+    special = torch.zeros(6, 256)
+    special[1] = -torch.rand(256) - 0.1            # all negative
+    special[2] = torch.rand(256) + 0.1             # all positive
+    special[3, ::2] = -0.0                         # signed zeros only
+    special[4, 5] = 3.0e38                         # one huge element
+    special[5, 7] = -1.0e-38                       # one subnormal-scale element
+    w = torch.cat(rows + [special]).to(torch.bfloat16)
+    _cmp_sd(ops.compress_weight(w.cuda(), Args(name)), O.compress(w, fmt, geom_of(name), nb, sym), f"{name}/adversarial")
+
+
 @pytest.mark.parametrize("name", ["int4_g128_asym", "int4_g32_sym", "int4_channel_asym", "int4_channel_sym", "int8_g128_sym", "nvfp4"])
 def test_fused_decompress_matches_two_step_oracle(name):
     """§8f rank 1: packed codes + qparams -> weights in one pass == the oracle's unpack followed by dequantize (which the CPU
