@@ -311,12 +311,22 @@ __global__ void __launch_bounds__(FP4_THREADS, 6) nvfp4_fused_kernel(const Group
     __shared__ uint32_t s_red[FP4_THREADS / 32];
     const int nblk = f.items_per_mat * f.span;                 // items per block
     const int S = f.n_spans, Lh = f.lookahead;
-    const int k = (int)(blockIdx.x / (unsigned)nblk), j = (int)(blockIdx.x - (unsigned)k * (unsigned)nblk);
+    // Launch order: |max| items of spans 0 .. Lh-1, then compress item j of span s and |max| item j of span s + Lh ALTERNATE item by
+    // item (the HBM-bound |max| pass and the ALU-bound compress pass are co-resident on every SM, and a compress CTA never finds
+    // its span incomplete: all |max| items of span s precede it), then the compress items of the last Lh spans.  Alternating
+    // whole spans instead serialises the two passes whenever Lh == 1 (spans of 20-100 MB: 0.58 -> see DESIGN.md).
+    const unsigned head = (unsigned)Lh * (unsigned)nblk, mid = (unsigned)(S - Lh) * 2u * (unsigned)nblk;
     bool is_b;
-    int s;
-    if (k < Lh) { is_b = false; s = k; }
-    else if (k >= 2 * S - Lh) { is_b = true; s = k - S; }
-    else { const int r = k - Lh; is_b = (r & 1) == 0; s = is_b ? r / 2 : Lh + r / 2; }
+    int s, j;
+    if (blockIdx.x < head) {
+        is_b = false; s = (int)(blockIdx.x / (unsigned)nblk); j = (int)(blockIdx.x - (unsigned)s * (unsigned)nblk);
+    } else if (blockIdx.x < head + mid) {
+        const unsigned b = blockIdx.x - head, pair = b / (2u * (unsigned)nblk), q = b - pair * 2u * (unsigned)nblk;
+        is_b = (q & 1u) == 0; j = (int)(q >> 1); s = is_b ? (int)pair : (int)pair + Lh;
+    } else {
+        const unsigned b = blockIdx.x - head - mid, t = b / (unsigned)nblk;
+        is_b = true; s = S - Lh + (int)t; j = (int)(b - t * (unsigned)nblk);
+    }
     const int mi = j / f.items_per_mat, item = j - mi * f.items_per_mat;
     const int64_t m = (int64_t)s * f.span + mi;
     const int tile0 = item * f.nt, tile1 = min(tile0 + f.nt, f.tiles_per_mat);
