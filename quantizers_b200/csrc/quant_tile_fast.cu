@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(FP4_THREADS, 6) nvfp4_flat_kernel(const GroupP
 struct Fp4FusedParams {
     int64_t groups_per_mat;
     int32_t tiles_per_mat, items_per_mat, span, n_spans, lookahead, nt;
+    int32_t by_item;  // alternate the two passes item by item instead of span by span
     uint32_t* sync;
     float* gs_out;  // [batch]
 };
@@ -311,10 +312,11 @@ __global__ void __launch_bounds__(FP4_THREADS, 6) nvfp4_fused_kernel(const Group
     __shared__ uint32_t s_red[FP4_THREADS / 32];
     const int nblk = f.items_per_mat * f.span;                 // items per block
     const int S = f.n_spans, Lh = f.lookahead;
-    // Launch order: |max| items of spans 0 .. Lh-1, then compress item j of span s and |max| item j of span s + Lh ALTERNATE item by
-    // item (the HBM-bound |max| pass and the ALU-bound compress pass are co-resident on every SM, and a compress CTA never finds
-    // its span incomplete: all |max| items of span s precede it), then the compress items of the last Lh spans.  Alternating
-    // whole spans instead serialises the two passes whenever Lh == 1 (spans of 20-100 MB: 0.58 -> see DESIGN.md).
+    // Launch order: |max| items of spans 0 .. Lh-1, then the compress pass of span s alternates with the |max| pass of span s + Lh,
+    // then the compress items of the last Lh spans; a compress CTA never finds its span incomplete (all |max| items of span s
+    // precede it).  The two passes alternate span by span when several spans fit the look-ahead window (MoE experts) and ITEM BY
+    // ITEM when Lh == 1 (dense shapes, spans of 20-100 MB): whole-span alternation would then serialise the HBM-bound |max| pass
+    // and the ALU-bound compress pass (0.49-0.50 -> 0.55-0.56 of the roofline on 50-100 MB spans).
     const unsigned head = (unsigned)Lh * (unsigned)nblk, mid = (unsigned)(S - Lh) * 2u * (unsigned)nblk;
     bool is_b;
     int s, j;
@@ -322,7 +324,9 @@ __global__ void __launch_bounds__(FP4_THREADS, 6) nvfp4_fused_kernel(const Group
         is_b = false; s = (int)(blockIdx.x / (unsigned)nblk); j = (int)(blockIdx.x - (unsigned)s * (unsigned)nblk);
     } else if (blockIdx.x < head + mid) {
         const unsigned b = blockIdx.x - head, pair = b / (2u * (unsigned)nblk), q = b - pair * 2u * (unsigned)nblk;
-        is_b = (q & 1u) == 0; j = (int)(q >> 1); s = is_b ? (int)pair : (int)pair + Lh;
+        if (f.by_item) { is_b = (q & 1u) == 0; j = (int)(q >> 1); }             // B(s)[0], A(s+Lh)[0], B(s)[1], A(s+Lh)[1], ...
+        else { is_b = q < (unsigned)nblk; j = (int)(is_b ? q : q - (unsigned)nblk); }  // B(s)[0..], then A(s+Lh)[0..]
+        s = is_b ? (int)pair : (int)pair + Lh;
     } else {
         const unsigned b = blockIdx.x - head - mid, t = b / (unsigned)nblk;
         is_b = true; s = S - Lh + (int)t; j = (int)(b - t * (unsigned)nblk);
@@ -430,6 +434,8 @@ int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_
     const int64_t span_bytes = groups_per_mat * 32 * span;
     f.nt = nt;
     f.lookahead = (int)max((int64_t)1, min(n_spans, ((int64_t)tune_env("B200Q_FP4_LOOKAHEAD_MB", 40) << 20) / max(span_bytes, (int64_t)1)));
+    const int by_item = tune_env("B200Q_FP4_BY_ITEM", -1);
+    f.by_item = by_item >= 0 ? by_item : (f.lookahead == 1 ? 1 : 0);
     f.sync = sync;
     f.gs_out = gs_out;
     cudaMemsetAsync(sync, 0, sizeof(uint32_t) * 2 * n_spans, st);
