@@ -288,8 +288,8 @@ __device__ __forceinline__ uint32_t fp4_absmax_tiles(const uint4* wbase, int til
     for (int tile = tile0; tile < tile1; tile++) {
         uint4 raw[FP4_UF][2];
         fp4_load_tile<true>(raw, wbase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, groups_per_mat, keep);
-        mm = hmaxabs2(mm, hmaxabs2(hmaxabs2(fp4_group_absmax2(raw[0]), fp4_group_absmax2(raw[1])),
-                                   hmaxabs2(fp4_group_absmax2(raw[2]), fp4_group_absmax2(raw[3]))));
+#pragma unroll
+        for (int u = 0; u < FP4_UF; u++) mm = hmaxabs2(mm, fp4_group_absmax2(raw[u]));
     }
     mm = hmaxabs2(mm, prmt(mm, mm, 0x1032));
     uint32_t bits = (mm << 16) & 0x7fff0000u;                  // |max| as fp32 bits: non-negative floats order like uints
