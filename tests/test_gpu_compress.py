@@ -352,3 +352,37 @@ def test_fused_decompress_matches_two_step_oracle(name):
         got = ops.decompress_nvfp4(stack("weight_packed"), stack("weight_scale"), stack("weight_global_scale"))
     for e, want in enumerate(wants):
         assert_bits_equal(got[e], want, f"{name}[{e}]")
+
+
+@pytest.mark.parametrize("name", list(FORMATS))
+def test_fused_compress_random_ragged_shapes(name):
+    """Seeded sweep over awkward shapes: single rows, a single group / block per row, row counts that leave the last CTA, warp
+    tile or zero-point word partly empty, column counts just above a tile boundary, stacks of 1-5 matrices, value scales from
+    1e-6 to 1e4 -- every output tensor bit-for-bit against the oracle."""
+    import random
+    import zlib
+
+    from quantizers_b200 import ops
+
+    fmt, qtype, nb, sym, strat, g, blk = FORMATS[name]
+    unit = {O.GROUP: g, O.BLOCK: 8, O.CHANNEL: 8, O.TENSOR: 8}[strat]
+    if qtype == O.FP4:
+        unit = 16
+    rng = random.Random(zlib.crc32(name.encode()))  # str hashes are salted per process
+    cases = [(1, unit), (1, unit * 3), (2, unit * 33), (7, unit), (9, max(unit, 136) // unit * unit)]
+    while len(cases) < 22:
+        cases.append((rng.choice([1, 3, 8, 15, 17, 64, 129, 200]), unit * rng.choice([1, 2, 5, 8, 17, 32, 33, 40])))
+    for i, (R, C) in enumerate(cases):
+        if R * C > 600_000:
+            continue
+        n = rng.choice([1, 1, 2, 5])
+        scale = 10.0 ** rng.uniform(-6, 4)
+        ws = [(synth_weight(R, C, torch.float32, 500 + 7 * i + e, edge=(i % 3 == 0)) * scale).to(torch.bfloat16) for e in range(n)]
+        got = ops.compress_weight(torch.stack(ws).cuda() if n > 1 else ws[0].cuda(), Args(name))
+        for e, w in enumerate(ws):
+            want = O.compress(w, fmt, geom_of(name), nb, sym)
+            for k, v in want.items():
+                if k == "weight_shape":
+                    continue
+                gk = got[k][e] if n > 1 else got[k]
+                assert_bits_equal(gk.reshape(v.shape), v, f"{name} case {i}: {n} x [{R}, {C}] scale {scale:.2e} [{e}].{k}")
