@@ -233,6 +233,10 @@ static int elementwise(int op, const void* x, int64_t rows, int64_t cols, const 
         return op == EW_QUANT ? dispatch_group<MODE_QUANT>(sc->dtype, sc->qtype, p, 1, st)
                               : dispatch_group<MODE_FQ>(sc->dtype, sc->qtype, p, 1, st);
     }
+    if (op == EW_DEQUANT && sc->qtype == B200Q_FP8 && sc->dtype == B200Q_BF16 && zp == nullptr && gs == nullptr && fast_paths_enabled()) {
+        const int rc = launch_decode_fp8_fast((const uint8_t*)x, rows, cols, sc->strategy, g, sc->block_h, sc->block_w, scale, out, st);
+        if (rc != B200Q_ENOSYS) return rc;
+    }
     ElemParams p{};
     p.x = x; p.rows = rows; p.cols = cols; p.strategy = sc->strategy; p.group = g; p.bh = sc->block_h; p.bw = sc->block_w;
     p.nbits = sc->num_bits; p.has_zp = sc->has_zp; p.scale = scale; p.zp = zp; p.gs = gs; p.out = out;
@@ -267,12 +271,21 @@ int b200q_decompress_int_packed(const int32_t* packed, const void* scale, const 
     if (int rc = check_scheme(sc)) return rc;
     REQ_PTR(packed); REQ_PTR(scale); REQ_PTR(out);
     B200Q_REQUIRE(sc->qtype == B200Q_INT && (sc->strategy == B200Q_GROUP || sc->strategy == B200Q_CHANNEL), "pack-quantized decompress: INT, group or channel");
+    if (sc->dtype == B200Q_BF16 && sc->num_bits == 4 && fast_paths_enabled()) {
+        const int rc = launch_decode_int4_fast(packed, scale, zp_packed, batch, rows, cols, sc->strategy == B200Q_GROUP ? sc->group_size : 0, out,
+                                               (cudaStream_t)stream);
+        if (rc != B200Q_ENOSYS) return rc;
+    }
     return launch_decompress_int_packed(sc->dtype, packed, scale, zp_packed, batch, rows, cols, sc->strategy == B200Q_GROUP ? sc->group_size : 0,
                                         sc->num_bits, out, (cudaStream_t)stream);
 }
 int b200q_decompress_nvfp4(const uint8_t* packed, const uint8_t* scale_e4m3, const float* global_scale, int64_t batch, int64_t rows, int64_t cols,
                            int32_t dtype, void* out, void* stream) {
     REQ_PTR(packed); REQ_PTR(scale_e4m3); REQ_PTR(global_scale); REQ_PTR(out);
+    if (dtype == B200Q_BF16 && fast_paths_enabled()) {
+        const int rc = launch_decode_nvfp4_fast(packed, scale_e4m3, global_scale, 1, batch, rows, cols, out, (cudaStream_t)stream);
+        if (rc != B200Q_ENOSYS) return rc;
+    }
     return launch_decompress_nvfp4(dtype, packed, scale_e4m3, global_scale, 1, batch, rows, cols, out, (cudaStream_t)stream);
 }
 int b200q_pack_int32(const int8_t* value, int64_t rows, int64_t cols, int32_t num_bits, int32_t packed_dim, int32_t* packed,

@@ -86,6 +86,13 @@ struct TileParams {
     float* workspace;     // TENSOR: fp32 absmax bits per batch
 };
 int launch_channel_compress(int dt, int qt, const TileParams& p, int64_t batch, cudaStream_t st);
+// bf16 decode at HBM speed (decode_fast.cu); B200Q_ENOSYS when the scheme / shape is not covered
+int launch_decode_int4_fast(const int32_t* packed, const void* scale, const int32_t* zp_packed, int64_t batch, int64_t rows, int64_t cols, int group,
+                            void* out, cudaStream_t st);
+int launch_decode_fp8_fast(const uint8_t* codes, int64_t rows, int64_t cols, int strategy, int group, int bh, int bw, const void* scale, void* out,
+                           cudaStream_t st);
+int launch_decode_nvfp4_fast(const uint8_t* packed, const uint8_t* scale, const float* gs, int gs_stride, int64_t batch, int64_t rows, int64_t cols,
+                             void* out, cudaStream_t st);
 // bf16 issue-tuned CHANNEL compress (quant_channel_fast.cu): FP8 and INT4; B200Q_ENOSYS when the shape is not covered
 int launch_channel_fast(int qt, const TileParams& p, int64_t batch, cudaStream_t st);
 int launch_block_fp8_compress(int dt, const TileParams& p, int64_t batch, cudaStream_t st);
