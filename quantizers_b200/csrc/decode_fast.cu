@@ -13,6 +13,7 @@
 //         T(q) - T(zp), then * scale rounded to T (forward_helpers.py:258-266);
 //   FP8 / FP4: cvt.rn.f16x2.{e4m3x2,e2m1x2} is exact, the fp32 product with the scale is exact (or rounded once for NVFP4's fp32
 //         scale), cvt.rn.bf16x2.f32 is the final cast to T.
+#include <cstdlib>
 #include "../../include/b200q.h"
 #include "common.cuh"
 #include "fastmath.cuh"
@@ -86,6 +87,63 @@ __global__ void __launch_bounds__(256) decode_int4_kernel(const uint32_t* __rest
     }
 }
 
+// Power-of-two group sizes (every recipe: 32, 128): the same row walk in BATCHES of U words per lane.  The kernel above leaves the
+// `shift or divide` choice and the dependent scale / zero-point loads inside the loop, and ptxas then serialises word -> scale ->
+// convert -> store with one word of prefetch: each warp has ~2 loads in flight and the kernel is latency-bound (the 48-register
+// asymmetric variant, 5 CTAs per SM, measured 0.66-0.73 of the HBM roofline against 0.86 symmetric).  Here all 2U (3U) loads of a
+// batch are independent of each other and issued before the first conversion.
+template <bool HAS_ZP, int U>
+__global__ void __launch_bounds__(256) decode_int4_batch_kernel(const uint32_t* __restrict__ packed, const uint16_t* __restrict__ scale,
+                                                                const uint32_t* __restrict__ zp_packed, int64_t total_rows, int64_t rows, int cols,
+                                                                int sh /* log2(words per group) */, uint4* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+    const int wpr = cols >> 3, gtot = wpr >> sh;
+    const int64_t step_b = nwarps / rows, step_r = nwarps - step_b * rows;
+    int64_t b = HAS_ZP ? warp / rows : 0, r = HAS_ZP ? warp - b * rows : 0;
+    for (int64_t br = warp; br < total_rows; br += nwarps) {
+        const uint32_t* prow = packed + br * wpr;
+        const uint16_t* srow = scale + br * gtot;
+        const uint32_t* zrow = nullptr;
+        int zshift = 0;
+        if (HAS_ZP) {
+            zrow = zp_packed + (b * ((rows + 7) >> 3) + (r >> 3)) * gtot;
+            zshift = 4 * (int)(r & 7);
+            b += step_b;
+            r += step_r;
+            if (r >= rows) { r -= rows; b++; }
+        }
+        uint4* orow = out + br * wpr;
+        for (int c0 = lane; c0 < wpr; c0 += 32 * U) {
+            uint32_t w[U], sc[U], zw[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int cw = c0 + 32 * u;
+                const bool ok = cw < wpr;
+                const int g = cw >> sh;
+                w[u] = ok ? __ldg(prow + cw) : 0u;
+                sc[u] = ok ? (uint32_t)__ldg(srow + g) : 0u;
+                zw[u] = (HAS_ZP && ok) ? __ldg(zrow + g) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int cw = c0 + 32 * u;
+                const uint32_t s2 = sc[u] * 0x10001u;
+                uint32_t c2 = 0x43084308u;  // bf16x2 (136, 136)
+                if (HAS_ZP) c2 = (0x4300u | ((zw[u] >> zshift) & 0xfu)) * 0x10001u;  // 128 + (zp + 8)
+                uint32_t y[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t t = w[u] >> (8 * k);
+                    const uint32_t pair = 0x43004300u | (t & 0xfu) | ((t & 0xf0u) << 12);
+                    y[k] = hmul2(hsub2(pair, c2), s2);
+                }
+                if (cw < wpr) stg_stream(orow + cw, make_uint4(y[0], y[1], y[2], y[3]));
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ FP8
 // one warp per row; lane handles 8-code chunks lane, lane + 32, ... (8-byte load, 16-byte store).  Scale index of chunk cw:
 //   s_row_stride * (row / rows_per_scale) + cw / chunks_per_scale
@@ -110,6 +168,46 @@ __global__ void __launch_bounds__(256) decode_fp8_kernel(const uint2* __restrict
             y.z = f16x2_scale_to_bf16x2(e4m3x2_to_f16x2(c.y & 0xffffu), s);
             y.w = f16x2_scale_to_bf16x2(e4m3x2_to_f16x2(c.y >> 16), s);
             stg_stream(orow + cw, y);
+        }
+    }
+}
+
+// Batched variant (see decode_int4_batch_kernel): U chunks per lane, every load of a batch issued before the first conversion.
+// ROW_SCALE: one scale for the whole row (channel / tensor / block or group at least as wide as the row) -> loaded once per row;
+// otherwise chunks_per_scale is a power of two (sh).
+template <bool ROW_SCALE, int U>
+__global__ void __launch_bounds__(256) decode_fp8_batch_kernel(const uint2* __restrict__ codes, const uint16_t* __restrict__ scale, int64_t rows, int cols,
+                                                               int rows_per_scale, int sh, int64_t s_row_stride, uint4* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+    const int cpr = cols >> 3;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const uint2* crow = codes + r * cpr;
+        const uint16_t* srow = scale + (r / rows_per_scale) * s_row_stride;
+        uint4* orow = out + r * cpr;
+        uint32_t s_row = 0;
+        if (ROW_SCALE) s_row = (uint32_t)__ldg(srow) << 16;
+        for (int c0 = lane; c0 < cpr; c0 += 32 * U) {
+            uint2 c[U];
+            uint32_t sc[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int cw = c0 + 32 * u;
+                const bool ok = cw < cpr;
+                c[u] = ok ? __ldg(crow + cw) : make_uint2(0u, 0u);
+                sc[u] = ROW_SCALE ? s_row : (ok ? (uint32_t)__ldg(srow + (cw >> sh)) << 16 : 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int cw = c0 + 32 * u;
+                const float s = __uint_as_float(sc[u]);
+                uint4 y;
+                y.x = f16x2_scale_to_bf16x2(e4m3x2_to_f16x2(c[u].x & 0xffffu), s);
+                y.y = f16x2_scale_to_bf16x2(e4m3x2_to_f16x2(c[u].x >> 16), s);
+                y.z = f16x2_scale_to_bf16x2(e4m3x2_to_f16x2(c[u].y & 0xffffu), s);
+                y.w = f16x2_scale_to_bf16x2(e4m3x2_to_f16x2(c[u].y >> 16), s);
+                if (cw < cpr) stg_stream(orow + cw, y);
+            }
         }
     }
 }
@@ -154,8 +252,14 @@ __global__ void __launch_bounds__(256) decode_nvfp4_kernel(const uint32_t* __res
     }
 }
 
-unsigned row_grid(int64_t rows) { return (unsigned)max((int64_t)1, min((int64_t)kNumSMs * 8, (rows + 7) / 8)); }
-
+// CTAs per SM a decode grid is sized for: the measured optimum `best` (fewer, fatter streams beat full residency once every warp has
+// a batch of loads in flight: INT4 symmetric 0.85 -> 0.92 of the HBM roofline at 3 instead of 8, NVFP4 0.83 -> 0.90 at 4), never more
+// than the kernel's own residency `per`.  B200Q_DECODE_CTAS overrides `best` (development sweeps).
+int ctas_cap(int per, int best = 0) {
+    static const int env = [] { const char* v = getenv("B200Q_DECODE_CTAS"); return (v && *v) ? atoi(v) : 0; }();
+    const int want = env > 0 ? env : best;
+    return want > 0 ? min(want, per) : per;
+}
 }  // namespace
 
 // bf16, 4 bits, GROUP (group % 8 == 0, cols % group == 0) or CHANNEL (group == 0).  B200Q_ENOSYS otherwise.
@@ -165,12 +269,25 @@ int launch_decode_int4_fast(const int32_t* packed, const void* scale, const int3
     if ((((uintptr_t)out) & 15) != 0 || (((uintptr_t)packed) & 3) != 0) return B200Q_ENOSYS;
     const int64_t total = batch * rows;
     if (total * cols == 0) return B200Q_OK;
-    if (zp_packed)
-        decode_int4_kernel<true><<<row_grid(total), 256, 0, st>>>((const uint32_t*)packed, (const uint16_t*)scale, (const uint32_t*)zp_packed, total,
-                                                                  rows, (int)cols, group / 8, (uint4*)out);
-    else
-        decode_int4_kernel<false><<<row_grid(total), 256, 0, st>>>((const uint32_t*)packed, (const uint16_t*)scale, nullptr, total, rows, (int)cols,
-                                                                   group / 8, (uint4*)out);
+    const uint32_t* pk = (const uint32_t*)packed;
+    const uint16_t* sc = (const uint16_t*)scale;
+    const uint32_t* zp = (const uint32_t*)zp_packed;
+    const int wpg = group / 8, wpr = (int)(cols >> 3);
+    // grid = one full wave of the kernel's own residency: a fixed 8 x SMs grid ran the 48-register asymmetric kernel (5 CTAs per SM) as
+    // 1.6 waves
+#define B200Q_DECODE_INT4(K, ARG, BEST) do { static const int per = [] { int n = 0; return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, K, 256, 0) == cudaSuccess && n > 0) ? n : 4; }(); \
+        const unsigned grid = (unsigned)max((int64_t)1, min((int64_t)kNumSMs * ctas_cap(per, BEST), (total + 7) / 8)); \
+        K<<<grid, 256, 0, st>>>(pk, sc, zp, total, rows, (int)cols, ARG, (uint4*)out); } while (0)
+    static const bool batched = getenv("B200Q_DECODE_INT4_LEGACY") == nullptr;  // A/B switch
+    if (batched && wpg > 0 && (wpg & (wpg - 1)) == 0) {
+        const int sh = __builtin_ctz((unsigned)wpg);
+        const bool u5 = wpr % 160 == 0;  // rows that split into whole batches of 5 words per lane (2560 columns)
+        // CTAs per SM from the sweeps in profiles/r1_decompress.json (three shapes): symmetric 3, asymmetric 5 (U = 5) / 4 (U = 4)
+        if (zp) { if (u5) B200Q_DECODE_INT4((decode_int4_batch_kernel<true, 5>), sh, 5); else B200Q_DECODE_INT4((decode_int4_batch_kernel<true, 4>), sh, 4); }
+        else { if (u5) B200Q_DECODE_INT4((decode_int4_batch_kernel<false, 5>), sh, 3); else B200Q_DECODE_INT4((decode_int4_batch_kernel<false, 4>), sh, 3); }
+    } else if (zp) B200Q_DECODE_INT4(decode_int4_kernel<true>, wpg, 0);
+    else B200Q_DECODE_INT4(decode_int4_kernel<false>, wpg, 0);
+#undef B200Q_DECODE_INT4
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }
@@ -192,8 +309,15 @@ int launch_decode_fp8_fast(const uint8_t* codes, int64_t rows, int64_t cols, int
         if (bh <= 0 || bw <= 0 || bw % 8 != 0) return B200Q_ENOSYS;
         rows_per_scale = bh; chunks_per_scale = bw / 8; stride = (cols + bw - 1) / bw;
     } else return B200Q_ENOSYS;
-    decode_fp8_kernel<<<row_grid(rows), 256, 0, st>>>((const uint2*)codes, (const uint16_t*)scale, rows, (int)cols, rows_per_scale, chunks_per_scale,
-                                                      stride, (uint4*)out);
+    static const bool batched = getenv("B200Q_DECODE_FP8_LEGACY") == nullptr;  // A/B switch
+    const bool row_scale = chunks_per_scale >= cpr, pow2 = (chunks_per_scale & (chunks_per_scale - 1)) == 0;
+#define B200Q_DECODE_FP8(K, SH, BEST) do { static const int per = [] { int n = 0; return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, K, 256, 0) == cudaSuccess && n > 0) ? n : 4; }(); \
+        const unsigned grid = (unsigned)max((int64_t)1, min((int64_t)kNumSMs * ctas_cap(per, BEST), (rows + 7) / 8)); \
+        K<<<grid, 256, 0, st>>>((const uint2*)codes, (const uint16_t*)scale, rows, (int)cols, rows_per_scale, SH, stride, (uint4*)out); } while (0)
+    if (batched && row_scale) B200Q_DECODE_FP8((decode_fp8_batch_kernel<true, 4>), 0, 4);  // per-row scale: 0.90 at 3-4 CTAs per SM, 0.86-0.88 at 8
+    else if (batched && pow2) B200Q_DECODE_FP8((decode_fp8_batch_kernel<false, 4>), __builtin_ctz((unsigned)chunks_per_scale), 0);
+    else B200Q_DECODE_FP8(decode_fp8_kernel, chunks_per_scale, 0);
+#undef B200Q_DECODE_FP8
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }
@@ -205,7 +329,10 @@ int launch_decode_nvfp4_fast(const uint8_t* packed, const uint8_t* scale, const 
     const int64_t words = rows * (cols >> 3);
     if (batch * words == 0) return B200Q_OK;
     if ((words * 4) % 4 != 0) return B200Q_ENOSYS;
-    const unsigned gx = (unsigned)max((int64_t)1, min((int64_t)kNumSMs * 8 / max(batch, (int64_t)1) + 1, (words + 1023) / 1024));
+    // at most ONE wave of resident CTAs over all matrices (the former "+ 1" put `batch` CTAs into a second wave: every CTA owns an equal
+    // share of the tiles, so the stragglers doubled the critical path)
+    static const int per = [] { int n = 0; return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, decode_nvfp4_kernel, 256, 0) == cudaSuccess && n > 0) ? n : 4; }();
+    const unsigned gx = (unsigned)max((int64_t)1, min((int64_t)kNumSMs * ctas_cap(per, 4) / max(batch, (int64_t)1), (words + 1023) / 1024));
     decode_nvfp4_kernel<<<dim3(gx, (unsigned)batch), 256, 0, st>>>((const uint32_t*)packed, scale, gs, gs_stride, words, (uint4*)out);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;

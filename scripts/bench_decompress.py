@@ -3,14 +3,16 @@ import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from quantizers_b200 import ops
-from quantizers_b200.scheduler import PRESETS, synth_stack
+from quantizers_b200.scheduler import PRESETS, SchemeArgs, synth_stack
 
 dev = torch.device("cuda", 0)
 peak = 6549.4
-w = synth_stack(list(range(32)), 9728, 2560, 0, dev)
+E, R, C = (int(v) for v in os.environ.get("B200Q_BENCH_SHAPE", "32,9728,2560").split(","))
+w = synth_stack(list(range(E)), R, C, 0, dev)
 rows = []
-for name in ("W4A16", "W4A16_ASYM", "INT4_G32_SYM", "NVFP4", "FP8_BLOCK", "FP8_G32", "FP8_CHANNEL"):
-    a = PRESETS[name]
+names = sys.argv[1:] or ["W4A16", "W4A16_ASYM", "INT4_G32_SYM", "INT4_G32_ASYM", "NVFP4", "FP8_BLOCK", "FP8_G32", "FP8_CHANNEL"]
+for name in names:
+    a = PRESETS[name] if name in PRESETS else SchemeArgs(4, "int", False, "group", 32)  # INT4_G32_ASYM
     sd = ops.compress_weight(w, a)
     if a.type == "int":
         fn = lambda: ops.decompress_int_packed(sd["weight_packed"], sd["weight_scale"], sd.get("weight_zero_point"), w.shape, a)
@@ -41,4 +43,5 @@ for name in ("W4A16", "W4A16_ASYM", "INT4_G32_SYM", "NVFP4", "FP8_BLOCK", "FP8_G
     print(f"{name:13s} {ms*1e3:8.1f} us  {w.numel()*2/ms/1e6:6.0f} GB/s bf16-out  {alg:6.0f} GB/s algorithmic  {alg/peak:.3f}", flush=True)
     del out, sd
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump({"stack": list(w.shape), "rows": rows}, open("gpurun_out/decompress.json", "w"), indent=1)
+tag = os.environ.get("B200Q_DECODE_INT4_PRE", "")
+json.dump({"stack": list(w.shape), "rows": rows}, open(f"gpurun_out/decompress{'_' + tag if tag else ''}.json", "w"), indent=1)
