@@ -4,7 +4,9 @@
 //   awq_scales     _compute_best_scale grid point s = x_mean^r / (w_mean^(1-r) + 1e-4) ... / sqrt(max*min)
 //   sq_err         _compute_loss partial          sum (T(y_ref - y_q))^2 in fp32
 // All HBM-bound single-pass reductions (2 B/element for bf16).
+#include <cstdlib>
 #include "common.cuh"
+#include "fastmath.cuh"
 #include "kernels.cuh"
 
 namespace b200q {
@@ -90,6 +92,82 @@ __global__ void __launch_bounds__(256) wmean_kernel(const void* __restrict__ w, 
     if (c < cols) atomicAdd(&acc[c], tot);
 }
 
+// bf16 fast path of the same statistic.  The generic kernel above issues one load per warp per row (shuffle inside the loop), an IEEE
+// division and an F2F.F64 conversion per element: 0.18 of the HBM roofline.  Here: U rows per warp per batch with every load issued
+// first; |max| as packed bf16x2; the quotient T(|w| / den) from the bracketed reciprocal (fastmath.cuh -- both bracket ends round
+// to the same bf16 or the chunk is redone with the IEEE division); bf16 -> fp64 by bit placement instead of a conversion.
+__device__ __forceinline__ double bf16_nonneg_to_double(uint32_t q) {
+    const uint32_t e = q & 0x7f80u;
+    if (e == 0u || e == 0x7f80u) return (double)__uint_as_float(q << 16);  // zero, subnormal, inf / NaN
+    return __hiloint2double((int)((q << 13) + 0x38000000u), 0);            // rebias 127 -> 1023, mantissa to the top of the 52 bits
+}
+__device__ __noinline__ void wmean_exact_chunk(const uint4 raw, float den, uint32_t q2[4]) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        const float lo = fabsf(__uint_as_float(w[k] << 16)), hi = fabsf(__uint_as_float(w[k] & 0xffff0000u));
+        q2[k] = fast::cvt_bf16x2(__fdiv_rn(hi, den), __fdiv_rn(lo, den));
+    }
+}
+template <int L, int U>
+__global__ void __launch_bounds__(256) wmean_bf16_kernel(const uint16_t* __restrict__ w, int64_t rows, int64_t cols, double* __restrict__ acc) {
+    __shared__ double sm[8][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * 256 + lane * 8;
+    const bool col_ok = c0 < cols;
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int64_t r_per = (rows + gridDim.y - 1) / gridDim.y;
+    const int64_t r_begin = (int64_t)blockIdx.y * r_per, r_end = min(rows, r_begin + r_per);
+    const int64_t r_stop = r_begin + ((r_per + 8 * U - 1) / (8 * U)) * (8 * U);  // warp-uniform trip count (shuffles inside)
+    for (int64_t r = r_begin + warp; r < r_stop; r += 8 * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t rr = r + 8 * u;
+            v[u] = (rr < r_end && col_ok) ? ldg_stream(w + rr * cols + c0) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool ok = (r + 8 * u) < r_end && col_ok;
+            uint32_t a2 = fast::hmaxabs2(fast::hmaxabs2(v[u].x, v[u].y), fast::hmaxabs2(v[u].z, v[u].w));
+            a2 = fast::hmaxabs2(a2, fast::prmt(a2, a2, 0x1032));
+#pragma unroll
+            for (int o = L >> 1; o > 0; o >>= 1) a2 = fast::hmaxabs2(a2, __shfl_xor_sync(0xffffffffu, a2, o));
+            const float a = __uint_as_float((a2 << 16) & 0x7fff0000u);
+            const float den = round_to<DT_BF16>(fadd(a, 1e-6f));
+            fast::Bracket br;
+            br.init(den);
+            const uint32_t wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            uint32_t q2[4], diff = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const fast::f32x2 x = fast::bf16x2_to_f32x2(wd[k] & 0x7fff7fffu);
+                float al, ah, bl, bh;
+                fast::unpack2(fast::mul2(x, br.lo), al, ah);
+                fast::unpack2(fast::mul2(x, br.hi), bl, bh);
+                q2[k] = fast::cvt_bf16x2(ah, al);
+                diff |= q2[k] ^ fast::cvt_bf16x2(bh, bl);
+            }
+            if (diff != 0 || !fast::scale_is_safe(__float_as_uint(den))) wmean_exact_chunk(v[u], den, q2);
+            if (ok) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    s[2 * k] += bf16_nonneg_to_double(q2[k] & 0xffffu);
+                    s[2 * k + 1] += bf16_nonneg_to_double(q2[k] >> 16);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) sm[warp][lane * 8 + i] = s[i];
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) tot += sm[r][threadIdx.x];
+    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c < cols) atomicAdd(&acc[c], tot);
+}
+
 int launch_wmean(int dt, const void* w, int64_t rows, int64_t cols, int group, double* acc, cudaStream_t st) {
     B200Q_REQUIRE(group == 16 || group == 32 || group == 64 || group == 128 || group == 256,
                   "w_mean: group_size %d unsupported (16/32/64/128/256)", group);
@@ -98,6 +176,25 @@ int launch_wmean(int dt, const void* w, int64_t rows, int64_t cols, int group, d
     if (rows * cols == 0) return B200Q_OK;
     const int64_t gx = (cols + 255) / 256;
     const int64_t gy = max((int64_t)1, min((rows + 31) / 32, (int64_t)(kNumSMs * 4 + gx - 1) / gx));
+    static const bool fast_bf16 = getenv("B200Q_WMEAN_LEGACY") == nullptr;  // A/B switch
+    if (fast_bf16 && dt == DT_BF16) {
+        const uint16_t* wp = (const uint16_t*)w;
+        // row slabs sized so that the whole grid is ONE wave of the kernel's residency (64 registers: 4 CTAs per SM; 600 CTAs on 592
+        // slots ran as two waves)
+#define B200Q_WMEAN(LANES) do { static const int per = [] { int n = 0; return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wmean_bf16_kernel<LANES, 4>, 256, 0) == cudaSuccess && n > 0) ? n : 2; }(); \
+            const int64_t slabs = max((int64_t)1, min((rows + 31) / 32, (int64_t)kNumSMs * per / gx)); \
+            wmean_bf16_kernel<LANES, 4><<<dim3((unsigned)gx, (unsigned)slabs), 256, 0, st>>>(wp, rows, cols, acc); } while (0)
+        switch (group) {
+            case 16: B200Q_WMEAN(2); break;
+            case 32: B200Q_WMEAN(4); break;
+            case 64: B200Q_WMEAN(8); break;
+            case 128: B200Q_WMEAN(16); break;
+            default: B200Q_WMEAN(32); break;
+        }
+#undef B200Q_WMEAN
+        B200Q_CHECK_LAUNCH();
+        return B200Q_OK;
+    }
     B200Q_DISPATCH_DT(dt, { wmean_kernel<DT><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(w, rows, cols, group, acc); });
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;

@@ -340,3 +340,24 @@ def test_gptq_hessian_accumulation():
     assert torch.allclose(H.cpu(), H.cpu().t(), rtol=0, atol=2e-5 * H_ref.abs().max().item())
     with pytest.raises(ValueError):
         gptq.accumulate_hessian(torch.zeros(4, K, device="cuda"), H, n)
+
+
+@pytest.mark.parametrize("group", [16, 32, 64, 128, 256])
+def test_wmean_bf16_fast_path_extremes(group):
+    """_compute_layer_means on bf16 (bracketed-reciprocal kernel): exact against the oracle with magnitudes from 1e-30 to > 1
+    (denominator outside the bracket's safe range -> IEEE repair), zero groups, ragged row counts and a column count that is
+    not a multiple of the 256-column tile."""
+    from quantizers_b200 import awq
+
+    g = torch.Generator().manual_seed(77)
+    rows, cols = 8 * 13 + 5, 256 * 3 + 256 * (group == 256) + group
+    w = torch.randn(rows, cols, generator=g) * 0.02
+    w[:, : group] *= 300.0          # |max| > 1
+    w[3, group: 2 * group] = 0.0    # zero group: 0 / 1e-6
+    w[4, :] = 1e-30
+    w[5, :8] = 6e-39                # bf16 subnormals
+    w[6, ::3] = -0.0
+    w = w.to(torch.bfloat16)
+    got = awq.compute_layer_means([w.cuda(), w[:7].cuda()], group).cpu()
+    ref = O.w_mean([w, w[:7]], group).float()
+    assert torch.equal(got, ref), group

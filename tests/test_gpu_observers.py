@@ -115,3 +115,35 @@ def test_mse_observer_early_stop_and_registry():
     s_ref, _ = O.calculate_qparams(rmn, rmx, O.INT, 4, True)
     assert_bits_equal(scale.reshape(s_ref.shape), s_ref, "mse scale")
     assert {"mse", "memoryless_mse"} <= set(Observer.registered_names())
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 16), (37, 768), (64 + 3, 2560 + 256), (128 + 17, 1024 + 128)])
+@pytest.mark.parametrize("group", [16, 32, 64, 128, 256, 0])
+def test_minmax_group_channel_bf16_fast_path(rows, cols, group):
+    """b200q_minmax GROUP / CHANNEL on bf16 (packed min/max kernels): bit-identical to the oracle over group sizes, ragged row
+    lengths (not a multiple of the 1024-column batch), the -0.0 row, the all-zero group and the 1e-30 values of synth_weight."""
+    from quantizers_b200 import ops
+
+    if group and cols % group:
+        pytest.skip("columns not divisible by the group")
+    w = synth_weight(rows, cols, torch.bfloat16, 11)
+    args = Args("int4_g128_asym")
+    args.strategy, args.group_size = ("group", group) if group else ("channel", None)
+    mn, mx = ops.observe_minmax(w.cuda(), args)
+    rmn, rmx = O.minmax(w, O.Geom(O.GROUP, group) if group else O.Geom(O.CHANNEL, 0))
+    assert_bits_equal(mn.reshape(rmn.shape), rmn, f"min g{group}")
+    assert_bits_equal(mx.reshape(rmx.shape), rmx, f"max g{group}")
+
+
+@pytest.mark.parametrize("rows,cols", [(128, 128), (256 + 64, 512), (100, 384 + 8), (3 * 128, 2560)])
+def test_minmax_block128_bf16_fast_path(rows, cols):
+    """128x128 block min/max on bf16, whole and ragged tiles (zero padding takes part, as in CT), stacked matrices."""
+    from quantizers_b200 import ops
+
+    ws = [synth_weight(rows, cols, torch.bfloat16, 20 + i) for i in range(2)]
+    ws[1] = ws[1].abs() + 0.01  # a matrix without negatives: ragged tiles must still report min 0
+    mn, mx = ops.observe_minmax(torch.stack(ws).cuda(), Args("fp8_block"))
+    for i, w in enumerate(ws):
+        rmn, rmx = O.minmax(w, O.Geom(O.BLOCK, 0, 128, 128))
+        assert_bits_equal(mn[i].reshape(rmn.shape), rmn, f"min {i}")
+        assert_bits_equal(mx[i].reshape(rmx.shape), rmx, f"max {i}")
