@@ -255,6 +255,10 @@ int b200q_quantize_pack(const void* x, int64_t batch, int64_t rows, int64_t cols
     GroupParams p{};
     p.w = x; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = sc->num_bits; p.symmetric = sc->symmetric;
     p.has_zp = sc->has_zp; p.scale = const_cast<void*>(scale); p.zp_in = zp; p.gs = gs; p.gs_stride = 0; p.out = packed;
+    if (sc->dtype == B200Q_BF16 && fast_paths_enabled() && tma_paths_enabled() && (sc->qtype == B200Q_FP8 || (sc->qtype == B200Q_INT && sc->num_bits == 4))) {
+        const int rc = launch_group_tma_supplied(sc->qtype == B200Q_FP8 ? QT_FP8 : QT_INT, p, batch, (cudaStream_t)stream);
+        if (rc != B200Q_ENOSYS) return rc;
+    }
     return dispatch_group<MODE_QUANT_PACK>(sc->dtype, sc->qtype, p, batch, (cudaStream_t)stream);
 }
 int b200q_fake_quantize(const void* x, int64_t rows, int64_t cols, const b200q_scheme* sc, const void* scale, const int8_t* zp,

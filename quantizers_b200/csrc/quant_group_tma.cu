@@ -55,6 +55,7 @@ struct TmaParams {
     uint8_t* out;             // packed codes, flat
     void* scale;              // bf16 (INT/FP8) or e4m3 bytes (FP4), flat [n_groups]
     int32_t* zp_packed;       // asym INT4
+    const int8_t* zp_in;      // SUPPLIED mode, asym INT4: int8 [n_groups]
     const float* gs;          // FP4: fp32 [batch] (stride 1) or [1] (stride 0)
     int32_t gs_stride;
     int32_t has_zp;
@@ -95,7 +96,9 @@ __device__ __noinline__ uint2 repair_chunk(const uint4 raw, float s, float z, bo
 // LOG2N: log2(chunks per group): 1 (g16) 2 (g32) 3 (g64) 4 (g128)
 // FMA: ALU-pipe relief variants (fastmath.cuh): FHFMA unpack, DPX 3-input max for the asymmetric statistics, bracket agreement
 // accumulated with HFMA2, nibble folding with LEA.HI
-template <int QT, bool SYM, int LOG2N, bool FMA, int TILE>
+// SUPPLIED: the caller's qparams (Compressor.compress with an observer's weight_scale / weight_zero_point, b200q_quantize_pack): the
+// statistics and qparam stages are replaced by one load per group; nothing but the packed codes is written.
+template <int QT, bool SYM, int LOG2N, bool FMA, int TILE, bool SUPPLIED = false>
 __global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_kernel(const TmaParams p) {
     constexpr int kWarps = WarpsFor<QT, TILE>::value;
     constexpr int kTileBytes = TILE * 2;
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_k
         // position of the tile's first group (warp-uniform, once per tile): matrix b0, row r0, group-in-row k0
         int64_t b0 = 0;
         uint32_t r0 = 0, k0 = 0;
-        if (QT == QT_INT && !SYM) {
+        if (QT == QT_INT && !SYM && !SUPPLIED) {
             b0 = g0 / p.groups_per_mat;
             const int64_t rem0 = g0 - b0 * p.groups_per_mat;
             r0 = (uint32_t)(rem0 / p.groups_per_row);
@@ -189,8 +192,9 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_k
             const bool owner = act && half == 0;     // writes the group's qparams
             const uint32_t gaddr = tin + (uint32_t)gl * (G * 2) + (uint32_t)half * (NL * 16);
             // ---- A. statistics (two independent chains for ILP)
-            uint32_t st_a, st_b = 0;
-            if (SYM) {
+            uint32_t st_a = 0, st_b = 0;
+            if (SUPPLIED) {
+            } else if (SYM) {
                 uint32_t a0 = 0, a1 = 0;
 #pragma unroll
                 for (int i = 0; i < NL; i += 2) {
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_k
                 st_a = hmax2(st_a, prmt(st_a, st_a, 0x1032));
                 st_b = hmin2(st_b, prmt(st_b, st_b, 0x1032));
             }
-            if (LPG == 2) {  // the other half of the group lives in the neighbouring lane
+            if (LPG == 2 && !SUPPLIED) {  // the other half of the group lives in the neighbouring lane
                 const uint32_t oa = __shfl_xor_sync(0xffffffffu, st_a, 1), ob = __shfl_xor_sync(0xffffffffu, st_b, 1);
                 if (SYM) st_a = hmaxabs2(st_a, oa);
                 else if (FMA) { st_a = __vmaxs2(st_a, oa); st_b = __vmaxu2(st_b, ob); }
@@ -247,7 +251,13 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_k
             float s, z = 0.0f;
             Bracket br;
             const int64_t gidx = g0 + gl;
-            if (QT == QT_FP4) {
+            if (SUPPLIED) {
+                const int64_t gq = act ? gidx : g0;  // inactive lanes of a partial tile read a valid entry and store nothing
+                if (QT == QT_FP4) s = __fdiv_rn(e4m3_decode(((const uint8_t*)p.scale)[gq]), p.gs[p.gs_stride ? gq / p.groups_per_mat : 0]);
+                else s = __uint_as_float((uint32_t)((const uint16_t*)p.scale)[gq] << 16);
+                if (QT == QT_INT && !SYM) z = (float)p.zp_in[gq];
+                br.init(s);
+            } else if (QT == QT_FP4) {
                 const float amax = __uint_as_float((st_a << 16) & 0x7fff0000u);
                 float gsv = gs_tile;
                 if (!gs_uniform && act) gsv = p.gs[gidx / p.groups_per_mat];
@@ -287,7 +297,7 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_k
                 s = s0;
                 if (s0 == 0.0f) { s = eps_of<DT_BF16>(); br.init(s); }
             }
-            if (QT != QT_FP4) {
+            if (QT != QT_FP4 && !SUPPLIED) {
                 if (owner) ((uint16_t*)p.scale)[gidx] = (uint16_t)(__float_as_uint(s) >> 16);
                 if (QT == QT_INT && !SYM && owner) {
                     const uint32_t gpr = (uint32_t)p.groups_per_row;  // launcher guarantees < 2^31
@@ -447,7 +457,62 @@ int launch_tma(const TmaParams& p, cudaStream_t st) {
     return fma ? launch_tma_v<QT, SYM, LOG2N, true, 4096>(p, st) : launch_tma_v<QT, SYM, LOG2N, false, 4096>(p, st);
 }
 
+template <int QT, bool SYM, int LOG2N>
+int launch_tma_supplied(const TmaParams& p, cudaStream_t st) {
+    constexpr int TILE = 4096;
+    constexpr bool FMA = QT == QT_INT;
+    constexpr int OUT_BYTES = (TILE / 8) * ((QT == QT_FP8) ? 8 : 4);
+    constexpr int kWarps = WarpsFor<QT, TILE>::value;
+    const size_t smem = (size_t)kWarps * (kStages * TILE * 2 + OUT_BYTES + 64);
+    static bool configured = false;  // benign race: idempotent attribute
+    if (!configured) {
+        cudaFuncSetAttribute(group_tma_kernel<QT, SYM, LOG2N, FMA, TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    constexpr int GPT = TILE / (8 << LOG2N);
+    const int64_t n_tiles = (p.n_groups + GPT - 1) / GPT;
+    const int64_t ctas = max((int64_t)1, min((int64_t)kNumSMs, (n_tiles + kWarps - 1) / kWarps));
+    group_tma_kernel<QT, SYM, LOG2N, FMA, TILE, true><<<(unsigned)ctas, kWarps * 32, smem, st>>>(p);
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
 }  // namespace
+
+// bf16 only, caller-supplied qparams (MODE_QUANT_PACK): scale bf16 [n_groups], zp int8 [n_groups] or null.  INT4 and FP8 GROUP.
+int launch_group_tma_supplied(int qt, const GroupParams& gp, int64_t batch, cudaStream_t st) {
+    const int g = gp.group;
+    if (!(g == 32 || g == 64 || g == 128) || gp.cols % g != 0) return B200Q_ENOSYS;
+    if ((((uintptr_t)gp.w) & 15) != 0 || (((uintptr_t)gp.out) & 15) != 0 || batch * gp.rows * gp.cols == 0) return B200Q_ENOSYS;
+    if ((batch * gp.rows * gp.cols) % 32 != 0 || (((uintptr_t)gp.scale) & 1) != 0) return B200Q_ENOSYS;
+    if (gp.cols / g >= (1ll << 30) || gp.rows >= (1ll << 40)) return B200Q_ENOSYS;
+    TmaParams p{};
+    p.w = (const uint16_t*)gp.w;
+    p.groups_per_row = gp.cols / g;
+    p.groups_per_mat = gp.rows * p.groups_per_row;
+    p.n_groups = batch * p.groups_per_mat;
+    p.rows = gp.rows;
+    p.out = (uint8_t*)gp.out;
+    p.scale = gp.scale;
+    p.zp_in = gp.zp_in;
+    p.has_zp = gp.has_zp;
+    if (qt == QT_INT && gp.nbits == 4) {
+        const bool sym = gp.zp_in == nullptr;  // quant_int adds the zero point only when one is supplied
+        switch (g) {
+        case 32: return sym ? launch_tma_supplied<QT_INT, true, 2>(p, st) : launch_tma_supplied<QT_INT, false, 2>(p, st);
+        case 64: return sym ? launch_tma_supplied<QT_INT, true, 3>(p, st) : launch_tma_supplied<QT_INT, false, 3>(p, st);
+        default: return sym ? launch_tma_supplied<QT_INT, true, 4>(p, st) : launch_tma_supplied<QT_INT, false, 4>(p, st);
+        }
+    }
+    if (qt == QT_FP8) {
+        switch (g) {
+        case 32: return launch_tma_supplied<QT_FP8, true, 2>(p, st);
+        case 64: return launch_tma_supplied<QT_FP8, true, 3>(p, st);
+        default: return launch_tma_supplied<QT_FP8, true, 4>(p, st);
+        }
+    }
+    return B200Q_ENOSYS;
+}
 
 // bf16 only.  Returns B200Q_ENOSYS when the scheme / shape is not covered.
 int launch_group_tma(int qt, const GroupParams& gp, int64_t batch, cudaStream_t st) {

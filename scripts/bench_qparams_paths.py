@@ -54,7 +54,7 @@ for name in names:
     # Q3 quantize: bf16 -> codes (INT: int8 per element; FP8: e4m3; FP4: grid values in bf16)
     q_out_bytes = n * (2 if (a.type == "float" and a.num_bits == 4) else 1)
     q = timed(f"{name} quantize", n * 2 + q_out_bytes,
-              lambda: ops.quantize(w, scale, zp, a, dtype=(torch.int8 if a.type == "int" else None), global_scale=gsc))
+              lambda: ops.quantize(w, scale, zp, a, dtype=(torch.int8 if a.type == "int" else (torch.float8_e4m3fn if a.num_bits == 8 else None)), global_scale=gsc))
     timed(f"{name} fake_quantize", n * 4, lambda: ops.fake_quantize(w, scale, zp, a, global_scale=gsc))
     if a.strategy in ("group", "tensor_group"):
         timed(f"{name} quantize_pack", n * 2 + code_bytes, lambda: ops.quantize_pack(w, scale, zp, a, global_scale=gsc))

@@ -386,3 +386,37 @@ def test_fused_compress_random_ragged_shapes(name):
                     continue
                 gk = got[k][e] if n > 1 else got[k]
                 assert_bits_equal(gk.reshape(v.shape), v, f"{name} case {i}: {n} x [{R}, {C}] scale {scale:.2e} [{e}].{k}")
+
+
+@pytest.mark.parametrize("name", ["int4_g128_asym", "int4_g128_sym", "int4_g32_sym", "int4_g32_asym", "fp8_g32", "fp8_g128"])
+@pytest.mark.parametrize("rows,cols", [(37, 768), (64, 2560), (3, 128)])
+def test_quantize_pack_with_foreign_qparams(name, rows, cols):
+    """Compressor.compress's arithmetic with qparams that did NOT come from this weight's min/max (an EMA / MSE observer, a
+    checkpoint): perturbed scales, random zero points, a zero scale and a huge one.  The bf16 fast path (TMA kernel, SUPPLIED
+    mode) must use exactly what it is given; partial last tiles and stacked matrices included."""
+    from quantizers_b200 import ops
+
+    fmt, qtype, nb, sym, strat, g, blk = FORMATS[name]
+    geom, args = geom_of(name), Args(name)
+    gen = torch.Generator().manual_seed(rows * 131 + cols)
+    ws = [synth_weight(rows, cols, torch.bfloat16, 50 + i) for i in range(2)]
+    G = cols // g
+    packs, scales, zps = [], [], []
+    for w in ws:
+        mn, mx = O.minmax(w, geom)
+        s, z = O.calculate_qparams(mn, mx, qtype, nb, sym)
+        s = (s.float() * (0.5 + 1.5 * torch.rand(s.shape, generator=gen))).to(torch.bfloat16)
+        s.view(-1)[0] = 0.0          # x / 0
+        s.view(-1)[-1] = 3.0e5       # outside the reciprocal bracket's safe range
+        if G > 2:
+            s.view(-1)[1] = 1e-35
+        z = torch.randint(-8, 8, s.shape, generator=gen, dtype=torch.int8) if (qtype == O.INT and not sym) else None
+        zarg = z if z is not None else (None if qtype == O.INT else torch.zeros(s.shape, dtype=torch.float8_e4m3fn))
+        q_o = O.quantize(w, s, zarg, geom, qtype, nb)
+        packs.append(O.pack_to_int32(q_o, nb) if qtype == O.INT else q_o)
+        scales.append(s)
+        zps.append(zarg)
+    zp_stack = None if zps[0] is None else torch.stack(zps).cuda()
+    got = ops.quantize_pack(torch.stack(ws).cuda(), torch.stack(scales).cuda(), zp_stack, args)
+    for i in range(2):
+        assert_bits_equal(got[i], packs[i], f"{name}[{i}]")
