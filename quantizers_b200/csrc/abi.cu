@@ -225,6 +225,14 @@ static int elementwise(int op, const void* x, int64_t rows, int64_t cols, const 
     if (sc->qtype == B200Q_FP4) B200Q_REQUIRE(gs != nullptr || sc->strategy != B200Q_GROUP || true, "unreachable");
     const bool vec_ok = cols % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0;
     const int g = sc->group_size;
+    static const bool ew_fast = getenv("B200Q_ELEMENTWISE_LEGACY") == nullptr;  // A/B switch
+    if (ew_fast && op != EW_DEQUANT && sc->dtype == B200Q_BF16 && gs == nullptr && vec_ok && fast_paths_enabled()) {
+        ElemParams f{};
+        f.x = x; f.rows = rows; f.cols = cols; f.strategy = sc->strategy; f.group = g; f.bh = sc->block_h; f.bw = sc->block_w;
+        f.nbits = sc->num_bits; f.has_zp = sc->has_zp; f.scale = scale; f.zp = zp; f.gs = gs; f.out = out;
+        const int rc = launch_elementwise_fast(op, sc->qtype, f, st);
+        if (rc != B200Q_ENOSYS) return rc;
+    }
     if (op != EW_DEQUANT && sc->strategy == B200Q_GROUP && vec_ok && (g == 16 || g == 32 || g == 64 || g == 128 || g == 256) &&
         cols % g == 0 && (sc->qtype != B200Q_FP4 || gs != nullptr)) {
         GroupParams p{};
@@ -232,6 +240,13 @@ static int elementwise(int op, const void* x, int64_t rows, int64_t cols, const 
         p.has_zp = sc->has_zp; p.scale = const_cast<void*>(scale); p.zp_in = zp; p.gs = gs; p.gs_stride = 0; p.out = out;
         return op == EW_QUANT ? dispatch_group<MODE_QUANT>(sc->dtype, sc->qtype, p, 1, st)
                               : dispatch_group<MODE_FQ>(sc->dtype, sc->qtype, p, 1, st);
+    }
+    if (ew_fast && op == EW_DEQUANT && sc->qtype == B200Q_INT && sc->dtype == B200Q_BF16 && gs == nullptr && fast_paths_enabled()) {
+        ElemParams f{};
+        f.x = x; f.rows = rows; f.cols = cols; f.strategy = sc->strategy; f.group = g; f.bh = sc->block_h; f.bw = sc->block_w;
+        f.nbits = sc->num_bits; f.has_zp = sc->has_zp; f.scale = scale; f.zp = zp; f.gs = gs; f.out = out;
+        const int rc = launch_dequant_int8_fast(f, st);
+        if (rc != B200Q_ENOSYS) return rc;
     }
     if (op == EW_DEQUANT && sc->qtype == B200Q_FP8 && sc->dtype == B200Q_BF16 && zp == nullptr && gs == nullptr && fast_paths_enabled()) {
         const int rc = launch_decode_fp8_fast((const uint8_t*)x, rows, cols, sc->strategy, g, sc->block_h, sc->block_w, scale, out, st);
@@ -257,6 +272,10 @@ int b200q_quantize_pack(const void* x, int64_t batch, int64_t rows, int64_t cols
     p.has_zp = sc->has_zp; p.scale = const_cast<void*>(scale); p.zp_in = zp; p.gs = gs; p.gs_stride = 0; p.out = packed;
     if (sc->dtype == B200Q_BF16 && fast_paths_enabled() && tma_paths_enabled() && (sc->qtype == B200Q_FP8 || (sc->qtype == B200Q_INT && sc->num_bits == 4))) {
         const int rc = launch_group_tma_supplied(sc->qtype == B200Q_FP8 ? QT_FP8 : QT_INT, p, batch, (cudaStream_t)stream);
+        if (rc != B200Q_ENOSYS) return rc;
+    }
+    if (sc->dtype == B200Q_BF16 && fast_paths_enabled() && sc->qtype == B200Q_FP4 && sc->group_size == 16) {
+        const int rc = launch_nvfp4_supplied(p, batch, (cudaStream_t)stream);
         if (rc != B200Q_ENOSYS) return rc;
     }
     return dispatch_group<MODE_QUANT_PACK>(sc->dtype, sc->qtype, p, batch, (cudaStream_t)stream);

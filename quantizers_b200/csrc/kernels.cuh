@@ -33,6 +33,7 @@ bool tma_paths_enabled();
 int launch_group_fast(int qt, const GroupParams& p, int64_t batch, cudaStream_t st);
 int launch_block_fp8_fast(const TileParams& p, int64_t batch, cudaStream_t st);
 int launch_nvfp4_fast(const GroupParams& p, int64_t batch, cudaStream_t st);
+int launch_nvfp4_supplied(const GroupParams& p, int64_t batch, cudaStream_t st);  // caller's bf16 group scales + global scale (quantize_pack)
 int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_out, uint32_t* sync, cudaStream_t st);
 int64_t nvfp4_resident_workspace(int64_t batch, int64_t rows, int64_t cols);  // bytes of sync words the persistent kernel needs
 int launch_nvfp4_resident(const GroupParams& p, int64_t batch, int span, float* gs_out, uint32_t* sync, cudaStream_t st);
@@ -50,6 +51,9 @@ struct ElemParams {
 };
 enum : int { EW_QUANT = 0, EW_FQ = 1, EW_DEQUANT = 2 };
 int launch_elementwise(int op, int dt, int qt, const ElemParams& p, cudaStream_t st);
+// bf16 fast path (elementwise_fast.cu): quantize / fake_quantize, INT4 or FP8, qparam constant per aligned 8 elements; B200Q_ENOSYS otherwise
+int launch_elementwise_fast(int op, int qt, const ElemParams& p, cudaStream_t st);
+int launch_dequant_int8_fast(const ElemParams& p, cudaStream_t st);
 
 // ---- observers / qparams (observers.cu)
 int launch_minmax(int dt, const void* w, int64_t batch, int64_t rows, int64_t cols, int strategy, int group, int bh, int bw,

@@ -263,6 +263,60 @@ __global__ void __launch_bounds__(FP4_THREADS, 6) nvfp4_flat_kernel(const GroupP
         fp4_compress_tile<false>(table, gs, wbase, sbase, obase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, groups_per_mat);
 }
 
+// Caller-supplied group scales AND global scale (nvfp4 Compressor.compress with the module's weight_scale / weight_global_scale,
+// b200q_quantize_pack): the scale arrives in the weight dtype (CT keeps it as a Parameter of dtype T holding e4m3-representable
+// values).  A scale that is a positive finite e4m3 value takes the per-CTA table; anything else (zero, negative, not representable)
+// is quantized with the exact IEEE chain on s / gs.
+__global__ void __launch_bounds__(FP4_THREADS, 6) nvfp4_supplied_kernel(const GroupParams p, int64_t groups_per_mat, int tiles_per_mat) {
+    __shared__ Fp4Entry table[128];
+    const int64_t b = blockIdx.y;
+    const float gs = p.gs[p.gs_stride ? b : 0];
+    fp4_build_table(table, gs);
+    __syncthreads();
+    const uint4* wbase = reinterpret_cast<const uint4*>((const char*)p.w + b * groups_per_mat * 32);
+    const uint16_t* sbase = (const uint16_t*)p.scale + b * groups_per_mat;
+    uint2* obase = reinterpret_cast<uint2*>((uint8_t*)p.out + b * groups_per_mat * 8);
+    for (int tile = blockIdx.x; tile < tiles_per_mat; tile += gridDim.x) {
+        const int64_t g0 = (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x;
+        uint4 raw[FP4_UF][2];
+        uint32_t sbits[FP4_UF];
+        fp4_load_tile(raw, wbase, g0, groups_per_mat);
+#pragma unroll
+        for (int u = 0; u < FP4_UF; u++) {
+            const int64_t g = g0 + u * FP4_THREADS;
+            sbits[u] = g < groups_per_mat ? (uint32_t)__ldg(sbase + g) << 16 : 0x3f800000u;
+        }
+#pragma unroll
+        for (int u = 0; u < FP4_UF; u++) {
+            const int64_t g = g0 + u * FP4_THREADS;
+            if (g >= groups_per_mat) continue;
+            const float sf = __uint_as_float(sbits[u]);
+            const uint32_t code = cvt_e4m3x2(0.0f, sf) & 0xffu;
+            const bool tabulated = code >= 1u && code <= 0x7eu && e4m3_decode((uint8_t)code) == sf;
+            Fp4Entry e = table[tabulated ? code : 1u];
+            if (!tabulated) {  // the table's recipe (fp4_build_table) on this scale
+                e.s_eff = fdiv(sf, gs);
+                const float r = rcp_approx(e.s_eff);
+                e.r_lo = __fmul_rn(r, 0.99999952316284179688f);
+                e.r_hi = __fmul_rn(r, 1.00000047683715820312f);
+                e.unsafe = fp4_scale_is_safe(e.s_eff) ? 0.0f : 1.0f;
+            }
+            const f32x2 rl = pack2(e.r_lo, e.r_lo), rh = pack2(e.r_hi, e.r_hi);
+            uint32_t out[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const f32x2 x0 = bf16x2_to_f32x2(raw[u][h].x), x1 = bf16x2_to_f32x2(raw[u][h].y);
+                const f32x2 x2 = bf16x2_to_f32x2(raw[u][h].z), x3 = bf16x2_to_f32x2(raw[u][h].w);
+                uint32_t packed = cvt_e2m1x8(mul2_plus0(x0, rl), mul2_plus0(x1, rl), mul2_plus0(x2, rl), mul2_plus0(x3, rl));
+                const uint32_t diff = packed ^ cvt_e2m1x8(mul2_plus0(x0, rh), mul2_plus0(x1, rh), mul2_plus0(x2, rh), mul2_plus0(x3, rh));
+                if (diff != 0 || e.unsafe != 0.0f) packed = fix_group_fp4(raw[u][h], e.s_eff, packed);
+                out[h] = packed;
+            }
+            stg_stream(obase + g, make_uint2(out[0], out[1]));
+        }
+    }
+}
+
 // Global scale computed here: the whole-matrix |max| must be known before the first code is emitted, i.e. two passes over the
 // weight.  One launch does both.  Block A(s) = |max| items of sibling span s (matrices that share min(global_scale): gate/up
 // of one expert), block B(s) = compress items of span s; an item is FP4_NT consecutive tiles of one matrix.  CTAs are laid out
@@ -410,6 +464,20 @@ int launch_nvfp4_fast(const GroupParams& p, int64_t batch, cudaStream_t st) {
     int64_t gx = tiles;
     if (batch * tiles > 4 * want) gx = max((int64_t)1, min(tiles, (4 * want + batch - 1) / batch));
     nvfp4_flat_kernel<<<dim3((unsigned)gx, (unsigned)batch), FP4_THREADS, 0, st>>>(p, groups_per_mat, (int)tiles);
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+// bf16 weight, bf16 group scales [batch, rows, cols / 16], fp32 global scale(s): packed e2m1 codes only
+int launch_nvfp4_supplied(const GroupParams& p, int64_t batch, cudaStream_t st) {
+    if (p.cols % 16 != 0 || (((uintptr_t)p.w) & 15) != 0 || (((uintptr_t)p.scale) & 1) != 0 || batch * p.rows * p.cols == 0) return B200Q_ENOSYS;
+    const int64_t groups_per_mat = p.rows * (p.cols >> 4);
+    const int64_t tiles = (groups_per_mat + FP4_TILE_GROUPS - 1) / FP4_TILE_GROUPS;
+    if (batch > 65535 || tiles > (1ll << 30) || (((uintptr_t)p.out) & 7) != 0 || p.gs == nullptr) return B200Q_ENOSYS;
+    const int64_t want = (int64_t)kNumSMs * 8;
+    int64_t gx = tiles;
+    if (batch * tiles > 4 * want) gx = max((int64_t)1, min(tiles, (4 * want + batch - 1) / batch));
+    nvfp4_supplied_kernel<<<dim3((unsigned)gx, (unsigned)batch), FP4_THREADS, 0, st>>>(p, groups_per_mat, (int)tiles);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }

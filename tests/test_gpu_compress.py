@@ -420,3 +420,77 @@ def test_quantize_pack_with_foreign_qparams(name, rows, cols):
     got = ops.quantize_pack(torch.stack(ws).cuda(), torch.stack(scales).cuda(), zp_stack, args)
     for i in range(2):
         assert_bits_equal(got[i], packs[i], f"{name}[{i}]")
+
+
+@pytest.mark.parametrize("name", ["int4_g128_asym", "int4_g128_sym", "int4_g32_asym", "int4_channel_asym", "int4_channel_sym",
+                                  "fp8_channel", "fp8_g32", "fp8_block", "fp8_tensor"])
+@pytest.mark.parametrize("rows,cols", [(37, 768), (200, 384 + 8), (5, 128)])
+def test_quantize_fake_quantize_with_foreign_qparams(name, rows, cols):
+    """CT quantize / fake_quantize (bf16 fast path, elementwise_fast.cu) with qparams that are not this tensor's own statistics:
+    perturbed scales, random zero points (one outside [-8, 7]), zero / tiny / huge scales, the -0.0 row of synth_weight (a negative
+    value rounding to zero must dequantize to -0.0), ragged blocks and rows that are not a multiple of the 1024-column batch."""
+    from quantizers_b200 import ops
+
+    fmt, qtype, nb, sym, strat, g, blk = FORMATS[name]
+    if strat == O.GROUP and cols % g:
+        pytest.skip("columns not divisible by the group")
+    geom, args = geom_of(name), Args(name)
+    gen = torch.Generator().manual_seed(rows * 17 + cols)
+    w = synth_weight(rows, cols, torch.bfloat16, 91)
+    mn, mx = O.minmax(w, geom)
+    s, z = O.calculate_qparams(mn, mx, qtype, nb, sym)
+    s = (s.float() * (0.5 + 1.5 * torch.rand(s.shape, generator=gen))).to(torch.bfloat16)
+    if s.numel() > 3:
+        if strat != O.BLOCK:  # block (0, 0) holds synth_weight's zero rows: 0 / 0 is a NaN whose SIGN differs between x86 and the GPU
+            s.view(-1)[0] = 0.0
+        s.view(-1)[1] = 1e-35
+        s.view(-1)[-1] = 3.0e5
+    for use_zp in ((True, False) if qtype == O.INT else (True,)):
+        if qtype == O.INT:
+            zarg = None
+            if use_zp:
+                zarg = torch.randint(-8, 8, s.shape, generator=gen, dtype=torch.int8) if not sym else torch.zeros(s.shape, dtype=torch.int8)
+                if not sym and zarg.numel() > 2:
+                    zarg.view(-1)[2] = 40
+        else:
+            zarg = torch.zeros(s.shape, dtype=torch.float8_e4m3fn)
+        q_o = O.quantize(w, s, zarg, geom, qtype, nb)
+        q = ops.quantize(w.cuda(), s.cuda(), None if zarg is None else zarg.cuda(), args,
+                         dtype=torch.int8 if qtype == O.INT else torch.float8_e4m3fn)
+        assert_bits_equal(q, q_o, f"{name} quantize zp={use_zp}")
+        fq_o = O.fake_quantize(w, s, zarg, geom, qtype, nb)
+        fq = ops.fake_quantize(w.cuda(), s.cuda(), None if zarg is None else zarg.cuda(), args)
+        assert_bits_equal(fq, fq_o, f"{name} fake_quantize zp={use_zp}")
+        if qtype == O.INT:  # un-packed int8 codes -> bf16 (full int8 range, not only the 4-bit codes)
+            codes = torch.randint(-128, 128, (rows, cols), generator=gen, dtype=torch.int8)
+            dq_o = O.dequantize(codes, s, zarg, geom, qtype)
+            dq = ops.dequantize(codes.cuda(), s.cuda(), None if zarg is None else zarg.cuda(), args)
+            assert_bits_equal(dq, dq_o, f"{name} dequantize zp={use_zp}")
+
+
+@pytest.mark.parametrize("rows,cols", [(37, 768), (64, 2560), (3, 16)])
+def test_nvfp4_quantize_pack_with_foreign_scales(rows, cols):
+    """nvfp4 Compressor.compress's arithmetic with the module's own weight_scale / weight_global_scale: group scales that are NOT what
+    this weight's |max| would give (neighbouring e4m3 codes), a zero scale, a value that is not an e4m3 number, stacked matrices."""
+    from quantizers_b200 import ops
+
+    geom, args = geom_of("nvfp4"), Args("nvfp4")
+    gen = torch.Generator().manual_seed(rows + cols)
+    ws = [synth_weight(rows, cols, torch.bfloat16, 70 + i) for i in range(2)]
+    gs = O.generate_gparam(min(float(w.float().min()) for w in ws), max(float(w.float().max()) for w in ws), torch.bfloat16)
+    packs, scales = [], []
+    for w in ws:
+        mn, mx = O.minmax(w, geom)
+        s, _ = O.calculate_qparams(mn, mx, O.FP4, 4, True, gs)           # fp32 values of e4m3 codes
+        codes = s.to(torch.float8_e4m3fn).view(torch.uint8).to(torch.int16)
+        codes = (codes + torch.randint(-2, 3, codes.shape, generator=gen, dtype=torch.int16)).clamp(1, 0x7e).to(torch.uint8)
+        s = codes.view(torch.float8_e4m3fn).to(torch.bfloat16)
+        s.view(-1)[0] = 0.0
+        if s.numel() > 2:
+            s.view(-1)[1] = 0.3          # not an e4m3 value
+        q_o = O.quantize(w, s, torch.zeros(s.shape, dtype=torch.float8_e4m3fn), geom, O.FP4, 4, gs)
+        packs.append(q_o[:, 0::2] | (q_o[:, 1::2] << 4))
+        scales.append(s)
+    got = ops.quantize_pack(torch.stack(ws).cuda(), torch.stack(scales).cuda(), None, args, global_scale=gs.cuda())
+    for i in range(2):
+        assert_bits_equal(got[i], packs[i], f"nvfp4[{i}]")
