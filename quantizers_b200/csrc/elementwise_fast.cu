@@ -22,6 +22,8 @@ namespace {
 using namespace fast;
 using fp4::cvt_e4m3x2;
 
+constexpr int EW_PACK = 3;  // INT4 only: quantize + pack_to_int32 (offset-binary nibbles, 8 per word)
+
 struct EwFast {
     const uint4* x;
     const uint16_t* scale;
@@ -49,7 +51,9 @@ __device__ __noinline__ uint4 exact_chunk(const uint4 raw, float s, float z, boo
 #pragma unroll 1
     for (int e = 0; e < 8; e++) {
         const float x = __uint_as_float((e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16));
-        if (OP == EW_QUANT) {
+        if (OP == EW_PACK) {
+            o[0] |= ((uint32_t)(quant_int<DT_BF16>(x, s, z, use_zp, -8.0f, 7.0f) + 8) & 0xfu) << (4 * e);
+        } else if (OP == EW_QUANT) {
             uint32_t c;
             if (QT == QT_INT) c = (uint32_t)quant_int<DT_BF16>(x, s, z, use_zp, -8.0f, 7.0f) & 0xffu;
             else c = quant_fp8<DT_BF16>(x, s, use_zp);
@@ -133,13 +137,17 @@ __global__ void __launch_bounds__(256) elementwise_fast_kernel(const EwFast p) {
                 }
                 uint4 o;
                 if (OP == EW_FQ) o = make_uint4(y[0], y[1], y[2], y[3]);
-                else if (QT == QT_INT) {
+                else if (OP == EW_PACK) {
+                    const uint32_t x01 = prmt(h[0], h[1], 0x6420), x23 = prmt(h[2], h[3], 0x6420);  // code + 8 is the stored nibble
+                    o = make_uint4(prmt(fold_nibbles(x01), fold_nibbles(x23), 0x6420), 0u, 0u, 0u);
+                } else if (QT == QT_INT) {
                     // code + 8 -> two's-complement nibble (xor 8) -> sign-extended byte (bit 3 * 0x1e fills the high nibble)
                     const uint32_t n01 = prmt(h[0], h[1], 0x6420) ^ 0x08080808u, n23 = prmt(h[2], h[3], 0x6420) ^ 0x08080808u;
                     o = make_uint4(n01 | ((n01 & 0x08080808u) * 0x1eu), n23 | ((n23 & 0x08080808u) * 0x1eu), 0u, 0u);
                 } else o = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), 0u, 0u);
                 if (diff != 0 || unsafe) o = exact_chunk<QT, OP>(v[u], s, z, ZP);
-                if (OP == EW_FQ) stg_stream((uint4*)p.out + row * p.cpr + c, o);
+                if (OP == EW_PACK) stg_stream((uint32_t*)p.out + row * p.cpr + c, o.x);
+                else if (OP == EW_FQ) stg_stream((uint4*)p.out + row * p.cpr + c, o);
                 else stg_stream((uint2*)p.out + row * p.cpr + c, make_uint2(o.x, o.y));
             }
         }
@@ -234,7 +242,8 @@ static bool ew_geometry(const ElemParams& e, EwFast& p) {
 
 // bf16, no global scale; INT4 (codes as int8) or FP8; op EW_QUANT / EW_FQ.  B200Q_ENOSYS when the scheme / shape is not covered.
 int launch_elementwise_fast(int op, int qt, const ElemParams& e, cudaStream_t st) {
-    if (op != EW_QUANT && op != EW_FQ) return B200Q_ENOSYS;
+    if (op != EW_QUANT && op != EW_FQ && op != EW_PACK) return B200Q_ENOSYS;
+    if (op == EW_PACK && qt != QT_INT) return B200Q_ENOSYS;
     if (e.gs != nullptr || e.cols % 8 != 0 || e.cols >= (1ll << 33) || e.rows * e.cols == 0) return B200Q_ENOSYS;
     if ((((uintptr_t)e.x) & 15) != 0 || (((uintptr_t)e.out) & 15) != 0 || (((uintptr_t)e.scale) & 1) != 0) return B200Q_ENOSYS;
     if (!(qt == QT_FP8 || (qt == QT_INT && e.nbits == 4))) return B200Q_ENOSYS;
@@ -242,6 +251,7 @@ int launch_elementwise_fast(int op, int qt, const ElemParams& e, cudaStream_t st
     if (!ew_geometry(e, p)) return B200Q_ENOSYS;
     const bool zp = qt == QT_INT ? e.zp != nullptr : e.has_zp != 0;
     if (qt == QT_INT) {
+        if (op == EW_PACK) return zp ? launch_variant<QT_INT, EW_PACK, true>(p, st) : launch_variant<QT_INT, EW_PACK, false>(p, st);
         if (op == EW_QUANT) return zp ? launch_variant<QT_INT, EW_QUANT, true>(p, st) : launch_variant<QT_INT, EW_QUANT, false>(p, st);
         return zp ? launch_variant<QT_INT, EW_FQ, true>(p, st) : launch_variant<QT_INT, EW_FQ, false>(p, st);
     }
