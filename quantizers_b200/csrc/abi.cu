@@ -233,6 +233,14 @@ static int elementwise(int op, const void* x, int64_t rows, int64_t cols, const 
         const int rc = launch_elementwise_fast(op, sc->qtype, f, st);
         if (rc != B200Q_ENOSYS) return rc;
     }
+    if (ew_fast && op != EW_DEQUANT && sc->qtype == B200Q_FP4 && sc->dtype == B200Q_BF16 && sc->strategy == B200Q_GROUP && g == 16 && gs != nullptr &&
+        vec_ok && cols % 16 == 0 && fast_paths_enabled()) {
+        GroupParams p{};
+        p.w = x; p.rows = rows; p.cols = cols; p.group = 16; p.nbits = 4; p.symmetric = 1; p.has_zp = sc->has_zp;
+        p.scale = const_cast<void*>(scale); p.gs = gs; p.gs_stride = 0; p.out = out;
+        const int rc = launch_nvfp4_supplied(p, 1, st, op == EW_QUANT ? 1 : 2);
+        if (rc != B200Q_ENOSYS) return rc;
+    }
     if (op != EW_DEQUANT && sc->strategy == B200Q_GROUP && vec_ok && (g == 16 || g == 32 || g == 64 || g == 128 || g == 256) &&
         cols % g == 0 && (sc->qtype != B200Q_FP4 || gs != nullptr)) {
         GroupParams p{};

@@ -33,7 +33,7 @@ bool tma_paths_enabled();
 int launch_group_fast(int qt, const GroupParams& p, int64_t batch, cudaStream_t st);
 int launch_block_fp8_fast(const TileParams& p, int64_t batch, cudaStream_t st);
 int launch_nvfp4_fast(const GroupParams& p, int64_t batch, cudaStream_t st);
-int launch_nvfp4_supplied(const GroupParams& p, int64_t batch, cudaStream_t st);  // caller's bf16 group scales + global scale (quantize_pack)
+int launch_nvfp4_supplied(const GroupParams& p, int64_t batch, cudaStream_t st, int op = 0);  // caller's bf16 group scales + global scale; op 0 pack, 1 quantize (values), 2 fake_quantize
 int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_out, uint32_t* sync, cudaStream_t st);
 int64_t nvfp4_resident_workspace(int64_t batch, int64_t rows, int64_t cols);  // bytes of sync words the persistent kernel needs
 int launch_nvfp4_resident(const GroupParams& p, int64_t batch, int span, float* gs_out, uint32_t* sync, cudaStream_t st);

@@ -267,6 +267,13 @@ __global__ void __launch_bounds__(FP4_THREADS, 6) nvfp4_flat_kernel(const GroupP
 // b200q_quantize_pack): the scale arrives in the weight dtype (CT keeps it as a Parameter of dtype T holding e4m3-representable
 // values).  A scale that is a positive finite e4m3 value takes the per-CTA table; anything else (zero, negative, not representable)
 // is quantized with the exact IEEE chain on s / gs.
+// OP 0: packed e2m1 codes (quantize_pack); 1: CT quantize -- the e2m1 grid VALUES in bf16 (-0.0 for a negative that rounds to zero);
+// 2: CT fake_quantize -- bf16(value * (scale / global_scale)) (forward.py:149-181 with forward_helpers.py:255-266 in fp32).
+__device__ __forceinline__ void e2m1x2_to_f32(uint32_t one_byte, float& lo, float& hi) {
+    asm("{ .reg .b8 t; .reg .b16 u, l, h; .reg .b32 r; cvt.u16.u32 u, %2; cvt.u8.u16 t, u; cvt.rn.f16x2.e2m1x2 r, t; mov.b32 {l, h}, r; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }"
+        : "=f"(lo), "=f"(hi) : "r"(one_byte));
+}
+template <int OP>
 __global__ void __launch_bounds__(FP4_THREADS, 6) nvfp4_supplied_kernel(const GroupParams p, int64_t groups_per_mat, int tiles_per_mat) {
     __shared__ Fp4Entry table[128];
     const int64_t b = blockIdx.y;
@@ -311,8 +318,18 @@ __global__ void __launch_bounds__(FP4_THREADS, 6) nvfp4_supplied_kernel(const Gr
                 const uint32_t diff = packed ^ cvt_e2m1x8(mul2_plus0(x0, rh), mul2_plus0(x1, rh), mul2_plus0(x2, rh), mul2_plus0(x3, rh));
                 if (diff != 0 || e.unsafe != 0.0f) packed = fix_group_fp4(raw[u][h], e.s_eff, packed);
                 out[h] = packed;
+                if (OP != 0) {
+                    uint32_t y[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        float lo, hi;
+                        e2m1x2_to_f32((packed >> (8 * k)) & 0xffu, lo, hi);
+                        y[k] = OP == 1 ? cvt_bf16x2(hi, lo) : cvt_bf16x2(__fmul_rn(hi, e.s_eff), __fmul_rn(lo, e.s_eff));
+                    }
+                    stg_stream(reinterpret_cast<uint4*>((uint16_t*)p.out + b * groups_per_mat * 16) + 2 * g + h, make_uint4(y[0], y[1], y[2], y[3]));
+                }
             }
-            stg_stream(obase + g, make_uint2(out[0], out[1]));
+            if (OP == 0) stg_stream(obase + g, make_uint2(out[0], out[1]));
         }
     }
 }
@@ -468,8 +485,8 @@ int launch_nvfp4_fast(const GroupParams& p, int64_t batch, cudaStream_t st) {
     return B200Q_OK;
 }
 
-// bf16 weight, bf16 group scales [batch, rows, cols / 16], fp32 global scale(s): packed e2m1 codes only
-int launch_nvfp4_supplied(const GroupParams& p, int64_t batch, cudaStream_t st) {
+// bf16 weight, bf16 group scales [batch, rows, cols / 16], fp32 global scale(s); op 0: packed e2m1 codes, 1: grid values (bf16), 2: fake_quantize (bf16)
+int launch_nvfp4_supplied(const GroupParams& p, int64_t batch, cudaStream_t st, int op) {
     if (p.cols % 16 != 0 || (((uintptr_t)p.w) & 15) != 0 || (((uintptr_t)p.scale) & 1) != 0 || batch * p.rows * p.cols == 0) return B200Q_ENOSYS;
     const int64_t groups_per_mat = p.rows * (p.cols >> 4);
     const int64_t tiles = (groups_per_mat + FP4_TILE_GROUPS - 1) / FP4_TILE_GROUPS;
@@ -477,7 +494,11 @@ int launch_nvfp4_supplied(const GroupParams& p, int64_t batch, cudaStream_t st) 
     const int64_t want = (int64_t)kNumSMs * 8;
     int64_t gx = tiles;
     if (batch * tiles > 4 * want) gx = max((int64_t)1, min(tiles, (4 * want + batch - 1) / batch));
-    nvfp4_supplied_kernel<<<dim3((unsigned)gx, (unsigned)batch), FP4_THREADS, 0, st>>>(p, groups_per_mat, (int)tiles);
+    if (op != 0 && (((uintptr_t)p.out) & 15) != 0) return B200Q_ENOSYS;
+    const dim3 grid((unsigned)gx, (unsigned)batch);
+    if (op == 0) nvfp4_supplied_kernel<0><<<grid, FP4_THREADS, 0, st>>>(p, groups_per_mat, (int)tiles);
+    else if (op == 1) nvfp4_supplied_kernel<1><<<grid, FP4_THREADS, 0, st>>>(p, groups_per_mat, (int)tiles);
+    else nvfp4_supplied_kernel<2><<<grid, FP4_THREADS, 0, st>>>(p, groups_per_mat, (int)tiles);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }

@@ -491,6 +491,13 @@ def test_nvfp4_quantize_pack_with_foreign_scales(rows, cols):
         q_o = O.quantize(w, s, torch.zeros(s.shape, dtype=torch.float8_e4m3fn), geom, O.FP4, 4, gs)
         packs.append(q_o[:, 0::2] | (q_o[:, 1::2] << 4))
         scales.append(s)
+        # CT quantize (grid values in bf16, -0.0 kept) and fake_quantize with the same foreign scales
+        vals = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0])[(q_o & 7).long()] * torch.where((q_o & 8) > 0, -1.0, 1.0)
+        zfp8 = torch.zeros(s.shape, dtype=torch.float8_e4m3fn)
+        q = ops.quantize(w.cuda(), s.cuda(), zfp8.cuda(), args, global_scale=gs.cuda())
+        assert_bits_equal(q, vals.to(torch.bfloat16), "nvfp4 quantize values")
+        fq = ops.fake_quantize(w.cuda(), s.cuda(), zfp8.cuda(), args, global_scale=gs.cuda())
+        assert_bits_equal(fq, O.fake_quantize(w, s, zfp8, geom, O.FP4, 4, gs), "nvfp4 fake_quantize")
     got = ops.quantize_pack(torch.stack(ws).cuda(), torch.stack(scales).cuda(), None, args, global_scale=gs.cuda())
     for i in range(2):
         assert_bits_equal(got[i], packs[i], f"nvfp4[{i}]")
