@@ -476,10 +476,11 @@ int launch_nvfp4_fast(const GroupParams& p, int64_t batch, cudaStream_t st) {
     // every matrix must start 16-byte aligned in the weight and 8-byte aligned in the packed output: groups_per_mat * 32 / * 8 do
     const int64_t tiles = (groups_per_mat + FP4_TILE_GROUPS - 1) / FP4_TILE_GROUPS;
     if (batch > 65535 || tiles > (1ll << 30) || (((uintptr_t)p.out) & 7) != 0) return B200Q_ENOSYS;
-    // enough CTAs to fill the machine (8 resident per SM) without rebuilding the table more often than once per ~32 KB
-    const int64_t want = (int64_t)kNumSMs * 8;
+    // enough CTAs to fill the machine without rebuilding the table more often than once per ~32 KB
+    // whole waves of the kernel's residency (launch bounds: 6 CTAs per SM), rounded DOWN so that no straggler wave is left
+    const int64_t want = (int64_t)kNumSMs * 6;
     int64_t gx = tiles;
-    if (batch * tiles > 4 * want) gx = max((int64_t)1, min(tiles, (4 * want + batch - 1) / batch));
+    if (batch * tiles > 4 * want) gx = max((int64_t)1, min(tiles, 4 * want / batch));
     nvfp4_flat_kernel<<<dim3((unsigned)gx, (unsigned)batch), FP4_THREADS, 0, st>>>(p, groups_per_mat, (int)tiles);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
@@ -491,9 +492,10 @@ int launch_nvfp4_supplied(const GroupParams& p, int64_t batch, cudaStream_t st, 
     const int64_t groups_per_mat = p.rows * (p.cols >> 4);
     const int64_t tiles = (groups_per_mat + FP4_TILE_GROUPS - 1) / FP4_TILE_GROUPS;
     if (batch > 65535 || tiles > (1ll << 30) || (((uintptr_t)p.out) & 7) != 0 || p.gs == nullptr) return B200Q_ENOSYS;
-    const int64_t want = (int64_t)kNumSMs * 8;
+    // whole waves of the kernel's residency (launch bounds: 6 CTAs per SM), rounded DOWN so that no straggler wave is left
+    const int64_t want = (int64_t)kNumSMs * 6;
     int64_t gx = tiles;
-    if (batch * tiles > 4 * want) gx = max((int64_t)1, min(tiles, (4 * want + batch - 1) / batch));
+    if (batch * tiles > 4 * want) gx = max((int64_t)1, min(tiles, 4 * want / batch));
     if (op != 0 && (((uintptr_t)p.out) & 15) != 0) return B200Q_ENOSYS;
     const dim3 grid((unsigned)gx, (unsigned)batch);
     if (op == 0) nvfp4_supplied_kernel<0><<<grid, FP4_THREADS, 0, st>>>(p, groups_per_mat, (int)tiles);

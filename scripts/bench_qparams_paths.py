@@ -12,7 +12,7 @@ dev = torch.device("cuda", 0)
 peak = 6549.4
 w = synth_stack(list(range(8)), 9728, 2560, 0, dev).reshape(-1, 2560).contiguous()
 n = w.numel()
-names = sys.argv[1:] or ["W4A16", "W4A16_ASYM", "INT4_G32_SYM", "FP8_BLOCK", "FP8_CHANNEL", "FP8_G32", "NVFP4"]
+names = [a for a in sys.argv[1:] if a != "PACK"] or ([] if sys.argv[1:] else ["W4A16", "W4A16_ASYM", "INT4_G32_SYM", "FP8_BLOCK", "FP8_CHANNEL", "FP8_G32", "NVFP4"])
 rows = []
 
 
@@ -61,6 +61,16 @@ for name in names:
     if q is not None and not (a.type == "float" and a.num_bits == 4):
         timed(f"{name} dequantize", q.numel() * q.element_size() + n * 2,
               lambda: ops.dequantize(q, scale, zp, args=a, dtype=torch.bfloat16))
+if not sys.argv[1:] or "PACK" in sys.argv[1:]:
+    # stand-alone pack helpers (Q7 / Q8 / Q9): only reached when a caller packs codes it already holds -- the patched compressors
+    # go through quantize_pack / the fused decompress kernels instead
+    codes = torch.randint(-8, 8, w.shape, dtype=torch.int8, device=dev)
+    packed = timed("pack_to_int32 (int8 codes, 4 bit)", n * 1.5, lambda: ops.pack_to_int32(codes, 4))
+    timed("unpack_from_int32 (4 bit)", n * 1.5, lambda: ops.unpack_from_int32(packed, 4, w.shape))
+    vals = ops.quantize(w[:, :], *(lambda sd: (sd["weight_scale"].to(torch.bfloat16), None))(ops.compress_weight(w, PRESETS["NVFP4"])), PRESETS["NVFP4"],
+                        global_scale=ops.weight_global_scales(w))
+    p4 = timed("pack_fp4_to_uint8 (bf16 grid values)", n * 2.5, lambda: ops.pack_fp4_to_uint8(vals))
+    timed("unpack_fp4_from_uint8 (-> bf16)", n * 2.5, lambda: ops.unpack_fp4_from_uint8(p4, w.shape[0], w.shape[1], torch.bfloat16))
 os.makedirs("gpurun_out", exist_ok=True)
 tag = os.environ.get("B200Q_BENCH_TAG", "")
 json.dump({"matrix": list(w.shape), "rows": rows}, open(f"gpurun_out/qparams_paths{'_' + tag if tag else ''}.json", "w"), indent=1)

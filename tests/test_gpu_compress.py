@@ -501,3 +501,28 @@ def test_nvfp4_quantize_pack_with_foreign_scales(rows, cols):
     got = ops.quantize_pack(torch.stack(ws).cuda(), torch.stack(scales).cuda(), None, args, global_scale=gs.cuda())
     for i in range(2):
         assert_bits_equal(got[i], packs[i], f"nvfp4[{i}]")
+
+
+def test_flat_pack_unpack_fast_paths():
+    """pack_to_int32 / unpack_from_int32 (4 bit, along the columns) and pack_fp4_to_uint8 / unpack_fp4_from_uint8 (bf16) on shapes that
+    take the flat vectorised kernels, including int8 codes outside [-8, 7] (the reference sums the shifted bytes un-masked) and NVFP4 inputs that
+    are not e2m1 grid points (first-minimum search in bf16), against the oracle."""
+    from quantizers_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    for R, C in [(16, 24), (37, 768), (128, 2560), (4, 8)]:
+        v = torch.randint(-8, 8, (R, C), generator=g, dtype=torch.int8)
+        p = ops.pack_to_int32(v.cuda(), 4)
+        assert_bits_equal(p, O.pack_to_int32(v, 4), f"pack {R}x{C}")
+        assert torch.equal(ops.unpack_from_int32(p, 4, v.shape).cpu(), v)
+        assert_bits_equal(ops.unpack_from_int32(p, 4, v.shape), O.unpack_from_int32(O.pack_to_int32(v, 4), 4, (R, C)), f"unpack {R}x{C}")
+        wild = torch.randint(-128, 128, (R, C), generator=g, dtype=torch.int8)
+        assert_bits_equal(ops.pack_to_int32(wild.cuda(), 4), O.pack_to_int32(wild, 4), f"pack wild {R}x{C}")
+        grid = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0])
+        x = (grid[torch.randint(0, 8, (R, C), generator=g)] * torch.where(torch.rand(R, C, generator=g) < 0.5, -1.0, 1.0)).to(torch.bfloat16)
+        pk = ops.pack_fp4_to_uint8(x.cuda())
+        assert_bits_equal(pk, O.pack_fp4_to_uint8(x), f"pack_fp4 {R}x{C}")
+        assert_bits_equal(ops.unpack_fp4_from_uint8(pk, R, C, torch.bfloat16), x, f"unpack_fp4 {R}x{C}")
+        off = (torch.randn(R, C, generator=g) * 3).to(torch.bfloat16)   # off-grid, some beyond +-6
+        off[0, 0] = -0.0
+        assert_bits_equal(ops.pack_fp4_to_uint8(off.cuda()), O.pack_fp4_to_uint8(off), f"pack_fp4 off-grid {R}x{C}")
