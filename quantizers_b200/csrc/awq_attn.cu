@@ -7,6 +7,7 @@
 //     y   = bf16(w * vn)
 //     out = bf16( bf16(y * cos) + bf16(rotate_half(y) * sin) )
 // One warp per (token, head): a lane owns d/32 consecutive elements; rotate_half's partner (i +- d/2) lives in lane ^ 16.
+#include <cstdlib>
 #include "../../include/b200q.h"
 #include "common.cuh"
 
@@ -16,8 +17,9 @@ namespace {
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
 
+// one vector per warp per step (the first version; kept as the B200Q_ROPE_BATCH=1 reference schedule)
 template <int EPL>  // elements per lane: 2 (d = 64) or 4 (d = 128)
-__global__ void __launch_bounds__(256) qk_norm_rope_kernel(uint16_t* __restrict__ qkv, int64_t tokens, int n_heads, int n_kv, int seq_len,
+__global__ void __launch_bounds__(256) qk_norm_rope_v1_kernel(uint16_t* __restrict__ qkv, int64_t tokens, int n_heads, int n_kv, int seq_len,
                                                            const uint16_t* __restrict__ qw, const uint16_t* __restrict__ kw,
                                                            const uint16_t* __restrict__ cosb, const uint16_t* __restrict__ sinb, float eps) {
     constexpr int D = EPL * 32;
@@ -80,6 +82,83 @@ __global__ void __launch_bounds__(256) qk_norm_rope_kernel(uint16_t* __restrict_
     }
 }
 
+// U (token, head) vectors per warp per step: the loads of all U vectors (row, cos, sin) are issued before the first shuffle.  With
+// U = 1 a warp has 256 bytes in flight and the kernel is latency-bound at ~2 TB/s (ptxas cannot hoist the next vector's loads across
+// the shuffles); the arithmetic per vector is unchanged.
+template <int EPL, int U>  // EPL: elements per lane: 2 (d = 64) or 4 (d = 128)
+__global__ void __launch_bounds__(256) qk_norm_rope_kernel(uint16_t* __restrict__ qkv, int64_t tokens, int n_heads, int n_kv, int seq_len,
+                                                           const uint16_t* __restrict__ qw, const uint16_t* __restrict__ kw,
+                                                           const uint16_t* __restrict__ cosb, const uint16_t* __restrict__ sinb, float eps) {
+    constexpr int D = EPL * 32;
+    constexpr int W = EPL / 2;  // 32-bit words per lane
+    const int lane = threadIdx.x & 31;
+    const int hq = n_heads + n_kv;
+    const int64_t n_vec = tokens * (int64_t)hq;
+    const int64_t row_elems = (int64_t)(n_heads + 2 * n_kv) * D;
+    const int64_t vstride = (int64_t)gridDim.x * 8;
+    // the norm weights depend only on (q or k, lane): both loaded once
+    uint32_t wq[W], wk[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        wq[i] = *reinterpret_cast<const uint32_t*>(qw + lane * EPL + 2 * i);
+        wk[i] = *reinterpret_cast<const uint32_t*>(kw + lane * EPL + 2 * i);
+    }
+    for (int64_t vec0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); vec0 < n_vec; vec0 += vstride * U) {  // warp-uniform
+        uint32_t raw[U][W], cr[U][W], sr[U][W];
+        uint16_t* ptr[U];
+        bool isq[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t vec = min(vec0 + u * vstride, n_vec - 1);  // out-of-range slots recompute the last vector and store nothing
+            const int64_t t = vec / hq;
+            const int h = (int)(vec - t * hq);  // heads 0..H-1 are q, H..H+Hkv-1 are k
+            isq[u] = h < n_heads;
+            ptr[u] = qkv + t * row_elems + (int64_t)h * D + lane * EPL;
+            const int64_t pos = (t % seq_len) * D + lane * EPL;
+#pragma unroll
+            for (int i = 0; i < W; i++) {
+                raw[u][i] = *reinterpret_cast<const uint32_t*>(ptr[u] + 2 * i);
+                cr[u][i] = __ldg(reinterpret_cast<const uint32_t*>(cosb + pos + 2 * i));
+                sr[u][i] = __ldg(reinterpret_cast<const uint32_t*>(sinb + pos + 2 * i));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            float x[EPL], ss = 0.0f;
+#pragma unroll
+            for (int i = 0; i < EPL; i++) {
+                x[i] = bf16_bits_to_float((raw[u][i >> 1] >> (16 * (i & 1))) & 0xffffu);
+                ss = __fadd_rn(ss, __fmul_rn(x[i], x[i]));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
+            const float r = rsqrtf(__fadd_rn(__fdiv_rn(ss, (float)D), eps));
+            float y[EPL], out[EPL];
+#pragma unroll
+            for (int i = 0; i < EPL; i++) {
+                const uint32_t wr = isq[u] ? wq[i >> 1] : wk[i >> 1];
+                const float w = bf16_bits_to_float((wr >> (16 * (i & 1))) & 0xffffu);
+                y[i] = bf16r(__fmul_rn(w, bf16r(__fmul_rn(x[i], r))));
+            }
+#pragma unroll
+            for (int i = 0; i < EPL; i++) {
+                const float partner = __shfl_xor_sync(0xffffffffu, y[i], 16);
+                const float rot = lane < 16 ? -partner : partner;  // first half: -x[i + d/2]; second half: x[i - d/2]
+                const float c = bf16_bits_to_float((cr[u][i >> 1] >> (16 * (i & 1))) & 0xffffu);
+                const float s = bf16_bits_to_float((sr[u][i >> 1] >> (16 * (i & 1))) & 0xffffu);
+                out[i] = __fadd_rn(bf16r(__fmul_rn(y[i], c)), bf16r(__fmul_rn(rot, s)));
+            }
+            if (vec0 + u * vstride < n_vec) {
+#pragma unroll
+                for (int i = 0; i < W; i++) {
+                    __nv_bfloat162 hv = __floats2bfloat162_rn(out[2 * i], out[2 * i + 1]);
+                    *reinterpret_cast<uint32_t*>(ptr[u] + 2 * i) = *reinterpret_cast<uint32_t*>(&hv);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 }  // namespace b200q
 
@@ -95,14 +174,22 @@ extern "C" int b200q_qk_norm_rope(void* qkv, int64_t tokens, int32_t n_heads, in
                   "pointers must be 8-byte aligned");
     if (tokens == 0) return B200Q_OK;
     const int64_t n_vec = tokens * (int64_t)(n_heads + n_kv);
-    const int grid = (int)min((n_vec + 7) / 8, (int64_t)kNumSMs * 16);
     cudaStream_t st = (cudaStream_t)stream;
-    if (head_dim == 128)
-        qk_norm_rope_kernel<4><<<grid, 256, 0, st>>>((uint16_t*)qkv, tokens, n_heads, n_kv, seq_len, (const uint16_t*)q_norm_weight,
-                                                     (const uint16_t*)k_norm_weight, (const uint16_t*)cos, (const uint16_t*)sin, eps);
-    else
-        qk_norm_rope_kernel<2><<<grid, 256, 0, st>>>((uint16_t*)qkv, tokens, n_heads, n_kv, seq_len, (const uint16_t*)q_norm_weight,
-                                                     (const uint16_t*)k_norm_weight, (const uint16_t*)cos, (const uint16_t*)sin, eps);
+    // B200Q_ROPE_BATCH=1 selects the one-vector-per-step schedule (A/B switch); the batched grid is one wave of the kernel's residency
+    static const int batch = [] { const char* v = getenv("B200Q_ROPE_BATCH"); return (v && v[0] == '1') ? 1 : 4; }();
+#define B200Q_ROPE(EPL_, U_) do { \
+        static const int per = [] { int n = 0; return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, qk_norm_rope_kernel<EPL_, U_>, 256, 0) == cudaSuccess && n > 0) ? n : 2; }(); \
+        const int grid = (int)min((n_vec + 8 * U_ - 1) / (8 * U_), (int64_t)kNumSMs * per); \
+        qk_norm_rope_kernel<EPL_, U_><<<grid, 256, 0, st>>>((uint16_t*)qkv, tokens, n_heads, n_kv, seq_len, (const uint16_t*)q_norm_weight, \
+                                                        (const uint16_t*)k_norm_weight, (const uint16_t*)cos, (const uint16_t*)sin, eps); } while (0)
+#define B200Q_ROPE_V1(EPL_) do { \
+        const int grid = (int)min((n_vec + 7) / 8, (int64_t)kNumSMs * 16); \
+        qk_norm_rope_v1_kernel<EPL_><<<grid, 256, 0, st>>>((uint16_t*)qkv, tokens, n_heads, n_kv, seq_len, (const uint16_t*)q_norm_weight, \
+                                                       (const uint16_t*)k_norm_weight, (const uint16_t*)cos, (const uint16_t*)sin, eps); } while (0)
+    if (head_dim == 128) { if (batch == 1) B200Q_ROPE_V1(4); else B200Q_ROPE(4, 4); }
+    else { if (batch == 1) B200Q_ROPE_V1(2); else B200Q_ROPE(2, 4); }
+#undef B200Q_ROPE_V1
+#undef B200Q_ROPE
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }

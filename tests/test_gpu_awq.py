@@ -226,7 +226,7 @@ def test_compute_best_scale_fused_attention_parent():
         assert res[fused][1] == r_ref
 
 
-@pytest.mark.parametrize("H,HKV,D,S,B", [(4, 2, 64, 64, 3), (32, 8, 128, 512, 2)])
+@pytest.mark.parametrize("H,HKV,D,S,B", [(4, 2, 64, 64, 3), (32, 8, 128, 512, 2), (5, 1, 128, 70, 1), (3, 1, 64, 33, 5)])
 def test_qk_norm_rope_vs_eager(H, HKV, D, S, B):
     """In-place q/k RMSNorm + RoPE kernel against the eager bf16 op chain of transformers' Qwen3Attention."""
     from quantizers_b200 import awq
