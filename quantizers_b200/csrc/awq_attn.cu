@@ -17,7 +17,7 @@ namespace {
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
 
-// one vector per warp per step (the first version; kept as the B200Q_ROPE_BATCH=1 reference schedule)
+// one vector per warp per step (default)
 template <int EPL>  // elements per lane: 2 (d = 64) or 4 (d = 128)
 __global__ void __launch_bounds__(256) qk_norm_rope_v1_kernel(uint16_t* __restrict__ qkv, int64_t tokens, int n_heads, int n_kv, int seq_len,
                                                            const uint16_t* __restrict__ qw, const uint16_t* __restrict__ kw,
@@ -82,9 +82,8 @@ __global__ void __launch_bounds__(256) qk_norm_rope_v1_kernel(uint16_t* __restri
     }
 }
 
-// U (token, head) vectors per warp per step: the loads of all U vectors (row, cos, sin) are issued before the first shuffle.  With
-// U = 1 a warp has 256 bytes in flight and the kernel is latency-bound at ~2 TB/s (ptxas cannot hoist the next vector's loads across
-// the shuffles); the arithmetic per vector is unchanged.
+// Experiment (B200Q_ROPE_BATCH=4): U (token, head) vectors per warp per step, the loads of all U vectors (row, cos, sin) issued before the
+// first shuffle; the arithmetic per vector is unchanged.  Measured SLOWER than the one-vector schedule (365 vs 323 us): not latency-bound.
 template <int EPL, int U>  // EPL: elements per lane: 2 (d = 64) or 4 (d = 128)
 __global__ void __launch_bounds__(256) qk_norm_rope_kernel(uint16_t* __restrict__ qkv, int64_t tokens, int n_heads, int n_kv, int seq_len,
                                                            const uint16_t* __restrict__ qw, const uint16_t* __restrict__ kw,
@@ -175,8 +174,10 @@ extern "C" int b200q_qk_norm_rope(void* qkv, int64_t tokens, int32_t n_heads, in
     if (tokens == 0) return B200Q_OK;
     const int64_t n_vec = tokens * (int64_t)(n_heads + n_kv);
     cudaStream_t st = (cudaStream_t)stream;
-    // B200Q_ROPE_BATCH=1 selects the one-vector-per-step schedule (A/B switch); the batched grid is one wave of the kernel's residency
-    static const int batch = [] { const char* v = getenv("B200Q_ROPE_BATCH"); return (v && v[0] == '1') ? 1 : 4; }();
+    // B200Q_ROPE_BATCH=4 selects the four-vectors-per-step schedule (A/B switch; its grid is one wave of the kernel's residency)
+    // measured (T = 32 768, 32 + 8 heads of 128): one vector per step 323 us, four per step 365 us -- the kernel is bound by its ~30
+    // instructions per element (0.3 of the HBM roofline either way), not by load latency, and 73 registers leave 3 CTAs per SM
+    static const int batch = [] { const char* v = getenv("B200Q_ROPE_BATCH"); return (v && v[0] == '4') ? 4 : 1; }();
 #define B200Q_ROPE(EPL_, U_) do { \
         static const int per = [] { int n = 0; return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, qk_norm_rope_kernel<EPL_, U_>, 256, 0) == cudaSuccess && n > 0) ? n : 2; }(); \
         const int grid = (int)min((n_vec + 8 * U_ - 1) / (8 * U_), (int64_t)kNumSMs * per); \
