@@ -76,3 +76,16 @@ def test_mse_observer_live(name, dtype):
     assert_bits_equal(gmn.reshape(rmn.shape), rmn, f"{name}/{dtype}: min")
     assert_bits_equal(gmx.reshape(rmx.shape), rmx, f"{name}/{dtype}: max")
     assert not torch.equal(rmn, torch.amin(L.flatten_weight(w, args), dim=(0, -1))), "the search must shrink some range"
+
+
+@pytest.mark.parametrize("shape", [(4, 8), (7, 13), (16, 24), (130, 77)])
+def test_pack_to_int32_out_of_range_codes_live(shape):
+    """pack_to_int32 SUMS the shifted (code + offset) bytes (CT:compressors/pack_quantized/helpers.py:20-90): for int8 codes outside the
+    4-bit range the carries spill into the neighbouring nibbles.  The oracle -- and, checked against it on the GPU, the CUDA kernels
+    (tests/test_gpu_compress.py::test_flat_pack_unpack_fast_paths) -- must reproduce that, not an OR of masked nibbles."""
+    from compressed_tensors.compressors.pack_quantized.helpers import pack_to_int32
+
+    g = torch.Generator().manual_seed(shape[0] * 100 + shape[1])
+    v = torch.randint(-128, 128, shape, generator=g, dtype=torch.int8)
+    for dim in (1, 0):
+        assert torch.equal(pack_to_int32(v, 4, packed_dim=dim), O.pack_to_int32(v, 4, dim)), (shape, dim)
