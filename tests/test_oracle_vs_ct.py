@@ -89,3 +89,49 @@ def test_pack_to_int32_out_of_range_codes_live(shape):
     v = torch.randint(-128, 128, shape, generator=g, dtype=torch.int8)
     for dim in (1, 0):
         assert torch.equal(pack_to_int32(v, 4, packed_dim=dim), O.pack_to_int32(v, 4, dim)), (shape, dim)
+
+
+@pytest.mark.parametrize("name", ["int4_g128_asym", "int4_g128_sym", "int4_channel_asym", "fp8_channel", "fp8_g32", "fp8_block", "nvfp4"])
+def test_quantize_fake_quantize_foreign_qparams_live(name):
+    """CT quantize / fake_quantize with qparams that are NOT the tensor's own statistics -- perturbed scales, a zero / 1e-35 / 3e5 scale,
+    zero points incl. one outside the 4-bit range, an NVFP4 group scale that is not an e4m3 number: the oracle must agree with live
+    compressed-tensors bit for bit, because the GPU tests of the supplied-qparams kernels (test_gpu_compress.py::*foreign*) are
+    anchored on the oracle for exactly these cases."""
+    from compressed_tensors.quantization.lifecycle.forward import fake_quantize, quantize
+
+    fmt, args = L.format_args(name)
+    _, qtype, nb, sym, strat, g, blk = FORMATS[name]
+    geom = geom_of(name)
+    rows, cols = (200, 392) if strat == O.BLOCK else (37, 768)
+    gen = torch.Generator().manual_seed(3)
+    w = synth_weight(rows, cols, torch.bfloat16, 91)
+    mn, mx = O.minmax(w, geom)
+    gs = O.generate_gparam(float(w.float().min()), float(w.float().max()), torch.bfloat16) if qtype == O.FP4 else None
+    s, _ = O.calculate_qparams(mn, mx, qtype, nb, sym, gs)
+    s = s.float() * (0.5 + 1.5 * torch.rand(s.shape, generator=gen))
+    if qtype == O.FP4:
+        s = s.clamp(max=448.0).to(torch.float8_e4m3fn).to(torch.bfloat16)
+        s.view(-1)[1] = 0.3
+    else:
+        s = s.to(torch.bfloat16)
+        if strat != O.BLOCK:  # block (0, 0) holds zero rows: 0 / 0 is a NaN whose payload is not comparable
+            s.view(-1)[0] = 0.0
+        s.view(-1)[1] = 1e-35
+        s.view(-1)[-1] = 3.0e5
+    if qtype == O.INT:
+        zp = torch.randint(-8, 8, s.shape, generator=gen, dtype=torch.int8) if not sym else torch.zeros(s.shape, dtype=torch.int8)
+        if not sym:
+            zp.view(-1)[2] = 40
+    else:
+        zp = torch.zeros(s.shape, dtype=torch.float8_e4m3fn)
+    q_live = quantize(w, s, zp, args, global_scale=gs)
+    fq_live = fake_quantize(w, s, zp, args, global_scale=gs)
+    q_o = O.quantize(w, s, zp, geom, qtype, nb, gs)
+    if qtype == O.INT:
+        assert torch.equal(q_live.to(torch.int8), q_o), name
+    elif qtype == O.FP8:
+        assert_bits_equal(q_live.to(torch.float8_e4m3fn), q_o, name)
+    else:
+        vals = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0])[(q_o & 7).long()] * torch.where((q_o & 8) > 0, -1.0, 1.0)
+        assert_bits_equal(q_live, vals.to(torch.bfloat16), name)
+    assert_bits_equal(fq_live, O.fake_quantize(w, s, zp, geom, qtype, nb, gs), name)
