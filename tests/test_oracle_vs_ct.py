@@ -135,3 +135,34 @@ def test_quantize_fake_quantize_foreign_qparams_live(name):
         vals = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0])[(q_o & 7).long()] * torch.where((q_o & 8) > 0, -1.0, 1.0)
         assert_bits_equal(q_live, vals.to(torch.bfloat16), name)
     assert_bits_equal(fq_live, O.fake_quantize(w, s, zp, geom, qtype, nb, gs), name)
+
+
+@pytest.mark.parametrize("name", ["int4_g128_asym", "int4_g128_sym", "int4_channel_asym"])
+def test_dequantize_int8_codes_foreign_qparams_live(name):
+    """CT dequantize on un-packed int8 codes over the FULL int8 range with foreign scales / zero points (and without a zero point):
+    anchors the GPU test of dequant_int8_fast_kernel."""
+    from compressed_tensors.quantization.lifecycle.forward import dequantize
+
+    fmt, args = L.format_args(name)
+    _, qtype, nb, sym, strat, gsz, blk = FORMATS[name]
+    geom = geom_of(name)
+    g = torch.Generator().manual_seed(9)
+    rows, cols = 37, 768
+    w = synth_weight(rows, cols, torch.bfloat16, 5)
+    s, _ = O.calculate_qparams(*O.minmax(w, geom), qtype, nb, sym)
+    s = (s.float() * (0.5 + 1.5 * torch.rand(s.shape, generator=g))).to(torch.bfloat16)
+    zp = torch.randint(-8, 8, s.shape, generator=g, dtype=torch.int8)
+    codes = torch.randint(-128, 128, (rows, cols), generator=g, dtype=torch.int8)
+    for z in (zp, None):
+        assert_bits_equal(dequantize(codes, s, z, args=args), O.dequantize(codes, s, z, geom, qtype), f"{name} zp={z is not None}")
+
+
+def test_pack_fp4_off_grid_values_live():
+    """pack_fp4_to_uint8 on values that are NOT e2m1 grid points (first minimum of |x| - grid evaluated in bf16, sign bit from the
+    input, magnitudes beyond 6): anchors the slow path of pack_fp4_flat_kernel."""
+    from compressed_tensors.compressors.nvfp4.helpers import pack_fp4_to_uint8
+
+    g = torch.Generator().manual_seed(9)
+    off = (torch.randn(16, 64, generator=g) * 3).to(torch.bfloat16)
+    off[0, :6] = torch.tensor([-0.0, 7.5, -100.0, 0.25, 0.75, -0.25], dtype=torch.bfloat16)
+    assert torch.equal(pack_fp4_to_uint8(off), O.pack_fp4_to_uint8(off))
