@@ -43,5 +43,5 @@ for name in names:
     print(f"{name:13s} {ms*1e3:8.1f} us  {w.numel()*2/ms/1e6:6.0f} GB/s bf16-out  {alg:6.0f} GB/s algorithmic  {alg/peak:.3f}", flush=True)
     del out, sd
 os.makedirs("gpurun_out", exist_ok=True)
-tag = os.environ.get("B200Q_DECODE_INT4_PRE", "")
+tag = os.environ.get("B200Q_BENCH_TAG") or os.environ.get("B200Q_DECODE_INT4_PRE", "")  # second name: the tag the round-1 sweep scripts used
 json.dump({"stack": list(w.shape), "rows": rows}, open(f"gpurun_out/decompress{'_' + tag if tag else ''}.json", "w"), indent=1)
