@@ -222,7 +222,6 @@ static int elementwise(int op, const void* x, int64_t rows, int64_t cols, const 
     if (int rc = check_scheme(sc)) return rc;
     REQ_PTR(x); REQ_PTR(scale); REQ_PTR(out);
     cudaStream_t st = (cudaStream_t)stream;
-    if (sc->qtype == B200Q_FP4) B200Q_REQUIRE(gs != nullptr || sc->strategy != B200Q_GROUP || true, "unreachable");
     const bool vec_ok = cols % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0;
     const int g = sc->group_size;
     static const bool ew_fast = getenv("B200Q_ELEMENTWISE_LEGACY") == nullptr;  // A/B switch
