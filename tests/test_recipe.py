@@ -1,5 +1,7 @@
 """CPU: recipe (YAML) parsing and target / mapping resolution -- host logic behind the reference's recipe schema
 (REF:configs/recipes/*.yaml; the YAML below is typed here in that schema, not copied)."""
+import os
+
 import pytest
 import torch
 
@@ -134,3 +136,33 @@ def test_errors():
         R._args_from_dict(dict(num_bits=4, type="int", strategy="group"))
     with pytest.raises(ValueError):
         R._args_from_dict(dict(num_bits=4, type="int", strategy="group", group_size=128, actorder="group"))
+
+
+_REF_RECIPES = "/root/reference/configs/recipes"
+
+
+@pytest.mark.skipif(not os.path.isdir(_REF_RECIPES), reason="reference checkout not present (GPU box)")
+def test_every_reference_recipe_parses():
+    """The reference's own YAML recipes (REF:configs/recipes/*.yaml) go through the parser unchanged: modifier kinds, at least one
+    config group with weight arguments each, AWQ mappings where the recipe defines them.  Read from the read-only reference checkout
+    when it exists (this container); the restated recipes in the tests above cover the same schema on the GPU box."""
+    from quantizers_b200 import recipe as R
+
+    want = {
+        "recipe_AR_W4A16G32.yaml": ["AutoRoundModifier"],
+        "recipe_Dense_NVFP4.yaml": ["QuantizationModifier"],
+        "recipe_Minimax-M2.1-AWQ-MixedPrec.yaml": ["AWQModifier"],
+        "recipe_Minimax-M2.1-Experts-only-AWQ.yaml": ["AWQModifier"],
+        "recipe_MoE_RTN_NVFP4.yaml": ["QuantizationModifier"],
+        "recipe_awq_w4a16.yaml": ["AWQModifier"],
+        "recipe_mixed_fp8_int4.yaml": ["QuantizationModifier", "AWQModifier"],
+    }
+    for fname, kinds in want.items():
+        r = R.load_recipe(os.path.join(_REF_RECIPES, fname))
+        assert [m.kind for m in r.modifiers] == kinds, fname
+        for m in r.modifiers:
+            assert m.config_groups, (fname, m.kind)
+            for grp in m.config_groups:
+                assert grp.weights is not None and grp.weights.num_bits in (4, 8), (fname, m.kind)
+    awq = R.load_recipe(os.path.join(_REF_RECIPES, "recipe_Minimax-M2.1-Experts-only-AWQ.yaml")).modifiers[0]
+    assert awq.mappings and len(awq.mappings) >= 2
