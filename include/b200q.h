@@ -71,6 +71,14 @@ int b200q_version(void);
  *   zp_packed  int32 [batch, ceil(rows*num_bits/32), n_groups]  (asymmetric only; may be NULL when symmetric) */
 int b200q_compress_int_packed(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* scheme,
                               int32_t* packed, void* scale, int32_t* zp_packed, void* stream);
+/* The same call with a caller-owned device workspace of b200q_compress_int_workspace(...) bytes.  Asymmetric GROUP schemes then
+ * write their zero points with plain int8 stores and row-pack them (pack_to_int32(zp, packed_dim=0),
+ * CT:compressors/pack_quantized/base.py:70-73) in a second small kernel, instead of one atomic per group into a zeroed buffer.
+ * workspace may be NULL (or too small): the call then behaves exactly like b200q_compress_int_packed.  Identical output bits. */
+int64_t b200q_compress_int_workspace(int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* scheme);
+int b200q_compress_int_packed_ws(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* scheme,
+                                 int32_t* packed, void* scale, int32_t* zp_packed, void* workspace, int64_t workspace_bytes,
+                                 void* stream);
 
 /* float-quantized (FP8 e4m3; CHANNEL, GROUP, BLOCK 128x128 or TENSOR):
  *   q      uint8 (float8_e4m3fn bits) [batch, rows, cols]

@@ -35,6 +35,8 @@ _SIGS = {
     "b200q_version": (_I, []),
     "b200q_last_error": (c_char_p, []),
     "b200q_compress_int_packed": (_I, [_P, c_int64, c_int64, c_int64, _S, _P, _P, _P, _P]),
+    "b200q_compress_int_workspace": (c_int64, [c_int64, c_int64, c_int64, _S]),
+    "b200q_compress_int_packed_ws": (_I, [_P, c_int64, c_int64, c_int64, _S, _P, _P, _P, _P, c_int64, _P]),
     "b200q_compress_fp8": (_I, [_P, c_int64, c_int64, c_int64, _S, _P, _P, _P, _P]),
     "b200q_compress_nvfp4": (_I, [_P, c_int64, c_int64, c_int64, c_int32, c_int32, _P, _P, _P, _P]),
     "b200q_compress_nvfp4_fused": (_I, [_P, c_int64, c_int64, c_int64, c_int32, c_int32, _P, _P, _P, _P, c_int64, _P]),

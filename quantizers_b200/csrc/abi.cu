@@ -48,8 +48,19 @@ extern "C" {
 const char* b200q_last_error(void) { return g_err; }
 int b200q_version(void) { return 100; }
 
+int64_t b200q_compress_int_workspace(int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* sc) {
+    if (sc == nullptr || sc->qtype != B200Q_INT || sc->symmetric || sc->strategy != B200Q_GROUP || sc->group_size <= 0) return 0;
+    return batch * rows * (cols / sc->group_size);  // one int8 zero point per group
+}
+
 int b200q_compress_int_packed(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* sc,
                               int32_t* packed, void* scale, int32_t* zp_packed, void* stream) {
+    return b200q_compress_int_packed_ws(weight, batch, rows, cols, sc, packed, scale, zp_packed, nullptr, 0, stream);
+}
+
+int b200q_compress_int_packed_ws(const void* weight, int64_t batch, int64_t rows, int64_t cols, const b200q_scheme* sc,
+                                 int32_t* packed, void* scale, int32_t* zp_packed, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
     if (int rc = check_scheme(sc)) return rc;
     B200Q_REQUIRE(sc->qtype == B200Q_INT, "pack-quantized needs an INT scheme");
     REQ_PTR(weight); REQ_PTR(packed); REQ_PTR(scale);
@@ -59,6 +70,9 @@ int b200q_compress_int_packed(const void* weight, int64_t batch, int64_t rows, i
         GroupParams p{};
         p.w = weight; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = sc->num_bits;
         p.symmetric = sc->symmetric; p.has_zp = 1; p.scale = scale; p.zp_packed = zp_packed; p.out = packed;
+        if (workspace != nullptr && !sc->symmetric && workspace_bytes >= b200q_compress_int_workspace(batch, rows, cols, sc) &&
+            getenv("B200Q_ZP_ATOMIC") == nullptr)
+            p.zp_scratch = (int8_t*)workspace;
         if (sc->dtype == B200Q_BF16 && fast_paths_enabled()) {
             int rc = tma_paths_enabled() ? launch_group_tma(QT_INT, p, batch, st) : B200Q_ENOSYS;
             if (rc == B200Q_ENOSYS) rc = launch_group_fast(QT_INT, p, batch, st);

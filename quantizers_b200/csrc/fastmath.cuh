@@ -71,6 +71,12 @@ struct Bracket {
         lo = pack2(a, a);
         hi = pack2(b, b);
     }
+    // single evaluation (bf16 value / bf16 scale: see group_tma_kernel's ONE note): lo = hi = (r, r)
+    __device__ __forceinline__ void init1(float s) {
+        const float r = rcp_approx(s);
+        lo = pack2(r, r);
+        hi = lo;
+    }
 };
 // exact T(a / divisor) for a non-negative bf16 statistic and a compile-time divisor, without an IEEE division on the
 // common path: multiply by the bracketed constant reciprocal, fall back when the two ends round differently.
@@ -80,6 +86,14 @@ __device__ __forceinline__ float div_const_bf16(float a, float divisor) {
     const uint32_t u = cvt_bf16x2(hi, lo);
     const bool ok = ((u >> 16) == (u & 0xffffu)) && (a == 0.0f || (a >= 7.8886090522101181e-31f && a <= 1.2676506002282294e30f));
     if (ok) return __uint_as_float(u << 16);
+    return round_to<DT_BF16>(__fdiv_rn(a, divisor));
+}
+
+// the same for callers that have proven the quotient can never sit within 2^-21 of a bf16 rounding boundary: a has an 8-bit
+// significand and the divisor at most 9 bits (7.5, 15, 448, 6), so a / divisor stays >= 2^-13 (relative) away from every boundary
+__device__ __forceinline__ float div_const_bf16_1(float a, float divisor) {
+    const float c = 1.0f / divisor;  // folded at compile time (round-to-nearest)
+    if (a == 0.0f || (a >= 7.8886090522101181e-31f && a <= 1.2676506002282294e30f)) return round_to<DT_BF16>(__fmul_rn(a, c));
     return round_to<DT_BF16>(__fdiv_rn(a, divisor));
 }
 

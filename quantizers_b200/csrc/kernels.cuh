@@ -18,6 +18,7 @@ struct GroupParams {
     void* scale;            // T [b, rows, G]  (FP4 compress: e4m3 bytes)
     const int8_t* zp_in;    // int8 [b, rows, G] or null
     int32_t* zp_packed;     // int32 [b, ceil(rows/pf), G]  (compress, asym)
+    int8_t* zp_scratch = nullptr;  // optional int8 [b, rows, G] workspace (TMA kernel: plain stores + a row-pack kernel instead of atomics)
     const float* gs;        // fp32 [b] (FP4) or null
     int32_t gs_stride;      // 1: per batch entry, 0: shared
     const float* col_scale; // fp32 [cols]: AWQ smoothing scale (MODE_OBS_FQ) or null

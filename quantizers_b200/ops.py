@@ -435,17 +435,75 @@ def unpack_fp4_from_uint8(a: torch.Tensor, m: int, n: int, dtype: Optional[torch
 
 
 # ----------------------------------------------------------------------------- fused compress
+def _out_buf(out: Optional[dict], key: str, shape, dtype, dev) -> torch.Tensor:
+    """``out[key]`` when the caller owns the buffer (checked), else a fresh allocation."""
+    if out is not None and key in out:
+        t = out[key]
+        if t.dtype == _FP8 and dtype == torch.uint8:
+            t = t.view(torch.uint8)
+        if tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev or not t.is_contiguous():
+            raise B200QError(f"out[{key!r}] must be a contiguous {dtype} tensor of shape {tuple(shape)} on {dev}, "
+                             f"got {t.dtype} {tuple(t.shape)} on {t.device}")
+        return t
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+def compress_outputs(weight_shape, args, dtype=torch.bfloat16, device="cuda", fuse_span: int = 1) -> dict:
+    """Caller-owned output (and workspace) buffers for :func:`compress_weight` on a weight / stack of ``weight_shape``: allocate
+    once, pass as ``out=`` for every weight of that shape class -- the call then allocates nothing and never touches the host."""
+    lead, rows, cols = tuple(weight_shape[:-2]), int(weight_shape[-2]), int(weight_shape[-1])
+    batch = 1
+    for d in lead:
+        batch *= int(d)
+    dev = torch.device(device)
+    qt, strat = _qtype_code(args), _strategy_code(args)
+    g = getattr(args, "group_size", None) or 0
+    if strat == L.GROUP:
+        qshape = (rows, cols // g)
+    elif strat == L.CHANNEL:
+        qshape = (rows, 1)
+    elif strat == L.BLOCK:
+        bh, bw = args.block_structure
+        qshape = (-(-rows // bh), -(-cols // bw))
+    else:
+        qshape = (1,)
+    if qt == L.INT:
+        pf = 32 // args.num_bits
+        out = {"weight_packed": torch.empty(lead + (rows, -(-cols // pf)), dtype=torch.int32, device=dev),
+               "weight_scale": torch.empty(lead + qshape, dtype=dtype, device=dev)}
+        if not args.symmetric:
+            out["weight_zero_point"] = torch.empty(lead + (-(-qshape[0] // pf), qshape[1]), dtype=torch.int32, device=dev)
+            if strat == L.GROUP:
+                out["_workspace"] = torch.empty(max(batch * rows * qshape[1], 1), dtype=torch.int8, device=dev)
+        return out
+    if qt == L.FP8:
+        out = {"weight": torch.empty(lead + (rows, cols), dtype=torch.uint8, device=dev).view(_FP8),
+               "weight_scale": torch.empty(lead + qshape, dtype=dtype, device=dev)}
+        if strat == L.TENSOR:
+            out["_workspace"] = torch.empty(max(batch, 1), dtype=torch.float32, device=dev)
+        return out
+    out = {"weight_packed": torch.empty(lead + (rows, cols // 2), dtype=torch.uint8, device=dev),
+           "weight_scale": torch.empty(lead + (rows, cols // 16), dtype=torch.uint8, device=dev).view(_FP8),
+           "weight_global_scale": torch.empty(lead + (1,), dtype=torch.float32, device=dev)}
+    nws = max(int(L.lib().b200q_compress_nvfp4_workspace(batch, rows, cols, int(fuse_span))) // 4, 2)
+    out["_workspace"] = torch.empty(nws, dtype=torch.int32, device=dev)
+    return out
+
+
 @torch.no_grad()
 def compress_weight(weight: torch.Tensor, args, global_scale: Optional[torch.Tensor] = None, has_zp: bool = True,
-                    fuse_span: int = 1) -> dict:
+                    fuse_span: int = 1, out: Optional[dict] = None) -> dict:
     """Fused observer -> qparams -> quantize -> pack of one weight ``[rows, cols]`` or a stack ``[E, rows, cols]``.
 
     Returns the tensors ``Compressor.compress`` puts in the state dict:
-      INT  : weight_packed int32, weight_scale T, weight_shape int64[2], (+ weight_zero_point int32 when asymmetric)
+      INT  : weight_packed int32, weight_scale T, weight_shape int64[2] on the CPU (CT:compressors/pack_quantized/base.py:68),
+             (+ weight_zero_point int32 when asymmetric)
       FP8  : weight e4m3, weight_scale T
       FP4  : weight_packed uint8, weight_scale e4m3, weight_global_scale fp32 [1] (per stacked weight: [E, 1]);
              ``fuse_span`` consecutive stacked weights share min(global_scale) (gate/up siblings, LLMC
              update_fused_layer_weight_global_scales) when the global scale is computed here
+    ``out``: buffers from :func:`compress_outputs` (same shape class) -- the results are written there, nothing is allocated and
+    no host synchronisation happens; without it every tensor is a fresh allocation.
     """
     L.require_cuda(weight, global_scale)
     if weight.ndim not in (2, 3):
@@ -470,14 +528,19 @@ def compress_weight(weight: torch.Tensor, args, global_scale: Optional[torch.Ten
             qshape = (rows, 1)
         else:
             raise B200QError("pack-quantized supports group and channel strategies")
-        packed = torch.empty(lead + (rows, -(-cols // pf)), dtype=torch.int32, device=dev)
-        scale = torch.empty(lead + qshape, dtype=w.dtype, device=dev)
-        zpp = None if args.symmetric else torch.empty(lead + (-(-qshape[0] // pf), qshape[1]), dtype=torch.int32, device=dev)
-        L.check(lib.b200q_compress_int_packed(L.ptr(w), batch, rows, cols, ctypes.byref(sc), L.ptr(packed), L.ptr(scale), L.ptr(zpp), st))
-        out = {"weight_packed": packed, "weight_scale": scale, "weight_shape": torch.tensor([rows, cols], device=dev)}
+        packed = _out_buf(out, "weight_packed", lead + (rows, -(-cols // pf)), torch.int32, dev)
+        scale = _out_buf(out, "weight_scale", lead + qshape, w.dtype, dev)
+        zpp = None if args.symmetric else _out_buf(out, "weight_zero_point", lead + (-(-qshape[0] // pf), qshape[1]), torch.int32, dev)
+        ws = None
+        if zpp is not None and strat == L.GROUP:
+            # int8 zero points land here with plain stores and are row-packed by a second small kernel (no atomics, no memset)
+            ws = _out_buf(out, "_workspace", (max(batch * rows * qshape[1], 1),), torch.int8, dev)
+        L.check(lib.b200q_compress_int_packed_ws(L.ptr(w), batch, rows, cols, ctypes.byref(sc), L.ptr(packed), L.ptr(scale), L.ptr(zpp),
+                                                 L.ptr(ws), 0 if ws is None else ws.numel(), st))
+        res = {"weight_packed": packed, "weight_scale": scale, "weight_shape": torch.tensor([rows, cols])}
         if zpp is not None:
-            out["weight_zero_point"] = zpp
-        return out
+            res["weight_zero_point"] = zpp
+        return res
     if qt == L.FP8:
         if strat == L.GROUP:
             qshape = (rows, cols // args.group_size)
@@ -488,20 +551,21 @@ def compress_weight(weight: torch.Tensor, args, global_scale: Optional[torch.Ten
             qshape = (-(-rows // bh), -(-cols // bw))
         else:
             qshape = (1,)
-        q = torch.empty(lead + (rows, cols), dtype=torch.uint8, device=dev)
-        scale = torch.empty(lead + qshape, dtype=w.dtype, device=dev)
-        ws = torch.empty(max(batch, 1), dtype=torch.float32, device=dev) if strat == L.TENSOR else None
+        q = _out_buf(out, "weight", lead + (rows, cols), torch.uint8, dev)
+        scale = _out_buf(out, "weight_scale", lead + qshape, w.dtype, dev)
+        ws = _out_buf(out, "_workspace", (max(batch, 1),), torch.float32, dev) if strat == L.TENSOR else None
         L.check(lib.b200q_compress_fp8(L.ptr(w), batch, rows, cols, ctypes.byref(sc), L.ptr(q), L.ptr(scale), L.ptr(ws), st))
         return {"weight": q.view(_FP8), "weight_scale": scale}
     # NVFP4
     if cols % 16 != 0:
         raise B200QError(f"tensor column shape must be divisble by the given group_size 16 but got {cols}")
-    packed = torch.empty(lead + (rows, cols // 2), dtype=torch.uint8, device=dev)
-    scale = torch.empty(lead + (rows, cols // 16), dtype=torch.uint8, device=dev)
+    packed = _out_buf(out, "weight_packed", lead + (rows, cols // 2), torch.uint8, dev)
+    scale = _out_buf(out, "weight_scale", lead + (rows, cols // 16), torch.uint8, dev)
     if global_scale is None:
         # NVFP4 siblings stacked next to each other (gate/up of one expert: fuse_span = 2) share min(global_scale)
-        gs = torch.empty(batch, dtype=torch.float32, device=dev)
-        ws = torch.empty(max(int(lib.b200q_compress_nvfp4_workspace(batch, rows, cols, int(fuse_span))) // 4, 2), dtype=torch.int32, device=dev)
+        gs = _out_buf(out, "weight_global_scale", lead + (1,), torch.float32, dev)
+        nws = max(int(lib.b200q_compress_nvfp4_workspace(batch, rows, cols, int(fuse_span))) // 4, 2)
+        ws = _out_buf(out, "_workspace", (nws,), torch.int32, dev)
         L.check(lib.b200q_compress_nvfp4_fused(L.ptr(w), batch, rows, cols, L.DTYPE_CODE[w.dtype], int(fuse_span), L.ptr(gs), L.ptr(packed),
                                                L.ptr(scale), L.ptr(ws), ws.numel() * 4, st))
         return {"weight_packed": packed, "weight_scale": scale.view(_FP8), "weight_global_scale": gs.reshape(lead + (1,))}

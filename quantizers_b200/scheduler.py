@@ -199,8 +199,30 @@ def synth_moe_awq_experts(layer_idx: int, experts: Sequence[int], tokens: int, d
 
 
 # ----------------------------------------------------------------------------- RTN quantize + pack of a shard
-def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Optional[list] = None) -> Dict[str, dict]:
+def _nvfp4_span(spec: ModelSpec, m: MatrixSpec) -> int:
+    """Stacked siblings that share min(global_scale) inside ONE stack (gate/up: per_unit = 2), else 1."""
+    a = PRESETS[m.preset]
+    if not (a.type == "float" and a.num_bits == 4):
+        return 1
+    members = [x for x in spec.matrices if (x.fuse_group or x.name) == (m.fuse_group or m.name)
+               and PRESETS[x.preset].type == "float" and PRESETS[x.preset].num_bits == 4]
+    return m.per_unit if len(members) == 1 else 1
+
+
+def alloc_outputs(spec: ModelSpec, arena: Dict[str, torch.Tensor]) -> Dict[str, dict]:
+    """Caller-owned output + workspace buffers for :func:`quantize_arena` (one set per shape class, reused for every pass): with
+    them a pass allocates nothing and never synchronises with the host."""
+    from . import ops
+
+    return {m.name: ops.compress_outputs(arena[m.name].shape, PRESETS[m.preset], arena[m.name].dtype, arena[m.name].device,
+                                         fuse_span=_nvfp4_span(spec, m)) for m in spec.matrices}
+
+
+def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Optional[list] = None,
+                   out: Optional[Dict[str, dict]] = None) -> Dict[str, dict]:
     """Fused observe -> qparams -> quantize -> pack for every stacked weight class of this rank's shard.
+
+    ``out``: buffers from :func:`alloc_outputs`; results are written in place (no allocation, no host sync).
 
     NVFP4: siblings in one ``fuse_group`` of a unit share min(global_scale) (LLMC
     update_fused_layer_weight_global_scales); the per-tensor scales come from one batched reduction per class.
@@ -208,7 +230,7 @@ def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Opt
     """
     from . import ops
 
-    out = {}
+    res = {}
     fused_gs: Dict[str, torch.Tensor] = {}
     nv = [m for m in spec.matrices if PRESETS[m.preset].type == "float" and PRESETS[m.preset].num_bits == 4]
     groups = {}
@@ -236,11 +258,12 @@ def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Opt
         if timings is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        out[m.name] = ops.compress_weight(w, args, global_scale=fused_gs.get(m.name), fuse_span=span_of.get(m.name, 1))
+        res[m.name] = ops.compress_weight(w, args, global_scale=fused_gs.get(m.name), fuse_span=span_of.get(m.name, 1),
+                                          out=None if out is None else out[m.name])
         if ev is not None:
             ev[1].record()
             timings.append((m.name, m.preset, w.numel(), ev[0], ev[1]))
-    return out
+    return res
 
 
 def launches_per_step(spec: ModelSpec) -> int:
@@ -252,6 +275,8 @@ def launches_per_step(spec: ModelSpec) -> int:
             n += 1  # fused |max| -> global scale -> compress kernel (siblings in one stack)
         elif a.strategy == "tensor":
             n += 3
+        elif a.type == "int" and not a.symmetric and a.strategy == "group":
+            n += 2  # fused compress + zero-point row-pack kernel
         else:
             n += 1
     return n
