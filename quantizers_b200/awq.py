@@ -304,11 +304,41 @@ def _first_min_device(acc: torch.Tensor) -> torch.Tensor:
 
 
 @torch.no_grad()
+def abs_mean_running(x: torch.Tensor, sample_len: int) -> torch.Tensor:
+    """``x_mean_dtype="act"``: llmcompressor's ``_accumulate_mean`` as recalled from upstream (SURVEY.md Appendix A line 489) -- the
+    hook keeps ``|x|`` in the ACTIVATION dtype, so each calibration batch contributes ``act(sum_t |x|)`` and the running mean
+    ``(prev_mean * prev_count + batch_sum) / (prev_count + T_b)`` is evaluated in that dtype, batch after batch.  The per-batch
+    sums come from ``b200q_abs_sum_cols`` (fp32 accumulation, rounded once like torch's reduction); the [K]-sized running update
+    is a handful of elementwise ops per batch.  Order dependent, hence not token-shardable."""
+    x2 = x.reshape(-1, x.shape[-1])
+    mean, count = None, 0
+    for t0 in range(0, x2.shape[0], sample_len):
+        xb = x2[t0:t0 + sample_len]
+        s = abs_sum_cols(xb).to(x.dtype)
+        mean = s / xb.shape[0] if mean is None else (mean * count + s) / (count + xb.shape[0])
+        count += xb.shape[0]
+    return mean.float()
+
+
+@torch.no_grad()
 def _search_device(x: torch.Tensor, weights: Sequence[torch.Tensor], parent: Callable, args, n_grid: int, duo_scaling: bool,
-                   process_group, fused: Optional[bool], token_chunk: int):
+                   process_group, fused: Optional[bool], token_chunk: int, x_mean_dtype: str = "fp32", loss_form: str = "float_pow",
+                   sample_len: Optional[int] = None):
     """Everything of ``_compute_best_scale`` that runs on the device, enqueued without a host synchronisation:
-    returns (scales fp32 [n_grid, K], acc fp32 [n_grid + 1] = summed squared errors + element count, ratios)."""
+    returns (scales fp32 [n_grid, K], acc fp32 [n_grid + 1] = summed squared errors + element count, ratios).
+
+    Fidelity switches for the two places where llmcompressor versions are known to differ (defaults = the fused path):
+      x_mean_dtype  "fp32" (|x| summed in fp32 over all tokens) | "act" (upstream's per-batch running mean in the activation dtype,
+                    needs ``sample_len``; not token-shardable)
+      loss_form     "float_pow" (``(a - b).float().pow(2).sum()``: bf16 difference, fp32 square / sum -- what the fused tcgen05
+                    epilogue computes) | "mse_bf16" (``F.mse_loss(a, b, reduction="sum")`` per batch on the bf16 tensors: square and
+                    per-batch result rounded to bf16; evaluated through the generic parent path, per ``sample_len`` tokens)"""
     import torch.distributed as dist
+
+    if x_mean_dtype not in ("fp32", "act") or loss_form not in ("float_pow", "mse_bf16"):
+        raise ValueError(f"unknown fidelity switch: x_mean_dtype={x_mean_dtype!r}, loss_form={loss_form!r}")
+    if (x_mean_dtype == "act" or loss_form == "mse_bf16") and not sample_len:
+        raise ValueError("x_mean_dtype='act' / loss_form='mse_bf16' follow the per-batch arithmetic and need sample_len")
 
     dev = x.device
     K = x.shape[-1]
@@ -316,15 +346,22 @@ def _search_device(x: torch.Tensor, weights: Sequence[torch.Tensor], parent: Cal
     # token-sharded calibration is explicit: layer- / expert-sharded ranks search different mappings and must NOT be reduced
     # together, so nothing is exchanged unless the caller names the group whose ranks hold shards of the same tokens
     dist_on = process_group is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+    if loss_form == "mse_bf16":
+        fused, token_chunk = False, int(sample_len)
     if fused is None:
         fused = hasattr(parent, "fused_losses") and x.dtype == torch.bfloat16
     # ---- statistics
-    xsum = abs_sum_cols(x)
-    if dist_on:
-        cnt = torch.full((1,), float(x.shape[0]), dtype=torch.float64, device=dev)
-        x_mean = reduce_token_stats(xsum, cnt, process_group)
+    if x_mean_dtype == "act":
+        if dist_on:
+            raise ValueError("x_mean_dtype='act' is a sequential running mean: run it unsharded")
+        x_mean = abs_mean_running(x, int(sample_len))
     else:
-        x_mean = xsum / float(x.shape[0])
+        xsum = abs_sum_cols(x)
+        if dist_on:
+            cnt = torch.full((1,), float(x.shape[0]), dtype=torch.float64, device=dev)
+            x_mean = reduce_token_stats(xsum, cnt, process_group)
+        else:
+            x_mean = xsum / float(x.shape[0])
     w_mean = compute_layer_means(weights, args.group_size) if duo_scaling else None
     ratios = [i / n_grid for i in range(n_grid)]
     scales = awq_scales(x_mean, w_mean, ratios, duo_scaling)
@@ -352,7 +389,10 @@ def _search_device(x: torch.Tensor, weights: Sequence[torch.Tensor], parent: Cal
             for w, o in zip(weights, wq):
                 scaled_fake_quantize(w, scales[i], args, out=o)
             for xc, ref in zip(chunks, refs):
-                sq_err_accumulate(ref, parent(wq, xc), acc[i:i + 1])
+                if loss_form == "mse_bf16":
+                    acc[i:i + 1] += torch.nn.functional.mse_loss(ref, parent(wq, xc), reduction="sum").float()
+                else:
+                    sq_err_accumulate(ref, parent(wq, xc), acc[i:i + 1])
         acc[n_grid:].fill_(float(numel))  # fill_ takes the scalar by value: `acc[i] = python_float` stages a host copy and blocks
     if dist_on:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=process_group)
@@ -362,7 +402,8 @@ def _search_device(x: torch.Tensor, weights: Sequence[torch.Tensor], parent: Cal
 @torch.no_grad()
 def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent: Callable, args, n_grid: int = 20,
                        duo_scaling: bool = True, process_group=None, fused: Optional[bool] = None, fused_linear: Optional[bool] = None,
-                       token_chunk: int = 8192) -> Tuple[torch.Tensor, float, List[float]]:
+                       token_chunk: int = 8192, x_mean_dtype: str = "fp32", loss_form: str = "float_pow",
+                       sample_len: Optional[int] = None) -> Tuple[torch.Tensor, float, List[float]]:
     """``AWQModifier._compute_best_scale`` for one mapping.
 
     x        [T_local, K] inputs of the balance layers (this rank's token shard; whole samples for an attention parent)
@@ -374,7 +415,8 @@ def compute_best_scale(x: torch.Tensor, weights: Sequence[torch.Tensor], parent:
     token counts and the loss accumulators are all-reduced (SUM), so every rank of the group returns the same argmin."""
     if fused is None and fused_linear is not None:
         fused = fused_linear
-    scales, acc, ratios = _search_device(x, weights, parent, args, n_grid, duo_scaling, process_group, fused, token_chunk)
+    scales, acc, ratios = _search_device(x, weights, parent, args, n_grid, duo_scaling, process_group, fused, token_chunk,
+                                         x_mean_dtype, loss_form, sample_len)
     best_i, losses = _select_host(acc.double().cpu())
     return scales[best_i].cpu(), ratios[best_i], losses
 
@@ -406,7 +448,8 @@ def decoder_layer_flops(T: int, hidden: int, inter: int, n_heads: int, n_kv: int
 
 @torch.no_grad()
 def search_decoder_layer(weights: dict, acts: dict, args, n_heads: int, n_kv: int, head_dim: int, seq_len: int, n_grid: int = 20,
-                         duo_scaling: bool = True, apply: bool = True, process_group=None) -> dict:
+                         duo_scaling: bool = True, apply: bool = True, process_group=None, x_mean_dtype: str = "fp32",
+                         loss_form: str = "float_pow") -> dict:
     """AWQ scale search of one dense decoder layer with llmcompressor's default Llama/Qwen mappings
     (LLMC modifiers/awq/mappings.py; REF:configs/recipes/recipe_awq_w4a16.yaml uses the defaults):
 
@@ -421,18 +464,19 @@ def search_decoder_layer(weights: dict, acts: dict, args, n_heads: int, n_kv: in
     Returns {mapping: (best_scales cpu, best_ratio, losses)}."""
     out = {}
     w = weights
+    fid = dict(x_mean_dtype=x_mean_dtype, loss_form=loss_form, sample_len=seq_len, token_chunk=seq_len * max(1, 8192 // seq_len))
     attn = AttentionParent(w["o"], n_heads, n_kv, head_dim, seq_len, w["q_norm"], w["k_norm"])
-    out["qkv"] = compute_best_scale(acts["attn_in"], [w["q"], w["k"], w["v"]], attn, args, n_grid, duo_scaling, process_group)
+    out["qkv"] = compute_best_scale(acts["attn_in"], [w["q"], w["k"], w["v"]], attn, args, n_grid, duo_scaling, process_group, **fid)
     if apply:
         smooth([w["q"], w["k"], w["v"]], w["input_layernorm"], out["qkv"][0])
     if w["v"].shape[0] == w["o"].shape[1]:
-        out["v_o"] = compute_best_scale(acts["o_in"], [w["o"]], linear_parent, args, n_grid, duo_scaling, process_group)
+        out["v_o"] = compute_best_scale(acts["o_in"], [w["o"]], linear_parent, args, n_grid, duo_scaling, process_group, **fid)
         if apply:
             smooth([w["o"]], w["v"], out["v_o"][0])
-    out["gate_up"] = compute_best_scale(acts["mlp_in"], [w["gate"], w["up"]], MLPParent(w["down"]), args, n_grid, duo_scaling, process_group)
+    out["gate_up"] = compute_best_scale(acts["mlp_in"], [w["gate"], w["up"]], MLPParent(w["down"]), args, n_grid, duo_scaling, process_group, **fid)
     if apply:
         smooth([w["gate"], w["up"]], w["post_attention_layernorm"], out["gate_up"][0])
-    out["down"] = compute_best_scale(acts["down_in"], [w["down"]], linear_parent, args, n_grid, duo_scaling, process_group)
+    out["down"] = compute_best_scale(acts["down_in"], [w["down"]], linear_parent, args, n_grid, duo_scaling, process_group, **fid)
     if apply:
         smooth([w["down"]], w["up"], out["down"][0])
     return out

@@ -156,11 +156,15 @@ awq_gemm_loss_kernel(const __grid_constant__ CUtensorMap map_aref, const __grid_
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            uint32_t it = 0, use_ref = 0, use_q = 0;
+            // Accumulator ping-pong: pass 0 (reference) lands in slot 0 and is parked in the epilogue's registers right away, so
+            // TMEM columns [0, 256) are idle for the remaining R passes -- the ratio passes alternate slot 1, 0, 1, ... and the
+            // MMAs of ratio r + 1 run while the epilogue warps still drain ratio r (round 1 had every ratio on slot 1: MMA and
+            // epilogue serialised on one accumulator).
+            uint32_t it = 0, use[2] = {0, 0};
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 for (int pass = 0; pass < passes; pass++) {
-                    const uint32_t slot = pass == 0 ? 0u : 1u;
-                    uint32_t& uses = pass == 0 ? use_ref : use_q;
+                    const uint32_t slot = (uint32_t)pass & 1u;
+                    uint32_t& uses = use[slot];
                     mbar_wait(bar_tempty + 8 * slot, (uses & 1u) ^ 1u);  // epilogue has drained this accumulator
                     uses++;
                     tc_fence_after();
@@ -183,11 +187,11 @@ awq_gemm_loss_kernel(const __grid_constant__ CUtensorMap map_aref, const __grid_
         // ------------------------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quadrant warp & 3)
         const uint32_t quad = (uint32_t)warp & 3u;
         const uint32_t t_lane = tmem_base + ((quad * 32u) << 16);
-        uint32_t use_ref = 0, use_q = 0;
+        uint32_t use[2] = {0, 0};
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             uint32_t ref[BN / 2];  // this thread's output row of the reference tile, packed bf16x2
-            mbar_wait(bar_tfull + 0, use_ref & 1u);
-            use_ref++;
+            mbar_wait(bar_tfull + 0, use[0] & 1u);
+            use[0]++;
             tc_fence_after();
 #pragma unroll
             for (int c = 0; c < BN / 32; c++) {
@@ -200,14 +204,15 @@ awq_gemm_loss_kernel(const __grid_constant__ CUtensorMap map_aref, const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 0);
             for (int r = 0; r < p.n_ratios; r++) {
-                mbar_wait(bar_tfull + 8, use_q & 1u);
-                use_q++;
+                const uint32_t slot = (uint32_t)(r + 1) & 1u;  // pass r + 1 of the MMA issuer's slot sequence
+                mbar_wait(bar_tfull + 8 * slot, use[slot] & 1u);
+                use[slot]++;
                 tc_fence_after();
                 float part = 0.0f;
 #pragma unroll
                 for (int c = 0; c < BN / 32; c++) {
                     uint32_t v[32];
-                    tc_ld32(t_lane + BN + c * 32, v);
+                    tc_ld32(t_lane + slot * BN + c * 32, v);
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         const uint32_t y = cvt_bf16x2(__uint_as_float(v[2 * j + 1]), __uint_as_float(v[2 * j]));
@@ -219,7 +224,7 @@ awq_gemm_loss_kernel(const __grid_constant__ CUtensorMap map_aref, const __grid_
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8);
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
                 if (lane == 0) atomicAdd(&p.acc[r], (double)part);

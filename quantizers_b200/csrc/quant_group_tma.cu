@@ -24,12 +24,13 @@ namespace b200q {
 namespace {
 using namespace fast;
 
-constexpr int kStages = 2;
+constexpr int kStages = 2;   // default ring depth per warp (template parameter STAGES overrides it for the A/B variants)
 // warps per CTA (one CTA per SM): as many as shared memory allows.  ncu: with 8 KB tiles (12 warps = 3 per scheduler) neither the
 // ALU nor the FMA pipe is saturated (51 % / 31 %), issue slots are 65 % busy and the stalls are fixed-latency waits -- too few
 // warps to hide them.  4 KB tiles double the warps per SM; a group of 128 is then shared by a pair of lanes.
-template <int QT, int TILE> struct WarpsFor {
-    static constexpr int value = TILE == 4096 ? ((QT == QT_FP8) ? 10 : 12) : ((QT == QT_FP8) ? 20 : 24);
+template <int QT, int TILE, int STAGES = kStages> struct WarpsFor {
+    static constexpr int value = STAGES == 2 ? (TILE == 4096 ? ((QT == QT_FP8) ? 10 : 12) : ((QT == QT_FP8) ? 20 : 24))
+                                             : (STAGES == 3 ? 8 : 6);   // 3 x 8 KB x 8 warps / 4 x 8 KB x 6 warps: deeper ring, fewer warps
 };
 
 using namespace async;
@@ -105,10 +106,11 @@ __device__ __noinline__ uint2 repair_chunk(const uint4 raw, float s, float z, bo
 // significands in tests/test_exact_reciprocal.py.  A product x * rcp(s) is within 2^-22 of the quotient, so it rounds to the same
 // bf16 as the reference's fp32 division: ONE evaluation, no bracket, no repair.  Only scales outside [2^-100, 1] (products that
 // overflow / flush) still take the IEEE chain, group-wide.  NVFP4 divides by an fp32 quotient and keeps the bracket.
-template <int QT, bool SYM, int LOG2N, bool FMA, int TILE, bool SUPPLIED = false, bool ONE = false>
-__global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_kernel(const TmaParams p) {
+template <int QT, bool SYM, int LOG2N, bool FMA, int TILE, bool SUPPLIED = false, bool ONE = false, bool PF = true, int STAGES = kStages>
+__global__ void __launch_bounds__(WarpsFor<QT, TILE, STAGES>::value * 32, 1) group_tma_kernel(const TmaParams p) {
     static_assert(!ONE || QT != QT_FP4, "NVFP4 needs the bracket");
-    constexpr int kWarps = WarpsFor<QT, TILE>::value;
+    constexpr int kStages = STAGES;
+    constexpr int kWarps = WarpsFor<QT, TILE, STAGES>::value;
     constexpr int kTileBytes = TILE * 2;
     constexpr int N = 1 << LOG2N;          // chunks (8 elements, 16 bytes) per group
     constexpr int G = 8 * N;               // group size
@@ -166,9 +168,9 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_k
         mbar_wait(bar_base + 8 * stage, parity);
         const uint32_t tin = in_base + stage * kTileBytes;
 
-        // the previous tile's bulk store must have finished READING the staging buffer before we overwrite it
-        if (lane == 0) bulk_wait_read0();
-        __syncwarp();
+        // (the previous tile's bulk store must have finished READING the output staging buffer before it is overwritten: that wait
+        // sits right before this tile's first staging store, after the statistics / qparam stages, so the store engine has that
+        // long to drain instead of stalling the warp at the top of the tile)
 
         // position of the tile's first group (warp-uniform, once per tile): matrix b0, row r0, group-in-row k0
         int64_t b0 = 0;
@@ -330,6 +332,10 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_k
                 }
             }
             // ---- C. quantize + pack into the staging buffer
+            if (gi == 0) {
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
+            }
             const bool unsafe = (QT == QT_FP4) ? !fp4_scale_is_safe(s) : !scale_is_safe(__float_as_uint(s));
             const bool add_zp = (QT == QT_FP8) ? (p.has_zp != 0) : true;
             const uint32_t z2 = (__float_as_uint(z) >> 16) * 0x10001u;
@@ -364,14 +370,14 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE>::value * 32, 1) group_tma_k
             for (int i0 = 0; i0 < NL; i0 += QB) {
             const uint32_t gblk = gswz ^ ((uint32_t)i0 << 4), oblk = oswz ^ ((uint32_t)i0 * OUT_CHUNK);
             uint4 vq[QB];
-            if (ONE) {  // the batch's loads first: one exposed LDS latency per QB chunks
+            if (ONE && PF) {  // the batch's loads first: one exposed LDS latency per QB chunks
 #pragma unroll
                 for (int j = 0; j < QB; j++) vq[j] = lds128(gblk ^ ((uint32_t)j << 4));
             }
 #pragma unroll
             for (int i = i0; i < i0 + QB; i++) {
                 const int c = i ^ rot;
-                const uint4 v = ONE ? vq[i - i0] : lds128(gblk ^ ((uint32_t)(i - i0) << 4));
+                const uint4 v = (ONE && PF) ? vq[i - i0] : lds128(gblk ^ ((uint32_t)(i - i0) << 4));
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
                 uint32_t h[4];
 #pragma unroll
@@ -487,20 +493,20 @@ __global__ void zp_pack_rows_kernel(const int8_t* __restrict__ zp, int64_t batch
     }
 }
 
-template <int QT, bool SYM, int LOG2N, bool FMA, int TILE, bool ONE>
+template <int QT, bool SYM, int LOG2N, bool FMA, int TILE, bool ONE, bool PF = true, int STAGES = kStages>
 int launch_tma_v(const TmaParams& p, cudaStream_t st) {
     constexpr int OUT_BYTES = (TILE / 8) * ((QT == QT_FP8) ? 8 : 4);
-    constexpr int kWarps = WarpsFor<QT, TILE>::value;
-    const size_t smem = (size_t)kWarps * (kStages * TILE * 2 + OUT_BYTES + 256);
+    constexpr int kWarps = WarpsFor<QT, TILE, STAGES>::value;
+    const size_t smem = (size_t)kWarps * (STAGES * TILE * 2 + OUT_BYTES + 256);
     static bool configured = false;  // benign race: idempotent attribute
     if (!configured) {
-        cudaFuncSetAttribute(group_tma_kernel<QT, SYM, LOG2N, FMA, TILE, false, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(group_tma_kernel<QT, SYM, LOG2N, FMA, TILE, false, ONE, PF, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     constexpr int GPT = TILE / (8 << LOG2N);
     const int64_t n_tiles = (p.n_groups + GPT - 1) / GPT;
     const int64_t ctas = max((int64_t)1, min((int64_t)kNumSMs, (n_tiles + kWarps - 1) / kWarps));
-    group_tma_kernel<QT, SYM, LOG2N, FMA, TILE, false, ONE><<<(unsigned)ctas, kWarps * 32, smem, st>>>(p);
+    group_tma_kernel<QT, SYM, LOG2N, FMA, TILE, false, ONE, PF, STAGES><<<(unsigned)ctas, kWarps * 32, smem, st>>>(p);
     B200Q_CHECK_LAUNCH();
     if (QT == QT_INT && !SYM && p.zp_i8 != nullptr) {
         const int64_t words = (p.n_groups / p.groups_per_mat) * ((p.rows + 7) >> 3) * p.groups_per_row;
@@ -525,6 +531,19 @@ int launch_tma(const TmaParams& p, cudaStream_t st) {
     static const int tile = getenv("B200Q_TMA_TILE") ? atoi(getenv("B200Q_TMA_TILE")) : 4096;
     static const bool fma = getenv("B200Q_TMA_LEGACY_ALU") ? false : (getenv("B200Q_TMA_FMA") ? true : QT == QT_INT);
     static const bool bracket = getenv("B200Q_TMA_BRACKET") != nullptr;
+    // A/B variants of the INT4 kernels (identical bits): B200Q_TMA_VAR = 1 ONE without the batched loads, 2 / 3 ONE with a 3- / 4-deep
+    // ring and 8 / 6 warps, 4 / 5 the bracket kernel with a 3- / 4-deep ring
+    static const int var = getenv("B200Q_TMA_VAR") ? atoi(getenv("B200Q_TMA_VAR")) : 0;
+    if constexpr (QT == QT_INT) {
+        switch (var) {
+        case 1: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, false, 2>(p, st);
+        case 2: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, true, 3>(p, st);
+        case 3: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, true, 4>(p, st);
+        case 4: return launch_tma_v<QT, SYM, LOG2N, true, 4096, false, true, 3>(p, st);
+        case 5: return launch_tma_v<QT, SYM, LOG2N, true, 4096, false, true, 4>(p, st);
+        default: break;
+        }
+    }
     if constexpr (QT != QT_FP4) {
         if (!bracket) return fma ? launch_tma_v<QT, SYM, LOG2N, true, 4096, true>(p, st) : launch_tma_v<QT, SYM, LOG2N, false, 4096, true>(p, st);
         if (tile == 2048) return launch_tma_v<QT, SYM, LOG2N, true, 2048, false>(p, st);

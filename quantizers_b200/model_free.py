@@ -34,7 +34,7 @@ import torch
 
 from . import _lib as L
 from . import numa, ops
-from .recipe import match_name, preset_args
+from .recipe import match_name, preset_args, preset_input_args
 from .scheduler import SchemeArgs
 
 _ST_DTYPES = {"BF16": (torch.bfloat16, 2), "F16": (torch.float16, 2), "F32": (torch.float32, 4), "F64": (torch.float64, 8),
@@ -294,11 +294,14 @@ def model_free_ptq(model_stub: str, save_directory: str, scheme="FP8_BLOCK", ign
         w.close()
 
     if rank == 0:
-        _write_sidecars(model_stub, save_directory, a, list(ignore), weight_map, shards)
+        # a preset name carries its input-activation half into quantization_config (FP8_BLOCK: dynamic group-128 fp8 inputs)
+        _write_sidecars(model_stub, save_directory, a, list(ignore), weight_map, shards,
+                        preset_input_args(scheme) if isinstance(scheme, str) else None)
     return stats
 
 
-def _write_sidecars(src: str, dst: str, a: SchemeArgs, ignore: List[str], weight_map: Dict[str, str], shards: List[str]):
+def _write_sidecars(src: str, dst: str, a: SchemeArgs, ignore: List[str], weight_map: Dict[str, str], shards: List[str],
+                    input_activations: Optional[SchemeArgs] = None):
     """index json with the new tensor names, config.json with the quantization_config block, every other small file copied."""
     for f in os.listdir(src):
         p = os.path.join(src, f)
@@ -318,11 +321,10 @@ def _write_sidecars(src: str, dst: str, a: SchemeArgs, ignore: List[str], weight
     if os.path.exists(cfg_path):
         with open(cfg_path) as f:
             cfg = json.load(f)
-    cfg["quantization_config"] = {
-        "quant_method": "compressed-tensors", "format": a.format, "quantization_status": "compressed", "ignore": ignore,
-        "config_groups": {"group_0": {"targets": ["Linear"], "format": a.format, "input_activations": None, "output_activations": None,
-                                      "weights": {"num_bits": a.num_bits, "type": a.type, "symmetric": a.symmetric, "strategy": a.strategy,
-                                                  "group_size": a.group_size, "block_structure": a.block_structure, "dynamic": False,
-                                                  "observer": "memoryless_minmax"}}}}
+    from .recipe import ConfigGroup, group_to_dict
+
+    grp = group_to_dict(ConfigGroup("group_0", ["Linear"], a, input_activations))
+    cfg["quantization_config"] = {"quant_method": "compressed-tensors", "format": grp["format"], "quantization_status": "compressed",
+                                  "ignore": ignore, "config_groups": {"group_0": grp}}
     with open(os.path.join(dst, "config.json"), "w") as f:
         json.dump(cfg, f, indent=2)

@@ -23,7 +23,8 @@ import torch
 
 from . import awq as _awq
 from . import ops
-from .recipe import ConfigGroup, ModifierSpec, Recipe, load_recipe, parse_recipe, resolve_mappings, resolve_targets
+from .recipe import (ConfigGroup, ModifierSpec, Recipe, default_mappings, group_to_dict, load_recipe, parse_recipe, resolve_mappings,
+                     resolve_targets)
 
 FUSED_SIBLINGS = (("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj"))  # LLMC modifiers/utils/helpers.py
 
@@ -98,16 +99,10 @@ def quantize_model(model: torch.nn.Module, recipe: Union[str, dict, Recipe], mod
     for g in spec.config_groups:
         if g.weights is None:
             continue
-        a = g.weights
-        formats.add(a.format)
-        cfg["config_groups"][g.name] = {
-            "targets": list(g.targets), "format": a.format,
-            "weights": {"num_bits": a.num_bits, "type": a.type, "symmetric": a.symmetric, "strategy": a.strategy,
-                        "group_size": a.group_size, "block_structure": a.block_structure, "dynamic": getattr(a, "dynamic", False),
-                        "observer": getattr(a, "observer", "memoryless_minmax")},
-            "input_activations": None if g.input_activations is None else {
-                "num_bits": g.input_activations.num_bits, "type": g.input_activations.type, "strategy": g.input_activations.strategy,
-                "group_size": g.input_activations.group_size, "dynamic": getattr(g.input_activations, "dynamic", False)}}
+        # weights AND input activations (dynamic ones included) + the format compressed-tensors infers from both: a serving
+        # engine picks its kernel from this block (FP8_BLOCK = dynamic group-128 fp8 activations, not W8A16)
+        cfg["config_groups"][g.name] = group_to_dict(g)
+        formats.add(cfg["config_groups"][g.name]["format"])
     cfg["format"] = formats.pop() if len(formats) == 1 else "mixed-precision"
     return sd, cfg
 
@@ -250,15 +245,23 @@ def awq_model(model: torch.nn.Module, recipe: Union[str, dict, Recipe], calibrat
     spec = rec.modifier(modifier)
     if spec is None:
         raise ValueError(f"the recipe has no {modifier}")
-    if not spec.mappings:
-        raise ValueError("AWQModifier needs explicit `mappings:` here (the model-family defaults live in llmcompressor)")
     lin = _linears(model)
     targets = resolve_targets(lin, spec)
     names = [n for n, _ in model.named_modules()]
     mods = dict(model.named_modules())
+    if not spec.mappings:
+        # no `mappings:` in the recipe (REF:configs/recipes/recipe_awq_w4a16.yaml): llmcompressor's model-family defaults
+        import dataclasses
+
+        spec = dataclasses.replace(spec, mappings=default_mappings(names))
     resolved = []
     for s_name, balance, parent in resolve_mappings(names, spec):
         balance = [b for b in balance if b in targets]
+        sm = mods[s_name]
+        if isinstance(sm, torch.nn.Linear) and balance and any(mods[b].in_features != sm.out_features for b in balance):
+            # v_proj -> o_proj under grouped-query attention: v has fewer output channels than o has inputs, the scales cannot
+            # be folded into v's rows; llmcompressor drops the mapping (modifiers/awq/base.py _set_resolved_mappings)
+            continue
         if balance:
             if len(balance) == 1:
                 parent = balance[0]

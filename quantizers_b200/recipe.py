@@ -40,15 +40,64 @@ _PRESET_WEIGHTS: Dict[str, Optional[dict]] = {
     "NVFP4A16": dict(num_bits=4, type="float", symmetric=True, strategy="tensor_group", group_size=16),
     "NVFP4": dict(num_bits=4, type="float", symmetric=True, strategy="tensor_group", group_size=16),
 }
-# input-activation halves that need calibration (static); dynamic ones have no observer and nothing to calibrate
+# input-activation halves of the presets (CT:quantization/quant_scheme.py:159-428).  Static ones (FP8, NVFP4's global scale) are
+# calibrated; dynamic ones carry no observer and calibrate nothing, but they ARE part of the scheme a serving engine reads from
+# ``quantization_config`` (FP8_BLOCK = W8A8 with dynamic per-token-group-128 fp8 activations, not W8A16) and they decide the
+# compression format (CT:compressors/format.py: INT weights + activations -> int-quantized, not pack-quantized).
 _PRESET_INPUTS: Dict[str, dict] = {
+    "W8A8": dict(num_bits=8, type="int", symmetric=True, strategy="token", dynamic=True, observer=None),
+    "INT8": dict(num_bits=8, type="int", symmetric=True, strategy="token", dynamic=True, observer=None),
+    "W4A8": dict(num_bits=8, type="int", symmetric=True, strategy="token", dynamic=True, observer=None),
+    "W4AFP8": dict(num_bits=8, type="float", symmetric=True, strategy="token", dynamic=True, observer=None),
     "FP8": dict(num_bits=8, type="float", symmetric=True, strategy="tensor", dynamic=False, observer="memoryless_minmax"),
+    "FP8_DYNAMIC": dict(num_bits=8, type="float", symmetric=True, strategy="token", dynamic=True, observer=None),
+    "FP8_BLOCK": dict(num_bits=8, type="float", symmetric=True, strategy="group", group_size=128, dynamic=True, observer=None),
     "NVFP4": dict(num_bits=4, type="float", symmetric=True, strategy="tensor_group", group_size=16, dynamic="local", observer="static_minmax"),
 }
 
 
 class RecipeError(ValueError):
     pass
+
+
+def preset_input_args(name: str) -> Optional[SchemeArgs]:
+    """``QuantizationArgs`` of a preset's input activations (None for weight-only presets)."""
+    kw = _PRESET_INPUTS.get(str(name).upper())
+    return None if kw is None else _args_from_dict(kw)
+
+
+def infer_format(weights: Optional[SchemeArgs], input_activations: Optional[SchemeArgs] = None) -> str:
+    """The compression format compressed-tensors infers for a Linear with this scheme: the first compressor of
+    COMPRESSION_FORMAT_PRIORITY whose ``can_compress`` accepts it (CT:compressors/format.py:18-27,75-96; nvfp4/base.py:112-120,
+    pack_quantized/base.py:122-130, naive_quantized/base.py:114-149)."""
+    if weights is None:
+        return "dense"
+    if weights.type == "float" and weights.num_bits == 4 and weights.group_size == 16:
+        return "nvfp4-pack-quantized"
+    if weights.type == "int" and weights.num_bits in (4, 8) and input_activations is None:
+        return "pack-quantized"
+    if weights.type == "int" and input_activations is not None:
+        return "int-quantized"
+    if weights.type == "float" and input_activations is not None:
+        return "float-quantized"
+    return "naive-quantized"
+
+
+def args_to_dict(a: Optional[SchemeArgs]) -> Optional[dict]:
+    """A ``QuantizationArgs`` block as compressed-tensors serialises it into ``quantization_config`` (the fields of
+    ``QuantizationArgs.model_dump()``, CT:quantization/quant_args.py:157-262)."""
+    if a is None:
+        return None
+    dyn = getattr(a, "dynamic", False)
+    return {"num_bits": a.num_bits, "type": a.type, "symmetric": a.symmetric, "group_size": a.group_size, "strategy": a.strategy,
+            "block_structure": a.block_structure, "dynamic": dyn, "actorder": None, "scale_dtype": None, "zp_dtype": None,
+            "observer": getattr(a, "observer", "memoryless_minmax"), "observer_kwargs": dict(getattr(a, "observer_kwargs", {}) or {})}
+
+
+def group_to_dict(g: "ConfigGroup") -> dict:
+    """One ``config_groups`` entry of ``quantization_config`` (CT QuantizationScheme.model_dump + the inferred format)."""
+    return {"targets": list(g.targets), "weights": args_to_dict(g.weights), "input_activations": args_to_dict(g.input_activations),
+            "output_activations": None, "format": infer_format(g.weights, g.input_activations)}
 
 
 def preset_args(name: str) -> Optional[SchemeArgs]:
@@ -92,7 +141,8 @@ def _args_from_dict(d: dict) -> SchemeArgs:
         raise RecipeError("actorder (g_idx) is not supported by the fused kernels (no reference recipe enables it)")
     a = SchemeArgs(num_bits, qtype, symmetric, strategy, group_size, list(block) if block else None)
     a.dynamic = d.get("dynamic", False)
-    a.observer = d.get("observer", "memoryless_minmax")
+    # CT drops the observer of dynamic (non-local) schemes (quant_args.py validate_model_after)
+    a.observer = d["observer"] if "observer" in d else (None if a.dynamic is True else "memoryless_minmax")
     a.observer_kwargs = dict(d.get("observer_kwargs") or {})
     return a
 
@@ -177,12 +227,11 @@ def _parse_modifier(kind: str, body: dict) -> ModifierSpec:
         if isinstance(scheme, dict):  # {preset: [targets]} form
             for pname, tg in scheme.items():
                 spec.config_groups.append(ConfigGroup(f"group_{len(spec.config_groups)}", _as_list(tg), preset_args(pname),
-                                                      _args_from_dict(_PRESET_INPUTS[pname.upper()]) if pname.upper() in _PRESET_INPUTS else None,
-                                                      preset=str(pname).upper()))
+                                                      preset_input_args(pname), preset=str(pname).upper()))
         else:
             key = str(scheme).upper()
             spec.config_groups.append(ConfigGroup(f"group_{len(spec.config_groups)}", targets, preset_args(key),
-                                                  _args_from_dict(_PRESET_INPUTS[key]) if key in _PRESET_INPUTS else None, preset=key))
+                                                  preset_input_args(key), preset=key))
     for m in body.get("mappings") or []:
         spec.mappings.append(Mapping(_clean_pattern(m["smooth_layer"]), _as_list(m["balance_layers"])))
     spec.extra = {k: v for k, v in body.items() if k in ("offload_device", "sequential_targets", "kv_cache_scheme")}
@@ -238,14 +287,43 @@ def is_match(name: str, module, targets: Iterable[str], ignore: Iterable[str] = 
 
 
 def resolve_targets(named_modules: Iterable[Tuple[str, object]], spec: ModifierSpec) -> Dict[str, ConfigGroup]:
-    """module name -> config group of this modifier (first matching group wins, like apply_quantization_config's ordered scan)."""
+    """module name -> config group of this modifier, with compressed-tensors' priority (``match_targets``, CT:utils/match.py:
+    targets sorted so that exact names come before ``re:`` patterns, NAME matches tried before CLASS matches, first hit wins) --
+    independent of the order the groups are listed in: a ``re:.*mlp.*`` group takes a module from a ``Linear`` group listed first."""
+    flat = sorted(((t, g) for g in spec.config_groups for t in g.targets), key=lambda tg: ("re:" in tg[0], tg[0]))
     out: Dict[str, ConfigGroup] = {}
     for name, mod in named_modules:
-        for g in spec.config_groups:
-            if is_match(name, mod, g.targets, spec.ignore):
-                out[name] = g
-                break
+        if any(match_name(name, i) or _match_class(mod, i) for i in spec.ignore):
+            continue
+        hit = next((g for t, g in flat if match_name(name, t)), None)
+        if hit is None:
+            hit = next((g for t, g in flat if _match_class(mod, t)), None)
+        if hit is not None:
+            out[name] = hit
     return out
+
+
+# llmcompressor's model-family defaults (modifiers/awq/mappings.py, as recalled in SURVEY.md Appendix A line 508): used when the
+# AWQModifier block has no ``mappings:`` -- REF:configs/recipes/recipe_awq_w4a16.yaml (the recipe behind
+# REF:configs/test-quantize_qwen3-4b-awq.yaml) relies on them.
+DEFAULT_MAPPINGS = [
+    ("re:.*input_layernorm$", ["re:.*q_proj$", "re:.*k_proj$", "re:.*v_proj$"]),
+    ("re:.*v_proj$", ["re:.*o_proj$"]),
+    ("re:.*post_attention_layernorm$", ["re:.*gate_proj$", "re:.*up_proj$"]),
+    ("re:.*up_proj$", ["re:.*down_proj$"]),
+]
+MOE_DEFAULT_MAPPINGS = [
+    ("re:.*input_layernorm$", ["re:.*q_proj$", "re:.*k_proj$", "re:.*v_proj$"]),
+    ("re:.*v_proj$", ["re:.*o_proj$"]),
+    ("re:.*post_attention_layernorm$", ["re:.*mlp.experts.*.gate_proj$", "re:.*mlp.experts.*.up_proj$"]),
+    ("re:.*up_proj$", ["re:.*down_proj$"]),
+]
+
+
+def default_mappings(names: Sequence[str]) -> List[Mapping]:
+    """Llama / Qwen3-style defaults; the MoE table when the model has ``mlp.experts.<i>`` Linears (Qwen3-MoE family)."""
+    moe = any(re.search(r"\.mlp\.experts\.\d+\.", n) for n in names)
+    return [Mapping(s, list(b)) for s, b in (MOE_DEFAULT_MAPPINGS if moe else DEFAULT_MAPPINGS)]
 
 
 def resolve_mappings(names: Sequence[str], spec: ModifierSpec) -> List[Tuple[str, List[str], str]]:
@@ -255,13 +333,15 @@ def resolve_mappings(names: Sequence[str], spec: ModifierSpec) -> List[Tuple[str
     (a single balance layer is its own parent).  Mappings whose balance layers are all outside ``targets`` are dropped by the caller."""
     out = []
     for m in spec.mappings:
-        for s_name in names:
-            if not match_name(s_name, m.smooth_layer):
-                continue
+        # every pattern is matched against the module names ONCE (not once per smooth layer: 1e9 regex calls on a 62-layer,
+        # 256-expert model otherwise)
+        smooth_names = [n for n in names if match_name(n, m.smooth_layer)]
+        cands_of = {pat: [n for n in names if match_name(n, pat)] for pat in m.balance_layers}
+        for s_name in smooth_names:
             s_parts = s_name.split(".")
             balance: List[str] = []
             for pat in m.balance_layers:
-                cands = [n for n in names if match_name(n, pat) and n != s_name]
+                cands = [n for n in cands_of[pat] if n != s_name]
                 if not cands:
                     continue
 

@@ -32,9 +32,11 @@ class SchemeArgs:
 
     @property
     def format(self) -> str:
+        """Compression format of a WEIGHT-ONLY scheme with these args (CT:compressors/format.py priority); schemes with input
+        activations go through ``recipe.infer_format``.  All of naive- / int- / float-quantized share one compress arithmetic."""
         if self.type == "int":
             return "pack-quantized"
-        return "float-quantized" if self.num_bits == 8 else "nvfp4-pack-quantized"
+        return "naive-quantized" if self.num_bits == 8 else "nvfp4-pack-quantized"
 
     def bytes_per_element(self, elem_size: int = 2) -> float:
         """ALGORITHMIC HBM bytes per weight element of the fused compress."""

@@ -532,3 +532,88 @@ def test_oneshot_moe_calibrate_all_experts_on_fused_experts():
         assert torch.allclose(s, s_ref, rtol=1e-5)
         for p in ("gate_proj", "up_proj", "down_proj"):
             assert f"{pre}.{e}.{p}.weight_packed" in sd
+
+
+# REF:configs/recipes/recipe_awq_w4a16.yaml restated (same keys, same layout): NO `mappings:` -- llmcompressor's model-family
+# defaults apply (input_layernorm -> q/k/v, v -> o [dropped under GQA], post_attention_layernorm -> gate/up, up -> down)
+AWQ_DEFAULTS_RECIPE = """
+quantization_scheme:
+  type: W4A16
+  targets: ["Linear"]
+
+modifiers:
+  - name: AWQModifier
+    config_groups:
+      group_0:
+        targets: ["Linear"]
+        weights:
+          num_bits: 4
+          type: int
+          symmetric: true
+          group_size: 32
+          strategy: group
+          dynamic: false
+          observer: memoryless_minmax
+    ignore:
+      - "lm_head"
+    duo_scaling: true
+"""
+
+
+class GQAAttn(torch.nn.Module):
+    """Grouped-query attention: k / v project to HEADS_KV * d < H, so v_proj.out_features != o_proj.in_features."""
+
+    def __init__(self, kv_heads):
+        super().__init__()
+        d = H // HEADS
+        self.kv_heads = kv_heads
+        self.q_proj = torch.nn.Linear(H, H, bias=False)
+        self.k_proj = torch.nn.Linear(H, kv_heads * d, bias=False)
+        self.v_proj = torch.nn.Linear(H, kv_heads * d, bias=False)
+        self.o_proj = torch.nn.Linear(H, H, bias=False)
+
+    def forward(self, x):
+        B, S, _ = x.shape
+        d = H // HEADS
+        q = self.q_proj(x).view(B, S, HEADS, d).transpose(1, 2)
+        k = self.k_proj(x).view(B, S, self.kv_heads, d).transpose(1, 2)
+        v = self.v_proj(x).view(B, S, self.kv_heads, d).transpose(1, 2)
+        o = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=self.kv_heads != HEADS)
+        return self.o_proj(o.transpose(1, 2).reshape(B, S, H))
+
+
+@pytest.mark.parametrize("kv_heads", [HEADS, HEADS // 2])
+def test_awq_recipe_without_mappings_uses_family_defaults(kv_heads):
+    """the reference's main AWQ recipe has no `mappings:`; oneshot() must run it end to end.  MHA keeps v -> o, GQA drops
+    it (shapes cannot be folded).  Every search is checked against the restated oracle on the weights it actually saw."""
+    from quantizers_b200 import recipe as RC
+    from quantizers_b200.oneshot import oneshot, awq_model
+
+    m = _model(9)
+    for blk in m.model.layers:
+        blk.self_attn = GQAAttn(kv_heads).to(torch.bfloat16).cuda()
+        for p in blk.self_attn.parameters():
+            p.data.normal_(0, 0.05)
+    batches = _batches()
+    rec = RC.parse_recipe(AWQ_DEFAULTS_RECIPE)
+    assert [mod.kind for mod in rec.modifiers] == ["AWQModifier"] and not rec.modifiers[0].mappings
+    sd, cfg, results = awq_model(m, rec, batches)
+    per_layer = 4 if kv_heads == HEADS else 3
+    assert len(results) == 2 * per_layer, sorted(results)
+    has_vo = any("v_proj -> " in k for k in results)
+    assert has_vo == (kv_heads == HEADS)
+    for k, (s, r, losses) in results.items():
+        assert 0.0 <= r < 1.0 and all(l == l and l >= 0 for l in losses), k
+    # all seven projections of both layers quantized, lm_head ignored, format as compressed-tensors infers it
+    assert cfg["format"] == "pack-quantized" and cfg["ignore"] == ["lm_head"]
+    for l in range(2):
+        for name in ("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj", "mlp.gate_proj", "mlp.up_proj", "mlp.down_proj"):
+            w = dict(m.named_parameters())[f"model.layers.{l}.{name}.weight"].detach().cpu()
+            want = O.compress(w, "pack-quantized", O.Geom(O.GROUP, 32), 4, True)
+            for key, v in want.items():
+                assert_bits_equal(sd[f"model.layers.{l}.{name}.{key}"].reshape(v.shape), v, f"{name}.{key}")
+    assert not any(k.startswith("lm_head.weight_packed") for k in sd)
+    # and through the oneshot() entry point itself
+    m2 = _model(9)
+    sd2, cfg2 = oneshot(m2, AWQ_DEFAULTS_RECIPE, dataset=batches)
+    assert cfg2["config_groups"]["group_0"]["weights"]["group_size"] == 32

@@ -39,9 +39,11 @@ def test_block_output_unchanged(norm):
         ref = model(x)
         with MC.moe_calibrate_all_experts(model) as names:
             assert names == ["mlp"]
-            assert isinstance(model.mlp, MC.CalibrationSparseMoeBlock) and model.mlp.calibrate_all_experts
+            # the BLOCK is kept (its own forward / router / buffers); only `experts` is linearized
+            assert type(model.mlp) is type(blk) and isinstance(model.mlp.experts, MC.LinearizedExperts)
+            assert model.mlp.experts.calibrate_all_experts
             got_all = model(x)
-        assert not model.mlp.calibrate_all_experts          # linearized for good, sparse again
+        assert not model.mlp.experts.calibrate_all_experts  # linearized for good, sparse again
         got_sparse = model(x)
     torch.testing.assert_close(got_all, ref, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(got_sparse, ref, rtol=1e-5, atol=1e-6)
@@ -116,11 +118,93 @@ def test_linear_router_and_module_list_experts():
     assert model.mlp.experts[0].w1.weight.shape == (I, H)    # expert modules kept as they were
 
 
-def test_blocks_with_shared_experts_are_left_alone():
+def test_block_with_buffers_and_shared_experts_is_kept():
+    """MiniMax-M2 / GLM style blocks -- a block-level correction-bias buffer used by the routing, a router called with
+    extra arguments, shared experts, w1/w3/w2 expert names.  The block must survive: same output, buffer still in the state dict,
+    expert Linears visible under the checkpoint's names, every expert sees every token inside the context."""
+    torch.manual_seed(3)
+    E, H, I, k = 4, 32, 16, 2
+
+    class Expert(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w1, self.w3, self.w2 = torch.nn.Linear(H, I, bias=False), torch.nn.Linear(H, I, bias=False), torch.nn.Linear(I, H, bias=False)
+
+        def forward(self, x):
+            return self.w2(torch.nn.functional.silu(self.w1(x)) * self.w3(x))
+
+    class Gate(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.weight = torch.nn.Parameter(torch.randn(E, H) * 0.3)
+
+        def forward(self, x, bias):                     # router called with the block's buffer
+            return torch.sigmoid(torch.nn.functional.linear(x, self.weight)) + bias
+
+    class MiniMaxM2SparseMoeBlock(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gate = Gate()
+            self.experts = torch.nn.ModuleList([Expert() for _ in range(E)])
+            self.shared_experts = Expert()
+            self.register_buffer("e_score_correction_bias", torch.randn(E) * 0.1)
+
+        def forward(self, x):
+            shp = x.shape
+            x = x.reshape(-1, H)
+            scores = self.gate(x, self.e_score_correction_bias)
+            w, idx = torch.topk(scores, k, dim=-1)
+            w = w / w.sum(-1, keepdim=True)
+            out = torch.zeros_like(x)
+            for e in range(E):
+                pos, tok = torch.where((idx == e).t())
+                if tok.numel():
+                    out.index_add_(0, tok, self.experts[e](x[tok]) * w[tok, pos, None])
+            return (out + self.shared_experts(x)).reshape(shp)
+
+    model = _Holder(MiniMaxM2SparseMoeBlock())
+    x = torch.randn(2, 11, H)
+    seen = {}
+    with torch.no_grad():
+        ref = model(x)
+        with MC.moe_calibrate_all_experts(model) as names:
+            assert names == ["mlp"] and type(model.mlp).__name__ == "MiniMaxM2SparseMoeBlock"
+            hs = [m.register_forward_pre_hook(lambda mod, a, n=n: seen.__setitem__(n, seen.get(n, 0) + a[0].shape[0]))
+                  for n, m in model.named_modules() if n.endswith(".w1") and ".experts." in n]
+            got = model(x)
+            for h in hs:
+                h.remove()
+        sparse = model(x)
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(sparse, ref, rtol=1e-5, atol=1e-6)
+    assert set(seen.values()) == {22} and len(seen) == E            # every expert saw all 22 tokens exactly once
+    sd = model.state_dict()
+    assert "mlp.e_score_correction_bias" in sd and "mlp.shared_experts.w1.weight" in sd
+    assert "mlp.experts.3.w2.weight" in sd and not any(".inner." in k2 for k2 in sd)
+
+
+def test_fused_experts_take_the_architecture_leaf_names():
     blk = _hf_block()
-    blk.shared_expert = torch.nn.Linear(64, 64)
-    model = _Holder(blk)
-    assert MC.replace_moe_blocks(model) == []
+    type(blk).__name__  # Qwen3MoeSparseMoeBlock -> gate_proj / up_proj / down_proj
+    assert MC.expert_leaf_names(blk) == ("gate_proj", "up_proj", "down_proj")
+
+    class MixtralSparseMoeBlock(torch.nn.Module):
+        pass
+
+    assert MC.expert_leaf_names(MixtralSparseMoeBlock()) == ("w1", "w3", "w2")
+    ex = MC.linearize_experts(blk.experts, ("w1", "w3", "w2"))
+    assert sorted(n for n, _ in ex[0].named_children() if n.startswith("w")) == ["w1", "w2", "w3"]
+
+
+def test_unhandled_experts_container_raises():
+    class Odd(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gate = torch.nn.Linear(4, 2)
+            self.experts = torch.nn.Linear(4, 4)           # neither fused 3-D parameters nor a ModuleList
+
+    with pytest.raises(NotImplementedError):
+        MC.replace_moe_blocks(_Holder(Odd()))
 
 
 def test_linearize_rejects_inconsistent_shapes():

@@ -166,3 +166,87 @@ def test_every_reference_recipe_parses():
                 assert grp.weights is not None and grp.weights.num_bits in (4, 8), (fname, m.kind)
     awq = R.load_recipe(os.path.join(_REF_RECIPES, "recipe_Minimax-M2.1-Experts-only-AWQ.yaml")).modifiers[0]
     assert awq.mappings and len(awq.mappings) >= 2
+
+
+def test_config_groups_serialise_like_compressed_tensors_presets():
+    """quantization_config carries the FULL preset (weights + input activations, dynamic ones included) and the format
+    compressed-tensors infers from both (FP8_BLOCK was written as W8A16 / INT+activations as pack-quantized)."""
+    ct = pytest.importorskip("compressed_tensors")
+    import json
+
+    from compressed_tensors.compressors.format import infer_module_format
+    from compressed_tensors.quantization.quant_scheme import preset_name_to_scheme
+    import torch
+
+    from quantizers_b200 import recipe as R
+
+    for name in ("W8A16", "W4A16", "W4A16_ASYM", "W8A8", "INT8", "W4A8", "W4AFP8", "FP8", "FP8_DYNAMIC", "FP8_BLOCK", "NVFP4A16", "NVFP4"):
+        scheme = preset_name_to_scheme(name, ["Linear"])
+        want = json.loads(scheme.model_dump_json())
+        grp = R.group_to_dict(R.ConfigGroup("g", ["Linear"], R.preset_args(name), R.preset_input_args(name), preset=name))
+        for half in ("weights", "input_activations"):
+            if want[half] is None:
+                assert grp[half] is None, (name, half)
+                continue
+            for key in ("num_bits", "type", "symmetric", "group_size", "strategy", "block_structure", "dynamic", "observer"):
+                assert grp[half][key] == want[half][key], (name, half, key, grp[half][key], want[half][key])
+        assert grp["format"] == infer_module_format(torch.nn.Linear, scheme).value, name
+
+
+def test_format_of_explicit_groups():
+    from quantizers_b200 import recipe as R
+
+    fp8_w = R._args_from_dict(dict(num_bits=8, type="float", strategy="group", group_size=32))
+    assert R.infer_format(fp8_w, None) == "naive-quantized"          # FP8 weight-only (MiniMax mixed-precision AWQ recipe)
+    int4 = R._args_from_dict(dict(num_bits=4, type="int", strategy="group", group_size=32))
+    assert R.infer_format(int4, None) == "pack-quantized"
+    assert R.infer_format(int4, R.preset_input_args("W4A8")) == "int-quantized"
+
+
+def test_resolve_targets_priority_is_order_independent():
+    """CT match_targets: name / regex matches beat class matches whatever the group order."""
+    import torch
+
+    from quantizers_b200 import recipe as R
+
+    doc = """
+quant_stage:
+  quant_modifiers:
+    QuantizationModifier:
+      ignore: ["lm_head"]
+      config_groups:
+        everything:
+          targets: ["Linear"]
+          weights: {num_bits: 8, type: float, strategy: channel}
+        mlp:
+          targets: ["re:.*mlp.*"]
+          weights: {num_bits: 4, type: int, strategy: group, group_size: 32}
+"""
+    spec = R.parse_recipe(doc).modifiers[0]
+    mods = [("model.layers.0.self_attn.q_proj", torch.nn.Linear(4, 4)), ("model.layers.0.mlp.up_proj", torch.nn.Linear(4, 4)),
+            ("lm_head", torch.nn.Linear(4, 4))]
+    got = R.resolve_targets(mods, spec)
+    assert got["model.layers.0.self_attn.q_proj"].name == "everything"
+    assert got["model.layers.0.mlp.up_proj"].name == "mlp"
+    assert "lm_head" not in got
+
+
+def test_default_mappings_and_bucketed_resolution():
+    from quantizers_b200 import recipe as R
+
+    names = []
+    for l in range(3):
+        p = f"model.layers.{l}"
+        names += [p, f"{p}.input_layernorm", f"{p}.self_attn", f"{p}.self_attn.q_proj", f"{p}.self_attn.k_proj", f"{p}.self_attn.v_proj",
+                  f"{p}.self_attn.o_proj", f"{p}.post_attention_layernorm", f"{p}.mlp", f"{p}.mlp.gate_proj", f"{p}.mlp.up_proj",
+                  f"{p}.mlp.down_proj"]
+    spec = R.ModifierSpec(kind="AWQModifier", mappings=R.default_mappings(names))
+    res = R.resolve_mappings(names, spec)
+    assert len(res) == 3 * 4
+    by_smooth = {s: (b, p) for s, b, p in res}
+    b, p = by_smooth["model.layers.1.input_layernorm"]
+    assert b == [f"model.layers.1.self_attn.{x}_proj" for x in "qkv"] and p == "model.layers.1.self_attn"
+    b, p = by_smooth["model.layers.2.mlp.up_proj"]
+    assert b == ["model.layers.2.mlp.down_proj"] and p == "model.layers.2.mlp.down_proj"
+    moe = [n.replace("mlp.gate_proj", "mlp.experts.0.gate_proj") for n in names]
+    assert R.default_mappings(moe)[2].balance_layers[0].startswith("re:.*mlp.experts")
