@@ -13,7 +13,11 @@ observer -> qparams -> quantize -> pack path over the whole model.
             packed HOST tensors out, host<->device copies inside the timed region
   roofline: dominant kernel (INT4 group kernel) algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
   N > 1   : weak scaling -- every rank quantizes its own 36-layer shard (layers are independent units; no
-            data-path collective), value = N * bytes / max-over-ranks time
+            data-path collective), value = N * bytes / max-over-ranks time.  ``headline_strong`` is the same job with a FIXED 36
+            layers partitioned over the ranks (scheduler.partition), replayed as one CUDA graph per rank.
+  legs    : further driver-visible legs -- config 1 AWQ search (layers/s, tensor roofline), config 3 GLM-4.7-Flash FP8 block /
+            per-channel + model_free_ptq file -> file, config 4 NVFP4 experts (strong), config 5 MiniMax expert mappings (strong);
+            a compact {value, frac} summary of every leg and the sharded == unsharded ``parity`` flags are the LAST keys of the line.
 """
 from __future__ import annotations
 
@@ -139,9 +143,51 @@ def cpu_kind():
     return "reference" if L.available() else "port"
 
 
+def cpu_observer_layer(layer, kind: str):
+    """Observer-only part of the metric on the CPU: min/max statistics -> calculate_qparams for every matrix of one layer."""
+    nbytes = 0
+    for _, fmt_name, w in layer:
+        if kind == "reference":
+            from oracle import ct_live as L
+
+            _, a = L.format_args(fmt_name)
+            L.weight_qparams(w, a)
+        else:
+            from oracle import oracle as O
+
+            geom = O.Geom(O.BLOCK, 0, 128, 128) if fmt_name == "fp8_block" else O.Geom(O.GROUP, 128)
+            mn, mx = O.minmax(w, geom)
+            O.calculate_qparams(mn, mx, O.FP8 if fmt_name == "fp8_block" else O.INT, 8 if fmt_name == "fp8_block" else 4, fmt_name == "fp8_block")
+        nbytes += w.numel() * 2
+    return nbytes
+
+
+def awq_cpu_layer(tokens: int, full_tokens: int):
+    """The restated llmcompressor search on LIVE compressed-tensors arithmetic (oracle/llmc_live.py), whole Qwen3-4B decoder layer
+    (q/k/v, gate/up, down mappings, n_grid 20, W4A16 g128 asym) on ``tokens`` calibration tokens, torch CPU GEMMs on all host
+    threads.  Returns (seconds measured, seconds extrapolated to ``full_tokens``, timers): the weight fake-quantisation does not
+    depend on the token count, statistics and parent forwards scale linearly with it."""
+    from oracle import ct_live as L
+    from oracle import llmc_live as V
+    from quantizers_b200 import scheduler as S
+
+    w, acts = S.synth_awq_layer(0, tokens, torch.device("cpu"))
+    _, a = L.format_args("int4_g128_asym")
+    timers = {}
+    t0 = time.perf_counter()
+    V.search_decoder_layer(w, acts, a, n_heads=32, n_kv=8, head_dim=128, seq_len=512, timers=timers)
+    sec = time.perf_counter() - t0
+    k = full_tokens / tokens
+    est = timers.get("weights", 0.0) + k * (timers.get("forward", 0.0) + timers.get("stats", 0.0))
+    est += max(sec - sum(timers.values()), 0.0)
+    return sec, est, {k2: round(v, 2) for k2, v in timers.items()}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation (live compressed_tensors when importable, else the
-    oracle port) on the host cores; each step = one decoder layer of the same workload (bounded sample)."""
+    oracle port) on the host cores; each step = one decoder layer of the same workload (bounded sample).  The other two parts
+    of the BASELINE metric ride along as ``legs``: observer-only (statistics -> qparams) and the AWQ search of one layer on a
+    token-subsampled problem (restated loop on live compressed-tensors)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -158,6 +204,20 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = nbytes / dt / 1e9
     sample = "one Qwen3-4B decoder layer (7 matrices, 201.9 MB bf16) per step"
+    legs = {}
+    t0 = time.perf_counter()
+    nb = sum(cpu_observer_layer(layers[i % 2], kind) for i in range(4))
+    legs["observer_only"] = {"value": nb / (time.perf_counter() - t0) / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "4 decoder layers: min/max statistics -> calculate_qparams only"}
+    if kind == "reference" and args.cpu_awq_tokens > 0:
+        try:
+            sec, est, timers = awq_cpu_layer(args.cpu_awq_tokens, args.awq_tokens)
+            legs["awq"] = {"value": 1.0 / est, "unit": "layers/s", "cores": cores, "kind": "reference (live compressed-tensors arithmetic, restated llmcompressor loop)",
+                           "measured_s": sec, "tokens": args.cpu_awq_tokens, "timers_s": timers,
+                           "sample": f"whole decoder layer (q/k/v, gate/up, down mappings, n_grid 20) on {args.cpu_awq_tokens} tokens took {sec:.1f} s; "
+                                     f"forward + statistics scaled by {args.awq_tokens}/{args.cpu_awq_tokens}, weight fake-quantisation kept -> {est:.0f} s per layer"}
+        except Exception as e:  # noqa: BLE001 -- informational leg
+            legs["awq"] = {"unavailable": str(e)[:200]}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -165,6 +225,7 @@ def run_reference(args):
         "config": {"workload": "qwen3-4b mixed FP8_BLOCK(attn)+INT4 g128 asym(MLP) RTN quantize+pack", "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "legs": legs,
     }), flush=True)
 
 
@@ -200,12 +261,43 @@ def run_e2e(spec, arena, steps, warmup, device_index):
         step()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    submit = 0.0
     for _ in range(steps):
-        step()
+        ts = time.perf_counter()
+        for hw, rows, cols, sc, codes, scale, zp in jobs:
+            L.check(lib.b200q_pipeline_compress_host(handle, L.ptr(hw), 1, rows, cols, ctypes.byref(sc), L.ptr(codes), L.ptr(scale),
+                                                     L.ptr(zp), None))
+        submit += time.perf_counter() - ts
+        L.check(lib.b200q_pipeline_sync(handle))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     lib.b200q_pipeline_destroy(handle)
-    return h2d * steps / dt / 1e9, h2d, d2h, dt, bound
+    # ---- what bounds it (round-1 verdict, weak #7): the same pinned buffers through bare copies, no kernels, all ranks at once
+    import torch.distributed as dist
+
+    def bare(direction):
+        dev_buf = arena[spec.matrices[-1].name]
+        src = jobs[-1][0]
+        n = 0
+        torch.cuda.synchronize()
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+        tb = time.perf_counter()
+        for hw, rows, cols, sc, codes, scale, zp in jobs:
+            if direction == "h2d":
+                dev_buf.view(-1)[: hw.numel()].copy_(hw.view(-1), non_blocking=True)
+                n += hw.numel() * 2
+            else:
+                codes.view(-1).copy_(dev_buf.view(torch.uint8).view(-1)[: codes.numel() * codes.element_size()].view(codes.dtype), non_blocking=True)
+                n += codes.numel() * codes.element_size()
+        torch.cuda.synchronize()
+        return n / (time.perf_counter() - tb) / 1e9
+
+    breakdown = {"h2d_only_GBps": bare("h2d"), "d2h_only_GBps": bare("d2h"), "submit_ms_per_step": submit / steps * 1e3,
+                 "step_ms": dt / steps * 1e3, "calls_per_step": len(jobs),
+                 "note": "bare cudaMemcpyAsync of the same pinned buffers on every rank at once vs the pipelined step (H2D and D2H overlap in the "
+                         "pipeline); submit = host time spent issuing the step's C calls"}
+    return h2d * steps / dt / 1e9, h2d, d2h, dt, bound, breakdown
 
 
 def _e2e_buffers(spec, arena, ops, PRESETS):
@@ -318,14 +410,17 @@ def run_awq(args, dev, world, rank, peaks):
                         "frac_of_burst": tf / float(peaks.get("bf16_tflops", 1667.5)) if peaks else None,
                         "kernels": "awq_gemm_project_kernel / awq_gemm_loss_kernel (tcgen05, TMEM)"},
            "e2e": {"value": world * 1e3 / float(e2e_ms.item()), "unit": "layers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.cpu_awq_tokens > 0:
         torch.set_num_threads(os.cpu_count() or 1)
-        sec = awq_cpu_sample(512)
-        # one mapping of three, 512 of T tokens: the GEMM + loss part scales with tokens and is 1.63/8.5 of a layer's FLOPs
-        est = sec * (T / 512) * (8.5 / 1.63)
-        out["cpu_baseline"] = {"value": 1.0 / est, "unit": "layers/s", "cores": torch.get_num_threads(), "kind": "port",
-                               "sample": f"restated search of the down_proj mapping on 512 tokens took {sec:.1f} s; scaled by tokens ({T}/512) "
-                                         "and by the mapping's share of a layer's FLOPs (1.63/8.5)"}
+        try:
+            sec, est, timers = awq_cpu_layer(args.cpu_awq_tokens, T)
+            out["cpu_baseline"] = {"value": 1.0 / est, "unit": "layers/s", "cores": torch.get_num_threads(),
+                                   "kind": "reference (live compressed-tensors arithmetic, restated llmcompressor loop)",
+                                   "measured_s": sec, "timers_s": timers,
+                                   "sample": f"whole decoder layer (q/k/v, gate/up, down mappings, n_grid 20) on {args.cpu_awq_tokens} tokens took {sec:.1f} s; "
+                                             f"forward + statistics scaled by {T}/{args.cpu_awq_tokens}, weight fake-quantisation kept -> {est:.0f} s per layer"}
+        except Exception as e:  # noqa: BLE001 -- informational leg
+            out["cpu_baseline"] = {"unavailable": str(e)[:200]}
     return out
 
 
@@ -474,6 +569,248 @@ def run_moe_block(args, dev, world, rank, peak):
                          "note": "routed pairs sorted expert-major, rows padded to 128-row tiles; per-GPU figure of the slowest rank"}}
 
 
+# ----------------------------------------------------------------------------- strong-scaling headline, GLM leg, parity
+def run_headline_strong(args, dev, world, rank, peaks):
+    """The headline job with a FIXED size: the 36 decoder layers of Qwen3-4B partitioned over the ranks (scheduler.partition,
+    4.5 layers per GPU at N = 8, no data-path collective).  One step = this rank's layers; the 7 launches of a step are captured
+    once in a CUDA graph and replayed (at N = 8 a step is ~0.2 ms of kernels, launch-bound otherwise)."""
+    import torch.distributed as dist
+
+    from quantizers_b200 import scheduler as S
+
+    layers = S.partition(36, world, rank)
+    spec = S.qwen3_4b(layers=len(layers))
+    arena = S.build_arena(spec, list(layers), dev)
+    outs = S.alloc_outputs(spec, arena)
+    for _ in range(3):
+        S.quantize_arena(spec, arena, out=outs)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        S.quantize_arena(spec, arena, out=outs)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(args.steps, 20)
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    total = 36 * S.qwen3_4b(layers=1).unit_bytes()
+    alg = sum(S.PRESETS[m.preset].bytes_per_element() * m.rows * m.cols * m.per_unit for m in spec.matrices) * len(layers)
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    return {"metric": METRIC, "value": total / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "scaling": "strong", "steps": steps,
+            "config": {"workload": "qwen3-4b mixed FP8_BLOCK + INT4 g128 asym, 36 layers partitioned over the ranks", "layers_per_gpu": len(layers),
+                       "launch": "one CUDA graph replay per step"},
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "note": "whole step (all 5 classes) of the slowest rank"}}
+
+
+def run_glm(args, dev, world, rank, peaks):
+    """configs[2]: GLM-4.7-Flash-shaped FP8 quantization (REF:scripts/quant_GLM-4.7-Flash-FP8.py:11-24).  (a) the fused kernels on the
+    synthetic expert / dense shapes incl. the ragged [2624, 2048] rows (FP8_BLOCK 128x128, and FP8 per-channel = FP8_DYNAMIC weights),
+    the ``--glm-units`` units sharded over the ranks (strong); (b) ``model_free_ptq`` file -> file on a page-cached synthetic
+    safetensors checkpoint, shards split over the ranks: read -> pinned staging -> H2D -> kernel -> D2H -> pwrite."""
+    import shutil
+    import tempfile
+
+    import torch.distributed as dist
+
+    from quantizers_b200 import scheduler as S
+
+    units = S.partition(args.glm_units, world, rank)
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    out = {}
+    for preset in ("FP8_BLOCK", "FP8_CHANNEL"):
+        spec = S.glm47_flash(preset, units=len(units))
+        arena = S.build_arena(spec, list(units), dev)
+        outs = S.alloc_outputs(spec, arena)
+        for _ in range(3):
+            S.quantize_arena(spec, arena, out=outs)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.moe_steps):
+            S.quantize_arena(spec, arena, out=outs)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / args.moe_steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        total = args.glm_units * spec.unit_bytes()
+        alg = S.PRESETS[preset].bytes_per_element() * len(units) * spec.unit_elements()
+        out[preset.lower()] = {"metric": METRIC, "value": total / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "scaling": "strong",
+                               "config": {"workload": f"glm-4.7-flash shapes {preset}: gate/up [1536,2048] x2, down [2048,1536], dense [10240,2048], "
+                                                      "ragged [2624,2048] per unit", "units": args.glm_units, "units_per_gpu": len(units)},
+                               "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                            "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None}}
+        del arena, outs
+        torch.cuda.empty_cache()
+    # ---- (b) model_free_ptq, file -> file
+    if args.glm_file_gb > 0:
+        from safetensors.torch import save_file
+
+        from quantizers_b200.model_free import model_free_ptq
+
+        root = None
+        if rank == 0:
+            root = tempfile.mkdtemp(prefix="b200q_glm_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        if world > 1:
+            box = [root]
+            dist.broadcast_object_list(box, src=0)
+            root = box[0]
+        src, dst = os.path.join(root, "src"), os.path.join(root, "dst")
+        n_shards = max(8, world)
+        per_layer = 2 * (1536 * 2048 * 2 + 2048 * 1536) + 10240 * 2048 * 2 + 2624 * 2048 * 2
+        layers_per_shard = max(1, int(args.glm_file_gb * 1e9 / n_shards / per_layer))
+        total = 0
+        if rank == 0:
+            os.makedirs(src)
+            g = torch.Generator().manual_seed(0)
+            for sh in range(n_shards):
+                t = {}
+                for i in range(layers_per_shard):
+                    l = sh * layers_per_shard + i
+                    t[f"model.layers.{l}.mlp.experts.0.gate_proj.weight"] = (torch.randn(1536, 2048, generator=g) * 0.02).to(torch.bfloat16)
+                    t[f"model.layers.{l}.mlp.experts.0.up_proj.weight"] = (torch.randn(1536, 2048, generator=g) * 0.02).to(torch.bfloat16)
+                    t[f"model.layers.{l}.mlp.experts.0.down_proj.weight"] = (torch.randn(2048, 1536, generator=g) * 0.02).to(torch.bfloat16)
+                    t[f"model.layers.{l}.mlp.shared_experts.up_proj.weight"] = (torch.randn(10240, 2048, generator=g) * 0.02).to(torch.bfloat16)
+                    t[f"model.layers.{l}.self_attn.kv_b_proj.weight"] = (torch.randn(2624, 2048, generator=g) * 0.02).to(torch.bfloat16)
+                    t[f"model.layers.{l}.self_attn.q_a_proj.weight"] = (torch.randn(768, 2048, generator=g) * 0.02).to(torch.bfloat16)   # ignored
+                    t[f"model.layers.{l}.input_layernorm.weight"] = torch.ones(2048, dtype=torch.bfloat16)
+                save_file(t, os.path.join(src, f"model-{sh + 1:05d}-of-{n_shards:05d}.safetensors"), metadata={"format": "pt"})
+            with open(os.path.join(src, "config.json"), "w") as f:
+                json.dump({"model_type": "glm4_moe_lite", "hidden_size": 2048}, f)
+        if world > 1:
+            dist.barrier()
+        total = sum(os.path.getsize(os.path.join(src, f)) for f in os.listdir(src) if f.endswith(".safetensors"))
+        ignore = ["re:.*q_a_proj$", "re:.*kv_a_proj_with_mqa$", "re:.*mlp.gate$", "lm_head"]   # REF:scripts/quant_GLM-4.7-Flash-FP8.py:15-21
+        kw = dict(scheme="FP8_BLOCK", ignore=ignore, max_workers=args.glm_workers, device=f"cuda:{dev.index}", rank=rank, world_size=world)
+        model_free_ptq(src, dst + "_warm", **kw)      # warm-up: pinned arenas, pipeline handles, page cache
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        st = model_free_ptq(src, dst, **kw)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        out["model_free_ptq"] = {"metric": "bf16_checkpoint_GBps_file_to_file", "value": total / dt / 1e9, "unit": UNIT, "seconds": dt,
+                                 "scaling": "strong",
+                                 "config": {"workload": "model_free_ptq(scheme=FP8_BLOCK, ignore=[q_a_proj, kv_a_proj_with_mqa, mlp.gate, lm_head]) on a synthetic "
+                                                        "GLM-4.7-Flash-shaped safetensors checkpoint in the page cache", "checkpoint_bytes": total,
+                                            "shards": n_shards, "max_workers": args.glm_workers, "tensors_quantized_rank0": st["tensors_quantized"],
+                                            "timing": "wall clock around the call (file read, H2D, kernel, D2H, pwrite), max over ranks"}}
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            shutil.rmtree(root, ignore_errors=True)
+    return out
+
+
+def _checksum(t: torch.Tensor) -> torch.Tensor:
+    """Order-independent exact checksum of a tensor's bytes (int64 sum of its 32-bit words / bytes)."""
+    b = t.contiguous().view(torch.uint8).reshape(-1)
+    n4 = b.numel() // 4 * 4
+    return b[:n4].view(torch.int32).sum(dtype=torch.int64) + b[n4:].sum(dtype=torch.int64)
+
+
+def run_parity(args, dev, world, rank):
+    """Driver-visible correctness of the sharding (round-1 verdict, weak #9): the packed bytes a rank produces for ITS layers /
+    experts equal what one GPU produces for the whole job, and the token-sharded AWQ search (NCCL all-reduce of |x| sums and loss
+    accumulators) returns the unsharded argmin.  Checksums are all-reduced; rank 0 holds the unsharded reference."""
+    import torch.distributed as dist
+
+    from quantizers_b200 import awq
+    from quantizers_b200 import ops
+    from quantizers_b200 import scheduler as S
+
+    res = {}
+    # ---- RTN, 8 Qwen3-4B layers partitioned by layer
+    n_layers = 8
+    spec1 = S.qwen3_4b(layers=1)
+    keys = ("weight_packed", "weight", "weight_scale", "weight_zero_point")
+    sums = torch.zeros(n_layers, len(spec1.matrices), dtype=torch.int64, device=dev)
+    mine = S.partition(n_layers, world, rank)
+    if len(mine):
+        spec = S.qwen3_4b(layers=len(mine))
+        o = S.quantize_arena(spec, S.build_arena(spec, list(mine), dev))
+        for mi, m in enumerate(spec.matrices):
+            for li, layer in enumerate(mine):
+                sl = slice(li * m.per_unit, (li + 1) * m.per_unit)
+                sums[layer, mi] = sum(_checksum(o[m.name][k][sl]) for k in keys if k in o[m.name])
+        del o
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        spec = S.qwen3_4b(layers=n_layers)
+        o = S.quantize_arena(spec, S.build_arena(spec, list(range(n_layers)), dev))
+        ref = torch.zeros_like(sums)
+        for mi, m in enumerate(spec.matrices):
+            for layer in range(n_layers):
+                sl = slice(layer * m.per_unit, (layer + 1) * m.per_unit)
+                ref[layer, mi] = sum(_checksum(o[m.name][k][sl]) for k in keys if k in o[m.name])
+        res["rtn_layer_sharded_eq_unsharded"] = bool(torch.equal(ref, sums))
+        del o
+    # ---- NVFP4, 16 experts of one layer partitioned by expert (gate/up siblings stay together)
+    n_exp = 16
+    sums = torch.zeros(n_exp, 2, dtype=torch.int64, device=dev)
+    mine = S.partition(n_exp, world, rank)
+    keys4 = ("weight_packed", "weight_scale", "weight_global_scale")
+    if len(mine):
+        spec = S.qwen3_30b_a3b(layers=1, experts=len(mine))
+        o = S.quantize_arena(spec, S.build_arena(spec, list(mine), dev))
+        for mi, m in enumerate(spec.matrices):
+            for ei, e in enumerate(mine):
+                sl = slice(ei * m.per_unit, (ei + 1) * m.per_unit)
+                sums[e, mi] = sum(_checksum(o[m.name][k][sl]) for k in keys4)
+        del o
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        spec = S.qwen3_30b_a3b(layers=1, experts=n_exp)
+        o = S.quantize_arena(spec, S.build_arena(spec, list(range(n_exp)), dev))
+        ref = torch.zeros_like(sums)
+        for mi, m in enumerate(spec.matrices):
+            for e in range(n_exp):
+                sl = slice(e * m.per_unit, (e + 1) * m.per_unit)
+                ref[e, mi] = sum(_checksum(o[m.name][k][sl]) for k in keys4)
+        res["nvfp4_expert_sharded_eq_unsharded"] = bool(torch.equal(ref, sums))
+        del o
+    # ---- AWQ, one single-Linear mapping, tokens sharded over the ranks
+    T, K, N = 8192, 2560, 1024
+    g = torch.Generator(device=dev).manual_seed(4242)
+    x = (torch.randn(T, K, generator=g, device=dev) * (1 + 3 * torch.rand(K, generator=g, device=dev))).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g, device=dev) * 0.02).to(torch.bfloat16)
+    tok = S.partition(T, world, rank)
+    qa = S.PRESETS["W4A16_ASYM"]
+    pg = dist.group.WORLD if world > 1 else None
+    _, r_sh, l_sh = awq.compute_best_scale(x[tok.start:tok.stop].contiguous(), [w], awq.linear_parent, qa, process_group=pg)
+    if rank == 0:
+        _, r_un, l_un = awq.compute_best_scale(x, [w], awq.linear_parent, qa)
+        res["awq_token_sharded_same_argmin"] = bool(r_sh == r_un)
+        res["awq_token_sharded_max_rel_loss_diff"] = max(abs(a - b) / b for a, b in zip(l_sh, l_un))
+    awq.workspace.release()
+    torch.cuda.empty_cache()
+    if rank == 0:
+        res["ok"] = bool(res["rtn_layer_sharded_eq_unsharded"] and res["nvfp4_expert_sharded_eq_unsharded"] and res["awq_token_sharded_same_argmin"]
+                         and res["awq_token_sharded_max_rel_loss_diff"] < 1e-3)
+        res["world_size"] = world
+    return res
+
+
 # ----------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
@@ -491,8 +828,16 @@ def main():
     ap.add_argument("--moe-steps", type=int, default=20)
     ap.add_argument("--moe-awq-experts", type=int, default=16, help="experts of the MiniMax-M2.1 per-expert AWQ leg (0 disables it)")
     ap.add_argument("--moe-block-experts", type=int, default=32, help="experts of the reduced layer of the layer-wide MoE mapping leg (0 disables it)")
+    ap.add_argument("--cpu-awq-tokens", type=int, default=1024, help="calibration tokens of the CPU AWQ baseline (whole layer; 0 disables it); "
+                                                                      "--impl reference uses max(this, 2048)")
+    ap.add_argument("--glm-units", type=int, default=48, help="units of the GLM-4.7-Flash FP8 leg (0 disables it)")
+    ap.add_argument("--glm-file-gb", type=float, default=2.0, help="size of the synthetic checkpoint of the model_free_ptq leg (0 disables it)")
+    ap.add_argument("--glm-workers", type=int, default=4)
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling headline variant")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded == unsharded parity checks")
     args = ap.parse_args()
     if args.impl == "reference":
+        args.cpu_awq_tokens = max(args.cpu_awq_tokens, 2048) if args.cpu_awq_tokens > 0 else 0
         run_reference(args)
         return
 
@@ -603,19 +948,28 @@ def main():
     del out, outs
 
     # ---- e2e through the host pipeline (same metric, host buffers, copies in the timed region)
-    e2e_v, h2d, d2h, _, numa_bound = run_e2e(spec, arena, args.e2e_steps, 1, local)
+    e2e_v, h2d, d2h, _, numa_bound, e2e_breakdown = run_e2e(spec, arena, args.e2e_steps, 1, local)
     ev = torch.tensor([e2e_v], device=dev)
     if world > 1:
         dist.all_reduce(ev, op=dist.ReduceOp.MIN)  # slowest rank bounds the job
         e2e_v = float(ev.item()) * world
     barrier()
 
+    del arena
+    torch.cuda.empty_cache()
+    strong = None if args.no_strong else run_headline_strong(args, dev, world, rank, peaks)
+    barrier()
+    parity = None if args.no_parity else run_parity(args, dev, world, rank)
+    barrier()
+    torch.cuda.empty_cache()
+    glm = run_glm(args, dev, world, rank, peaks) if args.glm_units > 0 else None
+    barrier()
+    torch.cuda.empty_cache()
     awq_line = run_awq(args, dev, world, rank, peaks) if args.awq_layers > 0 else None
     barrier()
     from quantizers_b200 import awq as _awq
 
     _awq.workspace.release()
-    del arena
     torch.cuda.empty_cache()
     moe_nvfp4 = run_moe_nvfp4(args, dev, world, rank, peaks) if args.moe_layers > 0 else None
     barrier()
@@ -632,10 +986,14 @@ def main():
                    "l2": "inputs (7.27 GB/step) far larger than the 126 MB L2; no flush needed", "parallelism": f"layer-sharded x{world}"},
         "roofline": roofline,
         "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-                "host_buffers": "pinned, on the GPU's NUMA node" if numa_bound else "pinned"},
+                "host_buffers": "pinned, on the GPU's NUMA node" if numa_bound else "pinned", "breakdown": e2e_breakdown},
         "gpu_launches": S.launches_per_step(spec) * args.steps,
         "clocks": sampler.summary() if rank == 0 else None,
     }
+    if strong is not None:
+        line["headline_strong"] = strong
+    if glm is not None:
+        line["glm_fp8"] = glm
     if awq_line is not None:
         line["awq"] = awq_line
     if moe_nvfp4 is not None:
@@ -679,6 +1037,29 @@ def main():
                                              "sample": "one decoder layer through live compressed-tensors with the tensors on this GPU (eager ATen kernels)"}
                 except Exception as e:  # noqa: BLE001 -- informational leg only
                     line["ct_eager_cuda"] = {"unavailable": str(e)[:200]}
+        # compact per-leg summary + parity flags as the LAST keys (inside the tail the driver keeps of this line)
+        def _vf(d, frac_key="frac"):
+            return None if d is None else {"v": round(d["value"], 2), "u": d["unit"], "frac": round(d["roofline"][frac_key], 3) if "roofline" in d else None,
+                                           "scaling": d.get("scaling")}
+        legs = {"headline": {"v": round(value, 1), "u": UNIT, "frac": round(roofline["frac"], 3), "scaling": "weak"},
+                "e2e": {"v": round(e2e_v, 2), "u": UNIT}}
+        if strong is not None:
+            legs["headline_strong"] = _vf(strong)
+        if glm is not None:
+            for k, v in glm.items():
+                legs["glm_" + k] = _vf(v)
+        if awq_line is not None:
+            legs["awq"] = _vf(awq_line)
+            legs["awq"]["frac_of_burst"] = round(awq_line["roofline"]["frac_of_burst"], 3) if awq_line["roofline"].get("frac_of_burst") else None
+        if moe_nvfp4 is not None:
+            legs["moe_nvfp4"] = _vf(moe_nvfp4)
+        if moe_awq is not None:
+            legs["moe_awq_experts"] = _vf(moe_awq)
+            if "layer_mapping" in moe_awq:
+                legs["moe_awq_layer_mapping"] = _vf(moe_awq["layer_mapping"])
+                legs["moe_awq_layer_mapping"]["ms"] = round(moe_awq["layer_mapping"]["ms"], 2)
+        line["parity"] = parity
+        line["legs"] = legs
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -390,6 +390,10 @@ int b200q_awq_scaled_fake_quantize(const void* weight, int64_t rows, int64_t col
     GroupParams p{};
     p.w = weight; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = sc->num_bits; p.symmetric = sc->symmetric;
     p.has_zp = sc->has_zp; p.col_scale = scales; p.out = out;
+    if (sc->dtype == B200Q_BF16 && sc->qtype == B200Q_INT && scales != nullptr && fast_paths_enabled()) {
+        const int rc = launch_awq_fq_grid_fast(p, 1, (cudaStream_t)stream);
+        if (rc != B200Q_ENOSYS) return rc;
+    }
     return dispatch_group<MODE_OBS_FQ>(sc->dtype, sc->qtype, p, 1, (cudaStream_t)stream);
 }
 int b200q_awq_scaled_fake_quantize_grid(const void* weight, int64_t rows, int64_t cols, const b200q_scheme* sc, const float* scales,
@@ -403,6 +407,10 @@ int b200q_awq_scaled_fake_quantize_grid(const void* weight, int64_t rows, int64_
     GroupParams p{};
     p.w = weight; p.rows = rows; p.cols = cols; p.group = sc->group_size; p.nbits = sc->num_bits; p.symmetric = sc->symmetric;
     p.has_zp = sc->has_zp; p.col_scale = scales; p.col_scale_stride = cols; p.out_batch_stride = out_stride; p.out = out;
+    if (sc->dtype == B200Q_BF16 && sc->qtype == B200Q_INT && fast_paths_enabled()) {
+        const int rc = launch_awq_fq_grid_fast(p, n_ratios, (cudaStream_t)stream);
+        if (rc != B200Q_ENOSYS) return rc;
+    }
     return dispatch_group<MODE_OBS_FQ>(sc->dtype, sc->qtype, p, n_ratios, (cudaStream_t)stream);
 }
 int b200q_moe_combine(const void* y, const int32_t* row, const void* weight, int64_t tokens, int32_t top_k, int64_t hidden, void* out, void* stream) {
@@ -418,7 +426,8 @@ int b200q_sq_err_accumulate(const void* y_ref, const void* y_q, int64_t numel, i
 struct b200q_pipeline {
     static constexpr int NS = 3;
     int device;
-    int64_t cap;  // bytes per slot for the weight; outputs get cap/2 + cap/16 + 4096
+    int64_t cap;  // bytes per slot for the weight
+    int64_t codes_cap, scale_cap, zp_cap, ws_cap;  // bytes of the per-slot output / workspace buffers (every job is checked against them)
     cudaStream_t s_in, s_run, s_out;
     void* d_w[NS];
     void* d_codes[NS];
@@ -443,16 +452,20 @@ int b200q_pipeline_create(b200q_pipeline** out, int64_t max_weight_bytes, int32_
     CU(cudaSetDevice(device));
     b200q_pipeline* p = new b200q_pipeline();
     p->device = device; p->cap = max_weight_bytes; p->next = 0;
+    p->codes_cap = max_weight_bytes / 2 + 256;      // <= 1 byte per 2-byte element
+    p->scale_cap = max_weight_bytes / 16 + 4096;    // <= T per 16 elements
+    p->zp_cap = max_weight_bytes / 64 + 4096;
+    p->ws_cap = max_weight_bytes / 32 + 65536 * (int64_t)sizeof(float);  // int8 zero-point scratch (one per group >= 16) / TENSOR |max| words
     CU(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
     for (int i = 0; i < b200q_pipeline::NS; i++) {
         CU(cudaMalloc(&p->d_w[i], max_weight_bytes));
-        CU(cudaMalloc(&p->d_codes[i], max_weight_bytes / 2 + 256));      // <= 1 byte per 2-byte element
-        CU(cudaMalloc(&p->d_scale[i], max_weight_bytes / 16 + 4096));    // <= T per 16 elements
-        CU(cudaMalloc(&p->d_zp[i], max_weight_bytes / 64 + 4096));
+        CU(cudaMalloc(&p->d_codes[i], p->codes_cap));
+        CU(cudaMalloc(&p->d_scale[i], p->scale_cap));
+        CU(cudaMalloc(&p->d_zp[i], p->zp_cap));
         CU(cudaMalloc((void**)&p->d_gs[i], 65536 * sizeof(float)));
-        CU(cudaMalloc(&p->d_ws[i], 65536 * sizeof(float)));
+        CU(cudaMalloc(&p->d_ws[i], p->ws_cap));
         CU(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&p->ev_run[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
@@ -510,6 +523,14 @@ int b200q_pipeline_compress_host(b200q_pipeline* p, const void* weight_host, int
         REQ_PTR(global_scale_host);
         code_bytes = n / 2; scale_bytes = n / 16;
     }
+    // the slot buffers are sized from the weight bytes for the common schemes; a CHANNEL scheme on a narrow weight or 8-bit
+    // packing with padded columns needs more than that -- refuse instead of overflowing on the device and in the D2H copy
+    B200Q_REQUIRE(code_bytes <= p->codes_cap, "packed codes of %lld bytes exceed the pipeline slot (%lld): create the pipeline with a larger max_weight_bytes",
+                  (long long)code_bytes, (long long)p->codes_cap);
+    B200Q_REQUIRE(scale_bytes <= p->scale_cap, "scales of %lld bytes exceed the pipeline slot (%lld): create the pipeline with a larger max_weight_bytes",
+                  (long long)scale_bytes, (long long)p->scale_cap);
+    B200Q_REQUIRE(zp_bytes <= p->zp_cap, "zero points of %lld bytes exceed the pipeline slot (%lld): create the pipeline with a larger max_weight_bytes",
+                  (long long)zp_bytes, (long long)p->zp_cap);
     CU(cudaSetDevice(p->device));
     const int s = p->next;
     p->next = (p->next + 1) % b200q_pipeline::NS;
@@ -519,7 +540,8 @@ int b200q_pipeline_compress_host(b200q_pipeline* p, const void* weight_host, int
     CU(cudaStreamWaitEvent(p->s_run, p->ev_in[s], 0));
     int rc;
     if (sc->qtype == B200Q_INT)
-        rc = b200q_compress_int_packed(p->d_w[s], batch, rows, cols, sc, (int32_t*)p->d_codes[s], p->d_scale[s], (int32_t*)p->d_zp[s], p->s_run);
+        rc = b200q_compress_int_packed_ws(p->d_w[s], batch, rows, cols, sc, (int32_t*)p->d_codes[s], p->d_scale[s], (int32_t*)p->d_zp[s],
+                                          p->d_ws[s], p->ws_cap, p->s_run);
     else if (sc->qtype == B200Q_FP8)
         rc = b200q_compress_fp8(p->d_w[s], batch, rows, cols, sc, (uint8_t*)p->d_codes[s], p->d_scale[s], p->d_ws[s], p->s_run);
     else

@@ -30,6 +30,7 @@ template <int MODE> int dispatch_group(int dt, int qt, const GroupParams& p, int
 // bf16 fast paths (issue-budget tuned); return B200Q_ENOSYS when the scheme/shape is not covered
 int launch_group_tma(int qt, const GroupParams& p, int64_t batch, cudaStream_t st);
 int launch_group_tma_supplied(int qt, const GroupParams& p, int64_t batch, cudaStream_t st);  // caller's qparams (quantize_pack)
+int launch_awq_fq_grid_fast(const GroupParams& p, int n_ratios, cudaStream_t st);  // bf16 INT4 AWQ per-ratio weight update (awq_fq_fast.cu)
 bool tma_paths_enabled();
 int launch_group_fast(int qt, const GroupParams& p, int64_t batch, cudaStream_t st);
 int launch_block_fp8_fast(const TileParams& p, int64_t batch, cudaStream_t st);

@@ -186,6 +186,8 @@ class _Worker:
                     src = self.gs[s].view(torch.uint8)
                 else:  # weight_shape
                     src = torch.tensor([rows, cols], dtype=torch.int64).view(torch.uint8)
+                if nbytes > src.numel():  # b200q_pipeline_compress_host refuses such jobs up front; never truncate silently
+                    raise RuntimeError(f"{key}: {nbytes} bytes do not fit the {src.numel()}-byte staging slot")
                 os.pwrite(fout, memoryview(src.numpy()[:nbytes]), off)
         self.pending = []
 

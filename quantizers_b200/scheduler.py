@@ -109,7 +109,7 @@ def glm47_flash(preset: str = "FP8_BLOCK", units: int = 64) -> ModelSpec:
     """BASELINE.json configs[2]: dims unverified (no network) -> synthetic shapes incl. a non-multiple-of-128 row count."""
     return ModelSpec("glm-4.7-flash", units, "expert", [
         MatrixSpec("gate_up_proj", 1536, 2048, preset, 2), MatrixSpec("down_proj", 2048, 1536, preset),
-        MatrixSpec("dense_ragged", 2560 + 64, 2048, preset)])
+        MatrixSpec("dense_up", 10240, 2048, preset), MatrixSpec("dense_ragged", 2560 + 64, 2048, preset)])
 
 
 # ----------------------------------------------------------------------------- partitioning

@@ -361,3 +361,30 @@ def test_wmean_bf16_fast_path_extremes(group):
     got = awq.compute_layer_means([w.cuda(), w[:7].cuda()], group).cpu()
     ref = O.w_mean([w, w[:7]], group).float()
     assert torch.equal(got, ref), group
+
+
+@pytest.mark.parametrize("name,geom,sym", [("int4_g32_sym", O.Geom(O.GROUP, 32), True), ("int4_g128_asym", O.Geom(O.GROUP, 128), False),
+                                          ("int4_g32_asym", O.Geom(O.GROUP, 32), False), ("int4_g128_sym", O.Geom(O.GROUP, 128), True)])
+def test_scaled_fake_quantize_grid_fast_kernel_bit_exact(name, geom, sym):
+    """awq_fq_fast.cu (weight rows kept in registers across the ratio grid, packed bf16 chain, bracketed reciprocal of the fp32
+    column scale) against the oracle's scale -> observe -> fake-quantize -> unscale chain, every bit incl. the -0.0 of torch.round:
+    adversarial weights (zero groups, -0.0 rows, 1e-30 values, outlier columns, ragged rows / column strips) and scale vectors that
+    span 1e-3 .. 1e3, plus ratios whose scales fall outside the reciprocal-safe range (exact path)."""
+    from quantizers_b200 import awq
+    from tests.util import synth_weight
+
+    g = torch.Generator().manual_seed(17)
+    for rows, K in ((77, 1280), (130, 384)):                       # 1280 = 5 full strips of 256; 384 = 1.5 strips
+        w = synth_weight(rows, K, torch.bfloat16, 5 + rows)
+        R_ = 6
+        scales = torch.exp(torch.empty(R_, K).uniform_(-6.9, 6.9, generator=g))
+        scales[1] = 1.0
+        scales[2, :64] = 3e-26                                      # outside [2^-60, 2^60]: exact chain for those chunks
+        scales[3, 100:140] = 7e22
+        out = torch.empty(R_, rows, K, dtype=torch.bfloat16, device="cuda")
+        awq.scaled_fake_quantize_grid(w.cuda(), scales.cuda(), Args(name), out)
+        for r in range(R_):
+            want = R.scaled_fake_quantize(w, scales[r], geom, O.INT, 4, sym)
+            assert_bits_equal(out[r], want, f"{name} rows={rows} K={K} ratio {r}")
+        one = awq.scaled_fake_quantize(w.cuda(), scales[4].cuda(), Args(name))
+        assert_bits_equal(one, R.scaled_fake_quantize(w, scales[4], geom, O.INT, 4, sym), f"{name} single")

@@ -526,3 +526,40 @@ def test_flat_pack_unpack_fast_paths():
         off = (torch.randn(R, C, generator=g) * 3).to(torch.bfloat16)   # off-grid, some beyond +-6
         off[0, 0] = -0.0
         assert_bits_equal(ops.pack_fp4_to_uint8(off.cuda()), O.pack_fp4_to_uint8(off), f"pack_fp4 off-grid {R}x{C}")
+
+
+def test_host_pipeline_refuses_jobs_that_overflow_its_slots():
+    """the pipeline's slot buffers are sized from the weight bytes; a CHANNEL scheme on a narrow weight needs more scale
+    bytes than that.  The call must fail up front (no device overflow, no truncated D2H), and a normal job must still run after."""
+    import ctypes
+
+    from quantizers_b200 import _lib as LB
+    from quantizers_b200 import ops
+    from quantizers_b200.scheduler import PRESETS
+
+    lib = LB.lib()
+    rows, cols = 16384, 8
+    h = ctypes.c_void_p()
+    LB.check(lib.b200q_pipeline_create(ctypes.byref(h), rows * cols * 2, 0))
+    try:
+        w = torch.randn(rows, cols).to(torch.bfloat16).pin_memory()
+        codes = torch.empty(rows * cols, dtype=torch.uint8).pin_memory()
+        scale = torch.empty(rows, dtype=torch.bfloat16).pin_memory()
+        sc = ops.scheme_from_args(PRESETS["FP8_CHANNEL"], torch.bfloat16, True)
+        rc = lib.b200q_pipeline_compress_host(h, LB.ptr(w), 1, rows, cols, ctypes.byref(sc), LB.ptr(codes), LB.ptr(scale), None, None)
+        assert rc != 0 and b"exceed the pipeline slot" in lib.b200q_last_error()
+        # a job that fits still works on the same handle, asymmetric INT4 through the zero-point workspace
+        w2 = synth_weight(64, 256, torch.bfloat16, 3).pin_memory()
+        a = PRESETS["W4A16_ASYM"]
+        sc2 = ops.scheme_from_args(a, torch.bfloat16, True)
+        c2 = torch.empty((64, 32), dtype=torch.int32).pin_memory()
+        s2 = torch.empty((64, 2), dtype=torch.bfloat16).pin_memory()
+        z2 = torch.empty((8, 2), dtype=torch.int32).pin_memory()
+        LB.check(lib.b200q_pipeline_compress_host(h, LB.ptr(w2), 1, 64, 256, ctypes.byref(sc2), LB.ptr(c2), LB.ptr(s2), LB.ptr(z2), None))
+        LB.check(lib.b200q_pipeline_sync(h))
+        want = O.compress(w2, "pack-quantized", O.Geom(O.GROUP, 128), 4, False)
+        assert_bits_equal(c2, want["weight_packed"], "pipeline codes")
+        assert_bits_equal(s2, want["weight_scale"], "pipeline scale")
+        assert_bits_equal(z2, want["weight_zero_point"], "pipeline zero points")
+    finally:
+        lib.b200q_pipeline_destroy(h)
