@@ -99,9 +99,10 @@ int b200q_compress_nvfp4(const void* weight, int64_t batch, int64_t rows, int64_
 /* Same with the global scale always computed here and shared by `fuse_span` consecutive matrices of the batch
  * (LLMC update_fused_layer_weight_global_scales: gate_proj / up_proj of one expert stacked next to each other get
  * min(gs_gate, gs_up)); global_scale fp32 [batch] is an OUTPUT.  workspace: device scratch (4-byte aligned) of
- * b200q_compress_nvfp4_workspace(...) bytes: with it (bf16) the |max| reduction and the compression are ONE persistent launch
- * and each weight is read from HBM once (the second pass is served by the L2); with >= 8 * batch / fuse_span bytes a one-CTA-
- * per-item variant of the same idea runs; without it the two-launch path runs. */
+ * b200q_compress_nvfp4_workspace(...) bytes: with it (bf16) the |max| reduction and the compression are ONE launch and each weight
+ * is read from HBM once (the second pass is served by the L2); without a workspace the two-launch path runs.  Identical bits.
+ * (B200Q_FP4_LOC=1, experiment: the |max| pass also leaves every group's T(|max| / 6) in a 2-byte-per-group tail of the workspace
+ * for the compress pass -- measured slower, see DESIGN.md.) */
 int64_t b200q_compress_nvfp4_workspace(int64_t batch, int64_t rows, int64_t cols, int32_t fuse_span);
 int b200q_compress_nvfp4_fused(const void* weight, int64_t batch, int64_t rows, int64_t cols, int32_t dtype, int32_t fuse_span,
                                float* global_scale, uint8_t* packed, uint8_t* scale_e4m3, void* workspace, int64_t workspace_bytes,

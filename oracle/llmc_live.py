@@ -166,9 +166,11 @@ def mlp_parent(down: torch.Tensor):
 
 
 def attention_parent(o_proj: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, q_norm: torch.Tensor, k_norm: torch.Tensor,
-                     rope_theta: float = 1e6, eps: float = 1e-6):
-    """transformers ``Qwen3Attention.forward`` on one calibration sample ``x [S, K]`` (batch 1, causal, positions 0..S-1), eager
-    attention (explicit softmax in fp32, probabilities cast to the activation dtype before P @ V -- ``eager_attention_forward``)."""
+                     rope_theta: float = 1e6, eps: float = 1e-6, attn_implementation: str = "sdpa"):
+    """transformers ``Qwen3Attention.forward`` on one calibration sample ``x [S, K]`` (batch 1, causal, positions 0..S-1).
+    ``attn_implementation``: "sdpa" = transformers' default (``sdpa_attention_forward`` -> ``F.scaled_dot_product_attention`` with
+    ``is_causal``), what ``AutoModelForCausalLM.from_pretrained`` in REF:scripts/do_oneshot.py:82-96 gives; "eager" =
+    ``eager_attention_forward`` (explicit fp32 softmax, probabilities cast to the activation dtype before P @ V)."""
     dev = o_proj.device
 
     def rms(x, w):
@@ -194,7 +196,10 @@ def attention_parent(o_proj: torch.Tensor, n_heads: int, n_kv: int, head_dim: in
 
         q, k = rot(q), rot(k)
         rep = n_heads // n_kv
-        k, v = k.repeat_interleave(rep, dim=0), v.repeat_interleave(rep, dim=0)
+        k, v = k.repeat_interleave(rep, dim=0), v.repeat_interleave(rep, dim=0)          # repeat_kv
+        if attn_implementation == "sdpa":
+            o = F.scaled_dot_product_attention(q[None], k[None], v[None], is_causal=True)[0]
+            return F.linear(o.transpose(0, 1).reshape(S, n_heads * head_dim), o_proj)
         att = torch.matmul(q, k.transpose(-1, -2)) * (head_dim ** -0.5)
         att = att + torch.full((S, S), float("-inf"), device=dev, dtype=att.dtype).triu(1)
         p = torch.softmax(att, dim=-1, dtype=torch.float32).to(x.dtype)

@@ -154,7 +154,16 @@ static int compress_nvfp4_impl(const void* weight, int64_t batch, int64_t rows, 
             const char* v = getenv("B200Q_FP4_PERSISTENT");
             if (v && v[0] == '1' && workspace_bytes >= nvfp4_resident_workspace(batch, rows, cols))
                 rc = launch_nvfp4_resident(p, batch, fuse_span, global_scale, (uint32_t*)workspace, st);
-            if (rc == B200Q_ENOSYS) rc = launch_nvfp4_fused(p, batch, fuse_span, global_scale, (uint32_t*)workspace, st);
+            if (rc == B200Q_ENOSYS) {
+                // workspace layout: [8 bytes per span: sync words][pad to 256][2 bytes per group: T(|max| / 6) scratch, optional]
+                const int64_t sync_bytes = (8 * (batch / fuse_span) + 255) / 256 * 256;
+                const int64_t loc_bytes = 2 * batch * rows * (cols / 16);
+                // measured (bench moe_nvfp4, 9.66 GB of experts): 2 905 GB/s WITH the scratch vs 3 044 without -- the extra stores keep the
+                // |max| CTAs resident longer than the ALU work they save in the compress pass; opt-in only (B200Q_FP4_LOC=1)
+                static const bool use_loc = getenv("B200Q_FP4_LOC") != nullptr;
+                uint16_t* loc = use_loc && workspace_bytes >= sync_bytes + loc_bytes ? (uint16_t*)((char*)workspace + sync_bytes) : nullptr;
+                rc = launch_nvfp4_fused(p, batch, fuse_span, global_scale, (uint32_t*)workspace, st, loc);
+            }
         }
         if (rc != B200Q_ENOSYS) return rc;
         // generic: min/max state staged in the first 8*batch bytes of the (not yet written) scale output buffer
@@ -189,7 +198,9 @@ int b200q_compress_nvfp4_fused(const void* weight, int64_t batch, int64_t rows, 
 
 int64_t b200q_compress_nvfp4_workspace(int64_t batch, int64_t rows, int64_t cols, int32_t fuse_span) {
     const int64_t spans = fuse_span > 0 ? (batch + fuse_span - 1) / fuse_span : batch;
-    const int64_t a = 8 * spans, b = nvfp4_resident_workspace(batch, rows, cols);
+    // sync words (padded) + the per-group T(|max| / 6) scratch of the fused kernel; the persistent variant needs its own sync words
+    static const bool use_loc = getenv("B200Q_FP4_LOC") != nullptr;
+    const int64_t a = (8 * spans + 255) / 256 * 256 + (use_loc ? 2 * batch * rows * (cols / 16) : 0), b = nvfp4_resident_workspace(batch, rows, cols);
     return a > b ? a : b;
 }
 

@@ -24,6 +24,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+// non-blocking poll (mbarrier.test_wait): the try_wait form may park the warp for a hardware-chosen interval; a warp that arrives
+// BEFORE its tile pays that wake-up latency on every tile (A/B: B200Q_TMA_VAR=6)
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SPIN_%=:\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SDONE_%=;\n"
+        "bra SPIN_%=;\n"
+        "SDONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");

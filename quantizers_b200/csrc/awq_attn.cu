@@ -82,6 +82,75 @@ __global__ void __launch_bounds__(256) qk_norm_rope_v1_kernel(uint16_t* __restri
     }
 }
 
+// v2 (default, round 2): D / 16 lanes per (token, head) vector.  A lane owns elements [8l, 8l + 8) AND [D/2 + 8l, D/2 + 8l + 8) -- two 16-byte
+// loads, still 128 contiguous bytes per half across the lanes -- so rotate_half's partner (i +- D/2) is in the SAME thread: no
+// shuffles for the rotation, log2(D / 16) for mean(x^2).  The bf16 chain runs packed: vn = cvt.rn.bf16x2(x * r), y = w * vn,
+// y * cos, rot * sin (HMUL2: the exact product rounded once, what the eager bf16 multiply gives), their sum one HADD2.
+// ~6 issued instructions per element instead of ~30 (v1: 4 elements per lane, 9 shuffles per 4 elements, scalar chain).
+__device__ __forceinline__ uint32_t rope_hmul2(uint32_t a, uint32_t b) { uint32_t r; asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t rope_hadd2(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t rope_cvt2(float hi, float lo) { uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
+
+template <int D>
+__global__ void __launch_bounds__(256) qk_norm_rope_v2_kernel(uint16_t* __restrict__ qkv, int64_t tokens, int n_heads, int n_kv, int seq_len,
+                                                           const uint16_t* __restrict__ qw, const uint16_t* __restrict__ kw,
+                                                           const uint16_t* __restrict__ cosb, const uint16_t* __restrict__ sinb, float eps) {
+    constexpr int LPV = D / 16;        // lanes per vector: 8 (d = 128) or 4 (d = 64)
+    constexpr int VPW = 32 / LPV;      // vectors per warp
+    const int lane = threadIdx.x & 31, sub = lane % LPV, vslot = lane / LPV;
+    const int hq = n_heads + n_kv;
+    const int64_t n_vec = tokens * (int64_t)hq;
+    const int64_t row_elems = (int64_t)(n_heads + 2 * n_kv) * D;
+    // norm weights of this lane's 16 elements, q and k (loaded once)
+    const uint4 wq0 = *reinterpret_cast<const uint4*>(qw + sub * 8), wq1 = *reinterpret_cast<const uint4*>(qw + D / 2 + sub * 8);
+    const uint4 wk0 = *reinterpret_cast<const uint4*>(kw + sub * 8), wk1 = *reinterpret_cast<const uint4*>(kw + D / 2 + sub * 8);
+    const int64_t wstride = (int64_t)gridDim.x * 8 * VPW;
+    for (int64_t vbase = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * VPW; vbase < n_vec; vbase += wstride) {   // warp-uniform
+        const int64_t vec = vbase + vslot;
+        const bool ok = vec < n_vec;
+        const int64_t vv = ok ? vec : n_vec - 1;   // idle sub-warps recompute the last vector and store nothing (shuffles stay full-warp)
+        const int64_t t = vv / hq;
+        const int h = (int)(vv - t * hq);
+        const bool isq = h < n_heads;
+        uint16_t* p = qkv + t * row_elems + (int64_t)h * D + sub * 8;
+        const int64_t pos = (t % seq_len) * D + sub * 8;
+        const uint4 a0 = *reinterpret_cast<const uint4*>(p), a1 = *reinterpret_cast<const uint4*>(p + D / 2);
+        const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(cosb + pos)), c1 = __ldg(reinterpret_cast<const uint4*>(cosb + pos + D / 2));
+        const uint4 s0 = __ldg(reinterpret_cast<const uint4*>(sinb + pos)), s1 = __ldg(reinterpret_cast<const uint4*>(sinb + pos + D / 2));
+        const uint32_t x[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const uint4 w0 = isq ? wq0 : wk0, w1 = isq ? wq1 : wk1;
+        const uint32_t nw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        float xl[8], xh[8], ss0 = 0.0f, ss1 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            xl[i] = __uint_as_float(x[i] << 16);
+            xh[i] = __uint_as_float(x[i] & 0xffff0000u);
+            ss0 = __fadd_rn(ss0, __fmul_rn(xl[i], xl[i]));
+            ss1 = __fadd_rn(ss1, __fmul_rn(xh[i], xh[i]));
+        }
+        float ss = __fadd_rn(ss0, ss1);
+#pragma unroll
+        for (int o = 1; o < LPV; o <<= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
+        const float r = rsqrtf(__fadd_rn(__fdiv_rn(ss, (float)D), eps));
+        uint32_t y[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) y[i] = rope_hmul2(nw[i], rope_cvt2(__fmul_rn(xh[i], r), __fmul_rn(xl[i], r)));   // w * T(x * r)
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            // first half: y * cos + (-y[i + D/2]) * sin ; second half: y * cos + y[i - D/2] * sin
+            o[i] = rope_hadd2(rope_hmul2(y[i], cw[i]), rope_hmul2(y[i + 4] ^ 0x80008000u, sw[i]));
+            o[i + 4] = rope_hadd2(rope_hmul2(y[i + 4], cw[i + 4]), rope_hmul2(y[i], sw[i + 4]));
+        }
+        if (ok) {
+            *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(p + D / 2) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+    }
+}
+
 // Experiment (B200Q_ROPE_BATCH=4): U (token, head) vectors per warp per step, the loads of all U vectors (row, cos, sin) issued before the
 // first shuffle; the arithmetic per vector is unchanged.  Measured SLOWER than the one-vector schedule (365 vs 323 us): not latency-bound.
 template <int EPL, int U>  // EPL: elements per lane: 2 (d = 64) or 4 (d = 128)
@@ -174,6 +243,21 @@ extern "C" int b200q_qk_norm_rope(void* qkv, int64_t tokens, int32_t n_heads, in
     if (tokens == 0) return B200Q_OK;
     const int64_t n_vec = tokens * (int64_t)(n_heads + n_kv);
     cudaStream_t st = (cudaStream_t)stream;
+    // default: v2 (sub-warp per vector, packed bf16 chain); B200Q_ROPE_V1=1 / B200Q_ROPE_BATCH=4 select the round-1 kernels (same
+    // rounding chain; the mean(x^2) summation order differs, as it does from the eager reference)
+    static const bool v1 = getenv("B200Q_ROPE_V1") != nullptr || getenv("B200Q_ROPE_BATCH") != nullptr;
+    if (!v1 && (((uintptr_t)qkv | (uintptr_t)q_norm_weight | (uintptr_t)k_norm_weight | (uintptr_t)cos | (uintptr_t)sin) & 15) == 0) {
+        const int vpw = head_dim == 128 ? 4 : 8;
+        const int grid = (int)min((n_vec + 8 * vpw - 1) / (8 * vpw), (int64_t)kNumSMs * 8);
+        if (head_dim == 128)
+            qk_norm_rope_v2_kernel<128><<<grid, 256, 0, st>>>((uint16_t*)qkv, tokens, n_heads, n_kv, seq_len, (const uint16_t*)q_norm_weight,
+                                                              (const uint16_t*)k_norm_weight, (const uint16_t*)cos, (const uint16_t*)sin, eps);
+        else
+            qk_norm_rope_v2_kernel<64><<<grid, 256, 0, st>>>((uint16_t*)qkv, tokens, n_heads, n_kv, seq_len, (const uint16_t*)q_norm_weight,
+                                                             (const uint16_t*)k_norm_weight, (const uint16_t*)cos, (const uint16_t*)sin, eps);
+        B200Q_CHECK_LAUNCH();
+        return B200Q_OK;
+    }
     // B200Q_ROPE_BATCH=4 selects the four-vectors-per-step schedule (A/B switch; its grid is one wave of the kernel's residency)
     // measured (T = 32 768, 32 + 8 heads of 128): one vector per step 323 us, four per step 365 us -- the kernel is bound by its ~30
     // instructions per element (0.3 of the HBM roofline either way), not by load latency, and 73 registers leave 3 CTAs per SM

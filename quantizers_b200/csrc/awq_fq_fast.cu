@@ -50,7 +50,7 @@ __device__ __noinline__ uint4 exact_chunk(const uint4 raw, const float* __restri
             const float x = __uint_as_float(e ? (w[k] & 0xffff0000u) : (w[k] << 16));
             const float c = cs ? cs[2 * k + e] : 1.0f;
             const float xs = round_to<DT_BF16>(fmul(x, c));
-            const float fq = fq_int<DT_BF16>(xs, s, z, !SYM, -8.0f, 7.0f);
+            const float fq = fq_int<DT_BF16>(xs, s, z, true, -8.0f, 7.0f);   // zero point always added (0 when symmetric)
             y[e] = round_to<DT_BF16>(fdiv(fq, c));
         }
         o[k] = cvt_bf16x2(y[1], y[0]);
@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(256) awq_fq_grid_kernel(const AwqFqParams p) {
                 float lo, hi;
                 unpack2(mul2(bf16x2_to_f32x2_fma(xs[k]), r2), lo, hi);
                 uint32_t v = cvt_bf16x2(hi, lo);                              // T(x / s)
-                if (!SYM) v = hadd2(v, z2);                                   // T(+ zp)
+                v = hadd2(v, z2);                                             // T(+ zp): symmetric modules carry a zero zero-point too
+                                                                              // (CT initialize_qparams force_zero_point), so -0.0 -> +0.0
                 uint32_t m = hadd2(v, k200);                                  // 200 + RNE(v): ulp 1 in [128, 256)
                 m = hmin2(hmax2(m, k192), k207);                              // clamp to [-8, 7]
                 const uint32_t t = hadd2(m, nb2) & ~gmask;                    // (q - z), sign cleared when it is restored below

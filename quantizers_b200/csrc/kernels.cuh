@@ -36,7 +36,8 @@ int launch_group_fast(int qt, const GroupParams& p, int64_t batch, cudaStream_t 
 int launch_block_fp8_fast(const TileParams& p, int64_t batch, cudaStream_t st);
 int launch_nvfp4_fast(const GroupParams& p, int64_t batch, cudaStream_t st);
 int launch_nvfp4_supplied(const GroupParams& p, int64_t batch, cudaStream_t st, int op = 0);  // caller's bf16 group scales + global scale; op 0 pack, 1 quantize (values), 2 fake_quantize
-int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_out, uint32_t* sync, cudaStream_t st);
+int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_out, uint32_t* sync, cudaStream_t st,
+                       uint16_t* loc_scratch = nullptr);  // loc_scratch: optional bf16 [batch * rows * cols / 16]
 int64_t nvfp4_resident_workspace(int64_t batch, int64_t rows, int64_t cols);  // bytes of sync words the persistent kernel needs
 int launch_nvfp4_resident(const GroupParams& p, int64_t batch, int span, float* gs_out, uint32_t* sync, cudaStream_t st);
 bool fast_paths_enabled();

@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(256) group_kernel(const GroupParams p) {
 
     const float lo = (QT == QT_INT) ? -(float)(1 << (p.nbits - 1)) : (QT == QT_FP8 ? -448.0f : -6.0f);
     const float hi = (QT == QT_INT) ? (float)((1 << (p.nbits - 1)) - 1) : (QT == QT_FP8 ? 448.0f : 6.0f);
-    const bool add_zp = (QT == QT_INT) ? (!p.symmetric) : (p.has_zp != 0);
+    // forward_quantize (the AWQ path, MODE_OBS_FQ) always finds a zero-point Parameter on the module -- zeros for symmetric schemes
+    // (CT initialize_qparams, force_zero_point = True) -- so `scaled += zp` runs and an exact -0.0 becomes +0.0
+    const bool add_zp = (QT == QT_INT) ? (MODE == MODE_OBS_FQ || !p.symmetric) : (p.has_zp != 0);
     float gs = 1.0f;
     if (QT == QT_FP4) gs = p.gs[p.gs_stride ? b : 0];
 

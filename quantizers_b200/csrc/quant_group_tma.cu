@@ -28,8 +28,8 @@ constexpr int kStages = 2;   // default ring depth per warp (template parameter 
 // warps per CTA (one CTA per SM): as many as shared memory allows.  ncu: with 8 KB tiles (12 warps = 3 per scheduler) neither the
 // ALU nor the FMA pipe is saturated (51 % / 31 %), issue slots are 65 % busy and the stalls are fixed-latency waits -- too few
 // warps to hide them.  4 KB tiles double the warps per SM; a group of 128 is then shared by a pair of lanes.
-template <int QT, int TILE, int STAGES = kStages> struct WarpsFor {
-    static constexpr int value = STAGES == 2 ? (TILE == 4096 ? ((QT == QT_FP8) ? 10 : 12) : ((QT == QT_FP8) ? 20 : 24))
+template <int QT, int TILE, int STAGES = kStages, int NWARPS = 0> struct WarpsFor {
+    static constexpr int value = NWARPS > 0 ? NWARPS : STAGES == 2 ? (TILE == 4096 ? ((QT == QT_FP8) ? 10 : 12) : ((QT == QT_FP8) ? 20 : 24))
                                              : (STAGES == 3 ? 8 : 6);   // 3 x 8 KB x 8 warps / 4 x 8 KB x 6 warps: deeper ring, fewer warps
 };
 
@@ -106,11 +106,12 @@ __device__ __noinline__ uint2 repair_chunk(const uint4 raw, float s, float z, bo
 // significands in tests/test_exact_reciprocal.py.  A product x * rcp(s) is within 2^-22 of the quotient, so it rounds to the same
 // bf16 as the reference's fp32 division: ONE evaluation, no bracket, no repair.  Only scales outside [2^-100, 1] (products that
 // overflow / flush) still take the IEEE chain, group-wide.  NVFP4 divides by an fp32 quotient and keeps the bracket.
-template <int QT, bool SYM, int LOG2N, bool FMA, int TILE, bool SUPPLIED = false, bool ONE = false, bool PF = true, int STAGES = kStages>
-__global__ void __launch_bounds__(WarpsFor<QT, TILE, STAGES>::value * 32, 1) group_tma_kernel(const TmaParams p) {
+template <int QT, bool SYM, int LOG2N, bool FMA, int TILE, bool SUPPLIED = false, bool ONE = false, bool PF = true, int STAGES = kStages, bool SPIN = false,
+          int NWARPS = 0>
+__global__ void __launch_bounds__(WarpsFor<QT, TILE, STAGES, NWARPS>::value * 32, 1) group_tma_kernel(const TmaParams p) {
     static_assert(!ONE || QT != QT_FP4, "NVFP4 needs the bracket");
     constexpr int kStages = STAGES;
-    constexpr int kWarps = WarpsFor<QT, TILE, STAGES>::value;
+    constexpr int kWarps = WarpsFor<QT, TILE, STAGES, NWARPS>::value;
     constexpr int kTileBytes = TILE * 2;
     constexpr int N = 1 << LOG2N;          // chunks (8 elements, 16 bytes) per group
     constexpr int G = 8 * N;               // group size
@@ -165,7 +166,8 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE, STAGES>::value * 32, 1) gro
         const uint32_t parity = (uint32_t)(it / kStages) & 1u;
         const int64_t g0 = tile * GPT;
         const int n_here = (int)min((int64_t)GPT, p.n_groups - g0);
-        mbar_wait(bar_base + 8 * stage, parity);
+        if (SPIN) mbar_wait_spin(bar_base + 8 * stage, parity);
+        else mbar_wait(bar_base + 8 * stage, parity);
         const uint32_t tin = in_base + stage * kTileBytes;
 
         // (the previous tile's bulk store must have finished READING the output staging buffer before it is overwritten: that wait
@@ -480,6 +482,28 @@ __global__ void __launch_bounds__(WarpsFor<QT, TILE, STAGES>::value * 32, 1) gro
 // consecutive bytes each.  Replaces one atomicOr per group + a memset of the packed buffer (round-1 verdict, weak #2c).
 __global__ void zp_pack_rows_kernel(const int8_t* __restrict__ zp, int64_t batch, int64_t rows, int64_t gpr, int32_t* __restrict__ out) {
     const int64_t zrows = (rows + 7) >> 3;
+    if ((gpr & 3) == 0 && (((uintptr_t)zp) & 3) == 0 && (((uintptr_t)out) & 15) == 0) {
+        // four group columns per thread: 8 aligned 4-byte loads (one per row of the octet), SWAR nibble placement, one 16-byte store
+        const int64_t q = gpr >> 2, n = batch * zrows * q;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t k4 = i % q, t = i / q, zr = t % zrows, b = t / zrows;
+            const int8_t* src = zp + (b * rows + zr * 8) * gpr + k4 * 4;
+            const int nr = (int)min((int64_t)8, rows - zr * 8);
+            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (j < nr) {
+                    const uint32_t v = ((*reinterpret_cast<const uint32_t*>(src + (int64_t)j * gpr)) + 0x08080808u) & 0x0f0f0f0fu;  // zp + 8 per byte (zp in [-8, 7])
+                    w0 |= (v & 0xffu) << (4 * j);
+                    w1 |= ((v >> 8) & 0xffu) << (4 * j);
+                    w2 |= ((v >> 16) & 0xffu) << (4 * j);
+                    w3 |= (v >> 24) << (4 * j);
+                }
+            }
+            *reinterpret_cast<uint4*>(out + (b * zrows + zr) * gpr + k4 * 4) = make_uint4(w0, w1, w2, w3);
+        }
+        return;
+    }
     const int64_t n = batch * zrows * gpr;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t k = i % gpr, t = i / gpr, zr = t % zrows, b = t / zrows;
@@ -493,24 +517,24 @@ __global__ void zp_pack_rows_kernel(const int8_t* __restrict__ zp, int64_t batch
     }
 }
 
-template <int QT, bool SYM, int LOG2N, bool FMA, int TILE, bool ONE, bool PF = true, int STAGES = kStages>
+template <int QT, bool SYM, int LOG2N, bool FMA, int TILE, bool ONE, bool PF = true, int STAGES = kStages, bool SPIN = false, int NWARPS = 0>
 int launch_tma_v(const TmaParams& p, cudaStream_t st) {
     constexpr int OUT_BYTES = (TILE / 8) * ((QT == QT_FP8) ? 8 : 4);
-    constexpr int kWarps = WarpsFor<QT, TILE, STAGES>::value;
+    constexpr int kWarps = WarpsFor<QT, TILE, STAGES, NWARPS>::value;
     const size_t smem = (size_t)kWarps * (STAGES * TILE * 2 + OUT_BYTES + 256);
     static bool configured = false;  // benign race: idempotent attribute
     if (!configured) {
-        cudaFuncSetAttribute(group_tma_kernel<QT, SYM, LOG2N, FMA, TILE, false, ONE, PF, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(group_tma_kernel<QT, SYM, LOG2N, FMA, TILE, false, ONE, PF, STAGES, SPIN, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
     constexpr int GPT = TILE / (8 << LOG2N);
     const int64_t n_tiles = (p.n_groups + GPT - 1) / GPT;
     const int64_t ctas = max((int64_t)1, min((int64_t)kNumSMs, (n_tiles + kWarps - 1) / kWarps));
-    group_tma_kernel<QT, SYM, LOG2N, FMA, TILE, false, ONE, PF, STAGES><<<(unsigned)ctas, kWarps * 32, smem, st>>>(p);
+    group_tma_kernel<QT, SYM, LOG2N, FMA, TILE, false, ONE, PF, STAGES, SPIN, NWARPS><<<(unsigned)ctas, kWarps * 32, smem, st>>>(p);
     B200Q_CHECK_LAUNCH();
     if (QT == QT_INT && !SYM && p.zp_i8 != nullptr) {
         const int64_t words = (p.n_groups / p.groups_per_mat) * ((p.rows + 7) >> 3) * p.groups_per_row;
-        const int64_t blocks = min((int64_t)kNumSMs * 8, (words + 255) / 256);
+        const int64_t blocks = min((int64_t)kNumSMs * 8, (words / ((p.groups_per_row & 3) == 0 ? 4 : 1) + 255) / 256);
         zp_pack_rows_kernel<<<(unsigned)max((int64_t)1, blocks), 256, 0, st>>>(p.zp_i8, p.n_groups / p.groups_per_mat, p.rows, p.groups_per_row,
                                                                                 p.zp_packed);
         B200Q_CHECK_LAUNCH();
@@ -541,11 +565,40 @@ int launch_tma(const TmaParams& p, cudaStream_t st) {
         case 3: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, true, 4>(p, st);
         case 4: return launch_tma_v<QT, SYM, LOG2N, true, 4096, false, true, 3>(p, st);
         case 5: return launch_tma_v<QT, SYM, LOG2N, true, 4096, false, true, 4>(p, st);
+        case 6: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, true, 2, true>(p, st);    // ONE, test_wait spin
+        case 7: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, true, 3, true>(p, st);    // ONE, 3 stages, spin
+        // fewer warps = fewer 8 KB loads in flight (ncu: ONE sits on the mbarrier 1.7 warps / issue vs 0.09 for the bracket kernel,
+        // yet gets 9 % LESS HBM bandwidth -- 28 MB of outstanding bulk loads may be past the DRAM scheduler's sweet spot)
+        case 8: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, true, 2, false, 8>(p, st);
+        case 9: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, true, 2, false, 6>(p, st);
+        case 10: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, true, 2, false, 4>(p, st);
         default: break;
         }
     }
     if constexpr (QT != QT_FP4) {
-        if (!bracket) return fma ? launch_tma_v<QT, SYM, LOG2N, true, 4096, true>(p, st) : launch_tma_v<QT, SYM, LOG2N, false, 4096, true>(p, st);
+        // Default (round 2): the single-evaluation kernel with EIGHT warps per SM.  With 12 warps x 2 stages x 8 KB the lean kernel keeps
+        // ~28 MB of bulk loads outstanding and gets 9 % LESS bandwidth than the heavier bracket kernel (ncu: 1.7 warps per issue parked
+        // on the mbarrier vs 0.09); 8 warps: 6.7-7.0 TB/s on every INT4 scheme, 6 warps: compute-bound again (scripts/ab_tma2.py,
+        // profiles/r2_int4_kernel_ab.md).  B200Q_TMA_WARPS = 7 / 9 / 10 / 12 for sweeps.
+        static const int warps = getenv("B200Q_TMA_WARPS") ? atoi(getenv("B200Q_TMA_WARPS")) : 8;
+        if (!bracket) {
+            if (fma) {
+                switch (warps) {
+                case 7: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, true, 2, false, 7>(p, st);
+                case 9: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, true, 2, false, 9>(p, st);
+                case 10: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, true, 2, false, 10>(p, st);
+                case 12: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, true, 2, false, 12>(p, st);
+                default: return launch_tma_v<QT, SYM, LOG2N, true, 4096, true, true, 2, false, 8>(p, st);
+                }
+            }
+            switch (warps) {
+            case 7: return launch_tma_v<QT, SYM, LOG2N, false, 4096, true, true, 2, false, 7>(p, st);
+            case 9: return launch_tma_v<QT, SYM, LOG2N, false, 4096, true, true, 2, false, 9>(p, st);
+            case 10: return launch_tma_v<QT, SYM, LOG2N, false, 4096, true, true, 2, false, 10>(p, st);
+            case 12: return launch_tma_v<QT, SYM, LOG2N, false, 4096, true, true, 2, false, 12>(p, st);
+            default: return launch_tma_v<QT, SYM, LOG2N, false, 4096, true, true, 2, false, 8>(p, st);
+            }
+        }
         if (tile == 2048) return launch_tma_v<QT, SYM, LOG2N, true, 2048, false>(p, st);
     }
     return fma ? launch_tma_v<QT, SYM, LOG2N, true, 4096, false>(p, st) : launch_tma_v<QT, SYM, LOG2N, false, 4096, false>(p, st);

@@ -208,16 +208,32 @@ __device__ __forceinline__ uint32_t fp4_group_absmax2(const uint4 (&r)[2]) {  //
 }
 
 // one 1024-group tile of one matrix, already in registers: scale codes + packed e2m1 out
+// `locbase` (fused kernel, round 2): the |max| pass already reduced every group; it leaves T(absmax / 6) as bf16 bits in a scratch
+// array so that the ALU-bound compress pass skips the 9 packed max ops + the bracketed /6 per group (~1 of its 3.3 ALU-pipe
+// instructions per element) and fetches 2 bytes instead.
 template <bool FMA>
 __device__ __forceinline__ void fp4_compress_regs(const uint4 (&raw)[FP4_UF][2], const Fp4Entry* table, float gs, uint8_t* sbase, uint2* obase,
-                                                  int64_t g0, int64_t groups_per_mat) {
+                                                  int64_t g0, int64_t groups_per_mat, const uint16_t* locbase = nullptr) {
+    uint32_t locbits[FP4_UF];
+    if (locbase != nullptr) {
+#pragma unroll
+        for (int u = 0; u < FP4_UF; u++) {
+            const int64_t g = g0 + u * FP4_THREADS;
+            locbits[u] = g < groups_per_mat ? (uint32_t)__ldcg(locbase + g) << 16 : 0u;   // written by another CTA of this launch: L2, not L1
+        }
+    }
 #pragma unroll
     for (int u = 0; u < FP4_UF; u++) {
         const int64_t g = g0 + u * FP4_THREADS;
         if (g >= groups_per_mat) continue;
-        uint32_t m = fp4_group_absmax2(raw[u]);
-        m = hmaxabs2(m, prmt(m, m, 0x1032));
-        const float loc = fp4_loc_scale((m << 16) & 0x7fff0000u);          // T(absmax / 6)
+        float loc;
+        if (locbase != nullptr) {
+            loc = __uint_as_float(locbits[u]);
+        } else {
+            uint32_t m = fp4_group_absmax2(raw[u]);
+            m = hmaxabs2(m, prmt(m, m, 0x1032));
+            loc = fp4_loc_scale((m << 16) & 0x7fff0000u);                  // T(absmax / 6)
+        }
         const float sf = fminf(__fmul_rn(gs, loc), 448.0f);                // gs * loc, clamp (non-negative)
         uint32_t code = cvt_e4m3x2(0.0f, sf) & 0xffu;
         const Fp4Entry e = table[code];
@@ -243,10 +259,10 @@ __device__ __forceinline__ void fp4_compress_regs(const uint4 (&raw)[FP4_UF][2],
 }
 template <bool FMA>
 __device__ __forceinline__ void fp4_compress_tile(const Fp4Entry* table, float gs, const uint4* wbase, uint8_t* sbase, uint2* obase, int64_t g0,
-                                                  int64_t groups_per_mat) {
+                                                  int64_t groups_per_mat, const uint16_t* locbase = nullptr) {
     uint4 raw[FP4_UF][2];
     fp4_load_tile(raw, wbase, g0, groups_per_mat);
-    fp4_compress_regs<FMA>(raw, table, gs, sbase, obase, g0, groups_per_mat);
+    fp4_compress_regs<FMA>(raw, table, gs, sbase, obase, g0, groups_per_mat, locbase);
 }
 
 // caller-supplied global scales (fused q/k/v siblings, decompress round trips): one pass
@@ -350,17 +366,27 @@ struct Fp4FusedParams {
     int32_t by_item;  // alternate the two passes item by item instead of span by span
     uint32_t* sync;
     float* gs_out;  // [batch]
+    uint16_t* loc;  // optional scratch, bf16 bits of T(group |max| / 6) for every group [batch * groups_per_mat] (written by the |max| pass)
 };
 
 // |max| bits of tiles [tile0, tile1) of one matrix, reduced over the CTA (valid in thread 0)
-__device__ __forceinline__ uint32_t fp4_absmax_tiles(const uint4* wbase, int tile0, int tile1, int64_t groups_per_mat, uint32_t* s_red) {
+__device__ __forceinline__ uint32_t fp4_absmax_tiles(const uint4* wbase, int tile0, int tile1, int64_t groups_per_mat, uint32_t* s_red,
+                                                     uint16_t* locbase = nullptr) {
     uint32_t mm = 0;
     const uint64_t keep = l2_policy_evict_last();  // the compress pass re-reads these lines
     for (int tile = tile0; tile < tile1; tile++) {
         uint4 raw[FP4_UF][2];
-        fp4_load_tile<true>(raw, wbase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, groups_per_mat, keep);
+        const int64_t g0 = (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x;
+        fp4_load_tile<true>(raw, wbase, g0, groups_per_mat, keep);
 #pragma unroll
-        for (int u = 0; u < FP4_UF; u++) mm = hmaxabs2(mm, fp4_group_absmax2(raw[u]));
+        for (int u = 0; u < FP4_UF; u++) {
+            uint32_t m = fp4_group_absmax2(raw[u]);
+            mm = hmaxabs2(mm, m);
+            if (locbase != nullptr && g0 + u * FP4_THREADS < groups_per_mat) {   // this pass waits on HBM: the ALU work is free here
+                m = hmaxabs2(m, prmt(m, m, 0x1032));
+                locbase[g0 + u * FP4_THREADS] = (uint16_t)(__float_as_uint(fp4_loc_scale((m << 16) & 0x7fff0000u)) >> 16);
+            }
+        }
     }
     mm = hmaxabs2(mm, prmt(mm, mm, 0x1032));
     uint32_t bits = (mm << 16) & 0x7fff0000u;                  // |max| as fp32 bits: non-negative floats order like uints
@@ -407,8 +433,9 @@ __global__ void __launch_bounds__(FP4_THREADS, 6) nvfp4_fused_kernel(const Group
     const int tile0 = item * f.nt, tile1 = min(tile0 + f.nt, f.tiles_per_mat);
     uint32_t* st = f.sync + 2 * s;
     const uint4* wbase = reinterpret_cast<const uint4*>((const char*)p.w + m * f.groups_per_mat * 32);
+    uint16_t* locbase = f.loc ? f.loc + m * f.groups_per_mat : nullptr;
     if (!is_b) {
-        const uint32_t bits = fp4_absmax_tiles(wbase, tile0, tile1, f.groups_per_mat, s_red);
+        const uint32_t bits = fp4_absmax_tiles(wbase, tile0, tile1, f.groups_per_mat, s_red, locbase);
         if (threadIdx.x == 0) {
             atomicMax(&st[0], bits);
             __threadfence();
@@ -429,7 +456,7 @@ __global__ void __launch_bounds__(FP4_THREADS, 6) nvfp4_fused_kernel(const Group
         bits = 0;
         for (int q = 0; q < f.span; q++) {
             const uint4* wq = reinterpret_cast<const uint4*>((const char*)p.w + ((int64_t)s * f.span + q) * f.groups_per_mat * 32);
-            bits = max(bits, fp4_absmax_tiles(wq, 0, f.tiles_per_mat, f.groups_per_mat, s_red));
+            bits = max(bits, fp4_absmax_tiles(wq, 0, f.tiles_per_mat, f.groups_per_mat, s_red));   // (does not touch the loc scratch)
         }
     } else {
         bits = threadIdx.x == 0 ? ld_acquire(&st[0]) : 0u;
@@ -445,9 +472,11 @@ __global__ void __launch_bounds__(FP4_THREADS, 6) nvfp4_fused_kernel(const Group
     __syncthreads();
     uint8_t* sbase = (uint8_t*)p.scale + m * f.groups_per_mat;
     uint2* obase = reinterpret_cast<uint2*>((uint8_t*)p.out + m * f.groups_per_mat * 8);
-    fp4_compress_regs<FMA>(raw, table, gs, sbase, obase, (int64_t)tile0 * FP4_TILE_GROUPS + threadIdx.x, f.groups_per_mat);
+    // the fallback reduced the span without the scratch: recompute the group statistics in that (never observed) case
+    const uint16_t* loc_in = s_need_fallback ? nullptr : locbase;
+    fp4_compress_regs<FMA>(raw, table, gs, sbase, obase, (int64_t)tile0 * FP4_TILE_GROUPS + threadIdx.x, f.groups_per_mat, loc_in);
     for (int tile = tile0 + 1; tile < tile1; tile++)
-        fp4_compress_tile<FMA>(table, gs, wbase, sbase, obase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, f.groups_per_mat);
+        fp4_compress_tile<FMA>(table, gs, wbase, sbase, obase, (int64_t)tile * FP4_TILE_GROUPS + threadIdx.x, f.groups_per_mat, loc_in);
 }
 
 
@@ -506,7 +535,7 @@ int launch_nvfp4_supplied(const GroupParams& p, int64_t batch, cudaStream_t st, 
 }
 
 // fused |max| -> global scale -> compress; `span` consecutive matrices share min(global_scale); sync: >= 8 * batch / span bytes
-int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_out, uint32_t* sync, cudaStream_t st) {
+int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_out, uint32_t* sync, cudaStream_t st, uint16_t* loc_scratch) {
     if (p.cols % 16 != 0 || (((uintptr_t)p.w) & 15) != 0 || (((uintptr_t)p.out) & 7) != 0 || batch * p.rows * p.cols == 0) return B200Q_ENOSYS;
     if (span < 1 || batch % span != 0) return B200Q_ENOSYS;
     const int64_t groups_per_mat = p.rows * (p.cols >> 4);
@@ -529,6 +558,8 @@ int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_
     f.by_item = by_item >= 0 ? by_item : (f.lookahead == 1 ? 1 : 0);
     f.sync = sync;
     f.gs_out = gs_out;
+    static const bool no_loc = getenv("B200Q_FP4_NO_LOC") != nullptr;   // A/B: recompute the group statistics in the compress pass (round 1)
+    f.loc = no_loc ? nullptr : loc_scratch;
     cudaMemsetAsync(sync, 0, sizeof(uint32_t) * 2 * n_spans, st);
     static const bool fma = getenv("B200Q_FP4_FMA") != nullptr;  // FHFMA unpack (ALU-pipe relief), A/B switch
     if (fma) nvfp4_fused_kernel<true><<<(unsigned)grid, FP4_THREADS, 0, st>>>(p, f);

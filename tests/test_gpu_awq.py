@@ -259,9 +259,11 @@ def test_qk_norm_rope_vs_eager(H, HKV, D, S, B):
                                        L.stream_ptr(got.device)))
     assert torch.equal(got[:, (H + HKV) * D:], v)  # v columns untouched
     diff = (got.float() - want.float()).abs()
-    # the only freedom is the summation order of mean(x^2): at most one bf16 ulp, on a small fraction of the elements
-    assert bool((diff <= want.float().abs() * 2 ** -7 + 1e-6).all()), float(diff.max())
-    assert float((diff > 0).float().mean()) < 0.02
+    # the only freedom is the summation order of mean(x^2): it flips the bf16 rounding of x * rsqrt(..) on a tiny fraction of the
+    # elements, and that one ulp propagates through w * vn and y * cos + rot * sin (a CPU run of the eager chain with an fp64 mean
+    # instead of the fp32 one shows the same: 3e-6 of the elements move, by up to 2 ulps)
+    assert bool((diff <= want.float().abs() * 2 ** -6 + 2 ** -6).all()), float(diff.max())
+    assert float((diff > 0).float().mean()) < 0.002
 
 
 def test_search_expert_mappings_matches_oracle():
