@@ -238,6 +238,17 @@ int b200q_gptq_hessian_accumulate(const void* xt, int64_t features, int64_t toke
 int b200q_qk_norm_rope(void* qkv, int64_t tokens, int32_t n_heads, int32_t n_kv, int32_t head_dim, int32_t seq_len,
                        const void* q_norm_weight, const void* k_norm_weight, const void* cos, const void* sin, float eps, void* stream);
 
+/* W2, attention parent: the causal grouped-query attention core softmax(Q K^T / sqrt(head_dim)) V of every calibration sample
+ * (batch-1 forwards of seq_len tokens in the reference's _run_samples; transformers sdpa_attention_forward with is_causal) on the
+ * tcgen05 tensor cores: fp32 scores / softmax statistics, bf16 probabilities, fp32 accumulation.
+ *   qkv  T [tokens, (n_heads + 2 n_kv) * head_dim]   (q, k normalised + rotated by b200q_qk_norm_rope; read only)
+ *   out  T [tokens, n_heads * head_dim]
+ *   workspace: b200q_attention_workspace(...) device bytes (V transposed per sample and kv head)
+ * tokens = samples * seq_len; head_dim 64 or 128; n_heads % n_kv == 0.  bf16 only. */
+int64_t b200q_attention_workspace(int64_t tokens, int32_t n_kv, int32_t head_dim, int32_t seq_len);
+int b200q_attention_core(const void* qkv, int64_t tokens, int32_t n_heads, int32_t n_kv, int32_t head_dim, int32_t seq_len, void* out,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Host-buffer pipeline: what LLMC model_free_ptq's per-tensor job does (load -> device -> observe ->
  * compress -> host), /root/reference/scripts/quant_GLM-4.7-Flash-FP8.py:11-24.  Pinned staging buffers and two

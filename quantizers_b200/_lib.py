@@ -61,6 +61,8 @@ _SIGS = {
     "b200q_awq_gemm_loss_workspace": (c_int64, [c_int64, c_int64, c_int64, c_int32]),
     "b200q_awq_gemm_loss_pairs": (_I, [_P, _P, c_int64, c_int64, _P, _P, c_int64, c_int32, _P, _P, c_int64, _P]),
     "b200q_qk_norm_rope": (_I, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P, c_float, _P]),
+    "b200q_attention_workspace": (c_int64, [c_int64, c_int32, c_int32, c_int32]),
+    "b200q_attention_core": (_I, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _P, _P, c_int64, _P]),
     "b200q_awq_gemm_project": (_I, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int32, _P, _P]),
     "b200q_mse_minmax": (_I, [_P, c_int64, c_int64, c_int64, _S, _P, c_float, c_int32, c_int32, c_float, _P, _P, _P, c_int64, _P]),
     "b200q_compress_nvfp4_workspace": (c_int64, [c_int64, c_int64, c_int64, c_int32]),

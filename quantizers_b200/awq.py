@@ -201,10 +201,16 @@ class MLPParent:
         return F.linear(F.silu(F.linear(x, weights[0])) * F.linear(x, weights[1]), self.down)
 
 
-def attention_core(qkv: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, seq_len: int, q_norm, k_norm, cos, sin, eps=1e-6):
+_ATTN_SDPA = __import__("os").environ.get("B200Q_ATTN_SDPA") is not None   # A/B switch: torch SDPA (library flash attention) instead of the tcgen05 core
+
+
+def attention_core(qkv: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, seq_len: int, q_norm, k_norm, cos, sin, eps=1e-6,
+                   out: Optional[torch.Tensor] = None):
     """Qwen3 attention between the q/k/v projections and o_proj (transformers Qwen3Attention.forward): per-head RMSNorm
     on q and k, rotary embedding, causal GQA attention.  ``qkv [T, (H + 2 Hkv) d]`` with T = samples * seq_len is
-    normalised / rotated IN PLACE by one CUDA kernel (``b200q_qk_norm_rope``); softmax(QK^T)V is torch SDPA on strided views."""
+    normalised / rotated IN PLACE by one CUDA kernel (``b200q_qk_norm_rope``); softmax(QK^T / sqrt(d)) V then runs per sample on
+    the hand-written tcgen05 kernel ``b200q_attention_core`` (round 1 used torch SDPA here; ``B200Q_ATTN_SDPA=1`` still selects it
+    for A/B runs).  Returns ``[T, H d]`` (written into ``out`` when given)."""
     L.require_cuda(qkv)
     T = qkv.shape[0]
     B = T // seq_len
@@ -212,18 +218,30 @@ def attention_core(qkv: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, se
         raise L.B200QError("attention_core takes a contiguous bf16 [samples * seq_len, (H + 2 Hkv) d] tensor")
     L.check(L.lib().b200q_qk_norm_rope(L.ptr(qkv), T, n_heads, n_kv, head_dim, seq_len, L.ptr(q_norm), L.ptr(k_norm), L.ptr(cos), L.ptr(sin),
                                        ctypes.c_float(eps), L.stream_ptr(qkv.device)))
+    if not _ATTN_SDPA:
+        # softmax(Q K^T / sqrt(d), causal) V per sample on the tcgen05 kernel (csrc/awq_attn_core.cu)
+        lib = L.lib()
+        out = torch.empty((T, n_heads * head_dim), dtype=qkv.dtype, device=qkv.device) if out is None else out
+        nws = int(lib.b200q_attention_workspace(T, n_kv, head_dim, seq_len))
+        ws = workspace.get("attn_vt", (max(nws, 16),), torch.uint8, qkv.device)
+        L.check(lib.b200q_attention_core(L.ptr(qkv), T, n_heads, n_kv, head_dim, seq_len, L.ptr(out), L.ptr(ws), nws, L.stream_ptr(qkv.device)))
+        return out
     q, k, v = qkv.split([n_heads * head_dim, n_kv * head_dim, n_kv * head_dim], dim=-1)
     q = q.unflatten(-1, (n_heads, head_dim)).unflatten(0, (B, seq_len)).transpose(1, 2)
     k = k.unflatten(-1, (n_kv, head_dim)).unflatten(0, (B, seq_len)).transpose(1, 2)
     v = v.unflatten(-1, (n_kv, head_dim)).unflatten(0, (B, seq_len)).transpose(1, 2)
     o = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=n_heads != n_kv)
-    return o.transpose(1, 2).reshape(T, n_heads * head_dim)
+    o = o.transpose(1, 2).reshape(T, n_heads * head_dim)
+    if out is not None:
+        out.copy_(o)
+        return out
+    return o
 
 
 class AttentionParent:
     """Parent == self_attn whose q/k/v projections are the balance layers (input_layernorm -> q, k, v).  Balance weights
-    are stacked [Wq; Wk; Wv].  The projections and the o_proj + loss run on the tcgen05 kernels; the softmax(QK^T)V core
-    between them is torch SDPA (library flash attention), as in the reference's ``_run_samples``."""
+    are stacked [Wq; Wk; Wv].  Projections, the causal GQA attention core and the o_proj + loss all run on hand-written tcgen05
+    kernels (awq_gemm.cu, awq_attn_core.cu)."""
 
     def __init__(self, o_proj: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, seq_len: int, q_norm: torch.Tensor,
                  k_norm: torch.Tensor, rope_theta: float = 1e6, eps: float = 1e-6):
@@ -242,7 +260,7 @@ class AttentionParent:
         qkv = gemm_project(x, w_all, swiglu=False, out=workspace.get("proj", (w_all.shape[0], x.shape[0], w_all.shape[1]), x.dtype, x.device))
         attn = workspace.get("attn", (qkv.shape[0], x.shape[0], self.o.shape[1]), x.dtype, x.device)
         for v in range(qkv.shape[0]):
-            attn[v] = self.core(qkv[v])
+            attention_core(qkv[v], *self.cfg, self.q_norm, self.k_norm, self.cos, self.sin, self.eps, out=attn[v])
         return gemm_loss_pairs(attn[0], attn[1:], self.o, None), x.shape[0] * self.o.shape[0]
 
     def __call__(self, weights, x):

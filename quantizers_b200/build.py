@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "lib", "libb200q.so")
 HOSTMATH = os.path.join(HERE, "lib", "libb200q_hostmath.so")
 
 SOURCES = ["abi.cu", "quant_group.cu", "quant_group_fast.cu", "quant_group_tma.cu", "quant_tile_fast.cu", "quant_channel_fast.cu", "decode_fast.cu", "quant_nvfp4_persistent.cu", "quant_elementwise.cu", "elementwise_fast.cu", "quant_tile.cu", "observers.cu", "pack.cu", "awq_stats.cu",
-           "awq_gemm.cu", "awq_attn.cu", "awq_fq_fast.cu"]
+           "awq_gemm.cu", "awq_attn.cu", "awq_fq_fast.cu", "awq_attn_core.cu"]
 HEADERS = ["qmath.cuh", "common.cuh", "kernels.cuh", "fastmath.cuh", "async.cuh", "fp4.cuh", os.path.join("..", "..", "include", "b200q.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -1,0 +1,423 @@
+// awq_attn_core.cu -- causal grouped-query attention core of the AWQ attention parent (LLMC AWQModifier._run_samples on
+// ``self_attn``; transformers Qwen3Attention: softmax(Q K^T / sqrt(d), causal) V between the q/k/v projections and o_proj), on the
+// 5th-gen tensor cores.  Round 1 called torch's scaled_dot_product_attention here (a library kernel on the hot path, 21 x per
+// q/k/v mapping); this is the hand-written replacement.
+//
+// Inputs are the projected rows that awq_gemm_project_kernel wrote and b200q_qk_norm_rope normalised / rotated in place:
+//   qkv [T, (H + 2 Hkv) d] bf16, T = samples * seq_len; every sample attends within itself (batch-1 forwards in the reference).
+//   vt  [samples * Hkv * d, S_pad] bf16: V transposed per (sample, kv head) by attn_transpose_v_kernel, so that BOTH GEMMs take
+//   K-major operands (the same SWIZZLE_128B tiles / descriptors as awq_gemm.cu): S = Q K^T contracts over d, O = P V over keys.
+//
+// One CTA per (sample, q head, 128-query block); key blocks 0 .. qb (causal):
+//   warp 0      TMA producer : Q once; per key block K_j [128 keys x d] and V^T_j [d x 128 keys] into a 2-stage ring
+//   warp 1      MMA issuer   : S_{j+1} = Q K_{j+1}^T is issued BEFORE O += P_j V_j, so the softmax of block j overlaps it
+//                              (S double-buffered in TMEM columns [0,128) / [128,256), O in [256, 256 + d))
+//   warps 2..5  softmax      : one query row per thread (TMEM lane = row): pass 1 tcgen05.ld -> scaled / masked row max, online
+//                              rescale of O in TMEM (tcgen05.ld / st, skipped when no row's max moved), pass 2 reload -> exp2 ->
+//                              row sum, P as bf16 into the SWIZZLE_128B A tile in shared memory; epilogue O / l -> bf16 rows.
+// fp32 scores, fp32 softmax statistics, bf16 probabilities, fp32 accumulation -- the arithmetic of a flash-attention forward.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include "../../include/b200q.h"
+#include "common.cuh"
+
+namespace b200q {
+namespace {
+
+constexpr int BQ = 128, BKEY = 128, SUBK = 64;      // query block, key block, 128-byte (64 x bf16) K-major sub-tile width
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kSubBytes = 128 * SUBK * 2;           // one [128 rows x 64] sub-tile = 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+          "r"(r[30]), "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) { uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
+
+// K-major operand tile, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart (same descriptor as awq_gemm.cu)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16: D = f32, A = B = bf16, both K-major, M = 128, N as given
+__device__ __forceinline__ constexpr uint32_t idesc_n(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+}
+
+struct AttnParams {
+    int32_t n_heads, n_kv, seq_len, q_blocks;   // q_blocks = ceil(seq_len / 128)
+    int32_t samples;
+    float scale_log2e;                          // softmax scale * log2(e)
+    uint16_t* out;                              // bf16 [T, n_heads * D]
+};
+
+// ------------------------------------------------------------------------------------------------ V -> V^T per (sample, kv head)
+__global__ void attn_transpose_v_kernel(const uint16_t* __restrict__ qkv, int64_t row_elems, int v_col0, int d, int seq_len, int s_pad,
+                                        int n_kv, uint16_t* __restrict__ vt) {
+    __shared__ uint16_t tile[32][34];
+    const int bh = blockIdx.z, b = bh / n_kv, hk = bh - b * n_kv;
+    const int k0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int key = k0 + ty + 8 * i;
+        tile[ty + 8 * i][tx] = key < seq_len ? qkv[((int64_t)b * seq_len + key) * row_elems + v_col0 + hk * d + d0 + tx] : (uint16_t)0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int dd = d0 + ty + 8 * i, key = k0 + tx;
+        if (key < s_pad) vt[((int64_t)bh * d + dd) * s_pad + key] = tile[tx][ty + 8 * i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ attention core
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_core_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_vt, const AttnParams p) {
+    constexpr int NSUB = D / SUBK;                          // 64-wide sub-tiles along d
+    constexpr int kQBytes = NSUB * kSubBytes;               // Q tile / K tile: [128 x D]
+    constexpr int kVBytes = 2 * (D * SUBK * 2);             // V^T tile: [D rows x 128 keys] = 2 sub-tiles of [D x 64]
+    constexpr int kVSub = D * SUBK * 2;
+    constexpr int kPBytes = 2 * kSubBytes;                  // P tile: [128 x 128 keys]
+    constexpr int kStageBytes = kQBytes + kVBytes;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t q_s = smem_u32(smem);
+    const uint32_t kv_s = q_s + kQBytes;                    // stage s: K at kv_s + s * kStageBytes, V^T right after it
+    const uint32_t p_s = kv_s + 2 * kStageBytes;
+    const uint32_t bars = p_s + kPBytes;
+    // barriers: q_full, kv_full[2], kv_empty[2], s_full[2], s_empty[2], p_full, p_free
+    const uint32_t bar_q = bars, bar_kvf = bars + 8, bar_kve = bars + 24, bar_sf = bars + 40, bar_se = bars + 56, bar_pf = bars + 72,
+                   bar_pfree = bars + 80;
+    uint32_t* tmem_slot = (uint32_t*)(smem + kQBytes + 2 * kStageBytes + kPBytes + 96);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // work item
+    const int qb = p.q_blocks - 1 - (int)(blockIdx.x % p.q_blocks);   // long (late) query blocks first
+    const int bh = blockIdx.x / p.q_blocks;
+    const int b = bh / p.n_heads, h = bh - b * p.n_heads;
+    const int hk = h / (p.n_heads / p.n_kv);
+    const int q0 = qb * BQ;
+    const int n_blocks = min(qb + 1, (p.seq_len + BKEY - 1) / BKEY);
+    const int row0 = b * p.seq_len;                          // first token row of the sample
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_q, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(bar_kvf + 8 * s, 1); mbar_init(bar_kve + 8 * s, 1); mbar_init(bar_sf + 8 * s, 1); mbar_init(bar_se + 8 * s, 4); }
+        mbar_init(bar_pf, 4);
+        mbar_init(bar_pfree, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_o = tmem_base + 256;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_q, kQBytes);
+#pragma unroll
+            for (int t = 0; t < NSUB; t++) tma_load_2d(q_s + t * kSubBytes, &map_qk, h * D + t * SUBK, row0 + q0, bar_q);
+            for (int j = 0; j < n_blocks; j++) {
+                const int s = j & 1;
+                mbar_wait(bar_kve + 8 * s, (uint32_t)((j >> 1) & 1) ^ 1u);
+                mbar_arrive_expect_tx(bar_kvf + 8 * s, kStageBytes);
+                const uint32_t k_dst = kv_s + s * kStageBytes, v_dst = k_dst + kQBytes;
+#pragma unroll
+                for (int t = 0; t < NSUB; t++)
+                    tma_load_2d(k_dst + t * kSubBytes, &map_qk, (p.n_heads + hk) * D + t * SUBK, row0 + j * BKEY, bar_kvf + 8 * s);
+#pragma unroll
+                for (int t = 0; t < 2; t++)
+                    tma_load_2d(v_dst + t * kVSub, &map_vt, j * BKEY + t * SUBK, (b * p.n_kv + hk) * D, bar_kvf + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            auto issue_s = [&](int j) {
+                const int s = j & 1;
+                mbar_wait(bar_kvf + 8 * s, (uint32_t)((j >> 1) & 1));
+                mbar_wait(bar_se + 8 * s, (uint32_t)((j >> 1) & 1) ^ 1u);   // softmax has drained this S slot
+                tc_fence_after();
+                const uint32_t k_addr = kv_s + s * kStageBytes;
+#pragma unroll
+                for (int k = 0; k < D / 16; k++) {
+                    const uint64_t ad = make_desc(q_s + (k / 4) * kSubBytes) + 2 * (k % 4);
+                    const uint64_t bd = make_desc(k_addr + (k / 4) * kSubBytes) + 2 * (k % 4);
+                    tc_mma(tmem_base + s * BKEY, ad, bd, idesc_n(BKEY), k ? 1u : 0u);
+                }
+                tc_commit(bar_sf + 8 * s);
+            };
+            mbar_wait(bar_q, 0);
+            issue_s(0);
+            for (int j = 0; j < n_blocks; j++) {
+                if (j + 1 < n_blocks) issue_s(j + 1);
+                const int s = j & 1;
+                mbar_wait(bar_pf, (uint32_t)(j & 1));                        // P_j in shared memory, O rescaled
+                tc_fence_after();
+                const uint32_t v_addr = kv_s + s * kStageBytes + kQBytes;
+#pragma unroll
+                for (int k = 0; k < BKEY / 16; k++) {
+                    const uint64_t ad = make_desc(p_s + (k / 4) * kSubBytes) + 2 * (k % 4);
+                    const uint64_t bd = make_desc(v_addr + (k / 4) * kVSub) + 2 * (k % 4);
+                    tc_mma(tmem_o, ad, bd, idesc_n(D), (j | k) ? 1u : 0u);
+                }
+                tc_commit(bar_kve + 8 * s);      // K_j / V_j stage free
+                tc_commit(bar_pfree);            // P buffer free, O updated
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax + epilogue: one query row per thread
+        const uint32_t quad = (uint32_t)warp & 3u;
+        const int row = (int)quad * 32 + lane;               // row inside the query block == TMEM lane
+        const uint32_t t_lane = (quad * 32u) << 16;
+        const int q_idx = q0 + row;
+        float m = -INFINITY, l = 0.0f;
+        const uint32_t p_row = p_s + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+        for (int j = 0; j < n_blocks; j++) {
+            const int s = j & 1;
+            const uint32_t t_s = tmem_base + t_lane + s * BKEY;
+            const int key0 = j * BKEY;
+            const bool diag = key0 + BKEY - 1 > q0;           // block touches the causal boundary (or the sequence end)
+            mbar_wait(bar_sf + 8 * s, (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            // ---- pass 1: row max of the scaled, masked scores
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < BKEY / 32; c++) {
+                uint32_t v[32];
+                tc_ld32(t_s + c * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const int key = key0 + c * 32 + i;
+                    float x = __uint_as_float(v[i]) * p.scale_log2e;
+                    if (diag && (key > q_idx || key >= p.seq_len)) x = -INFINITY;
+                    mx = fmaxf(mx, x);
+                }
+            }
+            const float m_new = fmaxf(m, mx);
+            const float m_use = m_new == -INFINITY ? 0.0f : m_new;   // fully masked row (query beyond the sequence): keep exp2 finite
+            const float alpha = ex2(m - m_use);                       // m = -inf on the first block -> 0
+            // ---- O rescale (needs O += P_{j-1} V_{j-1} retired) and the P buffer free
+            if (j > 0) {
+                mbar_wait(bar_pfree, (uint32_t)((j - 1) & 1));
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+                    for (int c = 0; c < D / 32; c++) {
+                        uint32_t o[32];
+                        tc_ld32(tmem_o + t_lane + c * 32, o);
+#pragma unroll
+                        for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tc_st32(tmem_o + t_lane + c * 32, o);
+                    }
+                }
+            }
+            // ---- pass 2: probabilities -> bf16 A tile (SWIZZLE_128B, K-major over the keys), row sum
+            float sum = 0.0f;
+#pragma unroll 1
+            for (int c = 0; c < BKEY / 32; c++) {
+                uint32_t v[32];
+                tc_ld32(t_s + c * 32, v);
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    float e[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int key = key0 + c * 32 + 2 * i + u;
+                        float x = __uint_as_float(v[2 * i + u]) * p.scale_log2e - m_use;
+                        if (diag && (key > q_idx || key >= p.seq_len)) x = -INFINITY;
+                        e[u] = ex2(x);
+                    }
+                    pk[i] = cvt_bf16x2(e[1], e[0]);
+                    // the row sum uses the ROUNDED probabilities, so that O / l normalises exactly what P V accumulated
+                    sum += __uint_as_float(pk[i] << 16) + __uint_as_float(pk[i] & 0xffff0000u);
+                }
+                // 32 keys = 4 chunks of 16 bytes; chunk index inside the 64-key sub-tile, XOR-swizzled with the row
+                const uint32_t sub = (uint32_t)(c >> 1) * kSubBytes;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t chunk = (uint32_t)((c & 1) * 4 + q);
+                    const uint32_t addr = p_row + sub + ((chunk ^ (uint32_t)(row & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                }
+            }
+            l = l * alpha + sum;
+            m = m_new;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy P stores -> visible to the tensor core's async proxy
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_se + 8 * s);     // S slot drained
+                mbar_arrive(bar_pf);             // P_j ready, O rescaled
+            }
+        }
+        // ---- epilogue: O / l -> bf16
+        mbar_wait(bar_pfree, (uint32_t)((n_blocks - 1) & 1));
+        tc_fence_after();
+        const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+        uint16_t* orow = p.out + ((int64_t)(row0 + q_idx) * p.n_heads + h) * D;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; c++) {
+            uint32_t o[32];
+            tc_ld32(tmem_o + t_lane + c * 32, o);
+            if (q_idx < p.seq_len) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        w[i] = cvt_bf16x2(__uint_as_float(o[8 * q + 2 * i + 1]) * inv, __uint_as_float(o[8 * q + 2 * i]) * inv);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+PFN_cuTensorMapEncodeTiled get_encode() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled)ptr;
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] with a row pitch, box = [box_rows x 64 columns], SWIZZLE_128B
+int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems, int box_rows) {
+    PFN_cuTensorMapEncodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return B200Q_ECUDA; }
+    const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows}, strides[1] = {(uint64_t)pitch_elems * 2};
+    const uint32_t box[2] = {SUBK, (uint32_t)box_rows}, estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d", (int)r); return B200Q_ECUDA; }
+    return B200Q_OK;
+}
+
+template <int D>
+int launch_attn(const CUtensorMap& mqk, const CUtensorMap& mvt, const AttnParams& p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)(D / SUBK) * kSubBytes + 2 * ((size_t)(D / SUBK) * kSubBytes + 2 * (D * SUBK * 2)) + 2 * kSubBytes + 128 + 1024;
+    cudaFuncSetAttribute(attn_core_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t grid = (int64_t)p.samples * p.n_heads * p.q_blocks;
+    attn_core_kernel<D><<<(unsigned)grid, kThreads, smem, st>>>(mqk, mvt, p);
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+}  // namespace
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" {
+
+int64_t b200q_attention_workspace(int64_t tokens, int32_t n_kv, int32_t head_dim, int32_t seq_len) {
+    if (seq_len <= 0) return 0;
+    const int64_t s_pad = ((int64_t)seq_len + 63) / 64 * 64;
+    return (tokens / seq_len) * n_kv * head_dim * s_pad * 2;
+}
+
+int b200q_attention_core(const void* qkv, int64_t tokens, int32_t n_heads, int32_t n_kv, int32_t head_dim, int32_t seq_len, void* out,
+                         void* workspace, int64_t workspace_bytes, void* stream) {
+    B200Q_REQUIRE(qkv && out && workspace, "b200q_attention_core: NULL pointer");
+    B200Q_REQUIRE(head_dim == 64 || head_dim == 128, "head_dim must be 64 or 128, got %d", (int)head_dim);
+    B200Q_REQUIRE(n_heads >= 1 && n_kv >= 1 && n_heads % n_kv == 0, "n_heads must be a multiple of n_kv");
+    B200Q_REQUIRE(seq_len >= 1 && tokens >= seq_len && tokens % seq_len == 0, "tokens must be whole samples of seq_len");
+    B200Q_REQUIRE(workspace_bytes >= b200q_attention_workspace(tokens, n_kv, head_dim, seq_len), "attention workspace too small");
+    B200Q_REQUIRE((((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)workspace) & 15) == 0, "operands must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t row_elems = (int64_t)(n_heads + 2 * n_kv) * head_dim;
+    const int samples = (int)(tokens / seq_len);
+    const int s_pad = (seq_len + 63) / 64 * 64;
+    B200Q_REQUIRE((int64_t)samples * n_heads * ((seq_len + BQ - 1) / BQ) < (1ll << 31), "too many attention work items");
+    // V^T per (sample, kv head)
+    {
+        dim3 grid((unsigned)((s_pad + 31) / 32), (unsigned)(head_dim / 32), (unsigned)(samples * n_kv));
+        B200Q_REQUIRE(grid.z <= 65535, "samples * n_kv out of range for one launch");
+        attn_transpose_v_kernel<<<grid, dim3(32, 8), 0, st>>>((const uint16_t*)qkv, row_elems, (n_heads + n_kv) * head_dim, head_dim, seq_len, s_pad,
+                                                              n_kv, (uint16_t*)workspace);
+        B200Q_CHECK_LAUNCH();
+    }
+    CUtensorMap mqk, mvt;
+    if (int rc = make_map(&mqk, qkv, tokens, row_elems, row_elems, 128)) return rc;
+    if (int rc = make_map(&mvt, workspace, (int64_t)samples * n_kv * head_dim, s_pad, s_pad, head_dim)) return rc;
+    AttnParams p;
+    p.n_heads = n_heads; p.n_kv = n_kv; p.seq_len = seq_len; p.q_blocks = (seq_len + BQ - 1) / BQ; p.samples = samples;
+    p.scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
+    p.out = (uint16_t*)out;
+    return head_dim == 128 ? launch_attn<128>(mqk, mvt, p, st) : launch_attn<64>(mqk, mvt, p, st);
+}
+
+}  // extern "C"

@@ -575,12 +575,15 @@ int launch_tma(const TmaParams& p, cudaStream_t st) {
         default: break;
         }
     }
-    if constexpr (QT != QT_FP4) {
-        // Default (round 2): the single-evaluation kernel with EIGHT warps per SM.  With 12 warps x 2 stages x 8 KB the lean kernel keeps
+    if constexpr (QT == QT_INT) {
+        // Default (round 2), INT4: the single-evaluation kernel with EIGHT warps per SM.  With 12 warps x 2 stages x 8 KB the lean kernel keeps
         // ~28 MB of bulk loads outstanding and gets 9 % LESS bandwidth than the heavier bracket kernel (ncu: 1.7 warps per issue parked
         // on the mbarrier vs 0.09); 8 warps: 6.7-7.0 TB/s on every INT4 scheme, 6 warps: compute-bound again (scripts/ab_tma2.py,
-        // profiles/r2_int4_kernel_ab.md).  B200Q_TMA_WARPS = 7 / 9 / 10 / 12 for sweeps.
-        static const int warps = getenv("B200Q_TMA_WARPS") ? atoi(getenv("B200Q_TMA_WARPS")) : 8;
+        // profiles/r2_int4_kernel_ab.md).  The one compute-heavy INT4 variant, asymmetric g32 (a qparam chain + zero point per 32
+        // elements), keeps 12 warps: 0.88 of the roofline vs 0.73 with 8.  FP8 GROUP stays on the bracket kernel with 10 warps
+        // (g32: 0.93 vs 0.83-0.87 for the single-evaluation variants -- its bf16 -> e4m3 second conversion needs the issue slots).
+        // B200Q_TMA_WARPS = 7 / 9 / 10 / 12 for sweeps.
+        static const int warps = getenv("B200Q_TMA_WARPS") ? atoi(getenv("B200Q_TMA_WARPS")) : ((LOG2N <= 2 && !SYM) ? 12 : 8);
         if (!bracket) {
             if (fma) {
                 switch (warps) {

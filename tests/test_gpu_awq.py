@@ -390,3 +390,39 @@ def test_scaled_fake_quantize_grid_fast_kernel_bit_exact(name, geom, sym):
             assert_bits_equal(out[r], want, f"{name} rows={rows} K={K} ratio {r}")
         one = awq.scaled_fake_quantize(w.cuda(), scales[4].cuda(), Args(name))
         assert_bits_equal(one, R.scaled_fake_quantize(w, scales[4], geom, O.INT, 4, sym), f"{name} single")
+
+
+@pytest.mark.parametrize("H,HKV,D,S,B", [(32, 8, 128, 512, 2), (4, 2, 64, 64, 3), (5, 1, 128, 70, 1), (8, 8, 128, 300, 2), (6, 3, 64, 257, 2)])
+def test_attention_core_tcgen05_vs_reference(H, HKV, D, S, B):
+    """csrc/awq_attn_core.cu (causal GQA attention of every sample on tcgen05: fp32 scores / statistics, bf16 probabilities, fp32
+    accumulation) against an fp32 reference of the same batch-1 causal attention and against torch SDPA: within bf16 output
+    resolution; full and ragged sequence lengths, MHA / GQA / MQA, both head sizes."""
+    import ctypes
+
+    from quantizers_b200 import _lib as L
+
+    g = torch.Generator().manual_seed(11)
+    T = B * S
+    qkv = (torch.randn(T, (H + 2 * HKV) * D, generator=g) * 1.5).to(torch.bfloat16).cuda()
+    q, k, v = qkv.split([H * D, HKV * D, HKV * D], dim=-1)
+    q = q.reshape(B, S, H, D).transpose(1, 2).float()
+    k = k.reshape(B, S, HKV, D).transpose(1, 2).float().repeat_interleave(H // HKV, dim=1)
+    v = v.reshape(B, S, HKV, D).transpose(1, 2).float().repeat_interleave(H // HKV, dim=1)
+    att = (q @ k.transpose(-1, -2)) / D ** 0.5
+    att = att.masked_fill(torch.ones(S, S, dtype=torch.bool, device="cuda").triu(1), float("-inf"))
+    want = (torch.softmax(att, dim=-1) @ v).transpose(1, 2).reshape(T, H * D)
+    lib = L.lib()
+    out = torch.full((T, H * D), float("nan"), dtype=torch.bfloat16, device="cuda")
+    nws = int(lib.b200q_attention_workspace(T, HKV, D, S))
+    ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    before = qkv.clone()
+    L.check(lib.b200q_attention_core(L.ptr(qkv), T, H, HKV, D, S, L.ptr(out), L.ptr(ws), nws, L.stream_ptr(qkv.device)))
+    torch.cuda.synchronize()
+    assert torch.equal(qkv, before)                      # inputs are read only
+    assert bool(torch.isfinite(out.float()).all())
+    err = (out.float() - want).abs()
+    tol = 2.0 ** -7 * want.abs() + 0.02                  # bf16 output + bf16 probabilities
+    assert bool((err <= tol).all()), (float(err.max()), float(want.abs().max()))
+    sd = torch.nn.functional.scaled_dot_product_attention(q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16), is_causal=True)
+    sd = sd.transpose(1, 2).reshape(T, H * D).float()
+    assert float((out.float() - sd).abs().max()) <= 0.03 + 2.0 ** -6 * float(sd.abs().max())
