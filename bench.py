@@ -519,7 +519,7 @@ def run_moe_awq(args, dev, world, rank, peaks):
 
 def run_moe_block(args, dev, world, rank, peak):
     """configs[4] kind (i): the layer-wide mapping post_attention_layernorm -> every expert's w1, w3 (one scale vector, parent =
-    the routed sparse-MoE block, top-8 routing) on a reduced layer of ``--moe-block-experts`` experts.  All experts live on every
+    the routed sparse-MoE block, top-8 routing) on a layer of ``--moe-block-experts`` experts (default: all 256 of MiniMax-M2.1).  All experts live on every
     rank; the T calibration tokens are sharded across the ranks (strong scaling) and the |x| sums / [n_grid] loss accumulators
     are all-reduced over NCCL -- the one real exchange step of the path."""
     import torch.distributed as dist
@@ -826,8 +826,8 @@ def main():
     ap.add_argument("--awq-tokens", type=int, default=64 * 512, help="calibration tokens per layer (64 samples x 512)")
     ap.add_argument("--moe-layers", type=int, default=8, help="layers of the Qwen3-30B-A3B NVFP4 expert-sharded leg (0 disables it)")
     ap.add_argument("--moe-steps", type=int, default=20)
-    ap.add_argument("--moe-awq-experts", type=int, default=16, help="experts of the MiniMax-M2.1 per-expert AWQ leg (0 disables it)")
-    ap.add_argument("--moe-block-experts", type=int, default=32, help="experts of the reduced layer of the layer-wide MoE mapping leg (0 disables it)")
+    ap.add_argument("--moe-awq-experts", type=int, default=256, help="experts of the MiniMax-M2.1 per-expert AWQ leg (256 = one full layer; 0 disables it)")
+    ap.add_argument("--moe-block-experts", type=int, default=256, help="experts of the layer-wide MoE mapping leg (256 = the full MiniMax-M2.1 layer; 0 disables it)")
     ap.add_argument("--cpu-awq-tokens", type=int, default=1024, help="calibration tokens of the CPU AWQ baseline (whole layer; 0 disables it); "
                                                                       "--impl reference uses max(this, 2048)")
     ap.add_argument("--glm-units", type=int, default=48, help="units of the GLM-4.7-Flash FP8 leg (0 disables it)")

@@ -8,13 +8,14 @@
 //   vt  [samples * Hkv * d, S_pad] bf16: V transposed per (sample, kv head) by attn_transpose_v_kernel, so that BOTH GEMMs take
 //   K-major operands (the same SWIZZLE_128B tiles / descriptors as awq_gemm.cu): S = Q K^T contracts over d, O = P V over keys.
 //
-// One CTA per (sample, q head, 128-query block); key blocks 0 .. qb (causal):
+// Work item = (sample, q head, 128-query block); key blocks 0 .. qb (causal); persistent CTAs, one per SM:
 //   warp 0      TMA producer : Q once; per key block K_j [128 keys x d] and V^T_j [d x 128 keys] into a 2-stage ring
 //   warp 1      MMA issuer   : S_{j+1} = Q K_{j+1}^T is issued BEFORE O += P_j V_j, so the softmax of block j overlaps it
 //                              (S double-buffered in TMEM columns [0,128) / [128,256), O in [256, 256 + d))
-//   warps 2..5  softmax      : one query row per thread (TMEM lane = row): pass 1 tcgen05.ld -> scaled / masked row max, online
-//                              rescale of O in TMEM (tcgen05.ld / st, skipped when no row's max moved), pass 2 reload -> exp2 ->
-//                              row sum, P as bf16 into the SWIZZLE_128B A tile in shared memory; epilogue O / l -> bf16 rows.
+//   warps 2..5  softmax      : one query row per thread (TMEM lane = row): the 128 scores of the row in registers (four x32
+//                              tcgen05.ld in flight, one wait), scaled / masked row max, LAZY running maximum (moves only when
+//                              the row max grew by > 2^8, so O in TMEM is almost never rescaled: tcgen05.ld / st only then),
+//                              exp2 -> row sum, P as bf16 into the SWIZZLE_128B A tile in shared memory; epilogue O / l -> bf16.
 // fp32 scores, fp32 softmax statistics, bf16 probabilities, fp32 accumulation -- the arithmetic of a flash-attention forward.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -74,6 +75,18 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the same load without the wait: issue several, then tc_wait_ld() once
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -125,39 +138,51 @@ __global__ void attn_transpose_v_kernel(const uint16_t* __restrict__ qkv, int64_
 }
 
 // ------------------------------------------------------------------------------------------------ attention core
+// Persistent: one CTA per SM walks the (query block, sample, head) items -- longest (latest query block) first -- and all three
+// roles run one item ahead of each other: Q is double-buffered in shared memory, O in TMEM (columns [256, 256 + D) / [384, 384 + D)),
+// and the MMA warp issues the first S = Q K^T of the NEXT item before the last O += P V of the current one, so TMA latency, the
+// softmax and the epilogue of neighbouring items overlap (the first cut, one CTA per item, spent ~6 of its ~10 us per item on
+// exposed start-up / drain: 554 us for the AWQ shape vs 217 us for cuDNN's flash kernel).
+struct ItemIter {
+    int t, end, stride;
+    int q_blocks, heads_total, n_heads, n_kv, seq_len;
+    __device__ __forceinline__ bool valid() const { return t < end; }
+    __device__ __forceinline__ void next() { t += stride; }
+    __device__ __forceinline__ void decode(int& b, int& h, int& qb, int& n_blocks) const {
+        qb = q_blocks - 1 - t / heads_total;          // items sorted by length: all (sample, head) pairs of the last query block first
+        const int bh = t - (t / heads_total) * heads_total;
+        b = bh / n_heads;
+        h = bh - b * n_heads;
+        n_blocks = min(qb + 1, (seq_len + BKEY - 1) / BKEY);
+    }
+};
+
 template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_core_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_vt, const AttnParams p) {
     constexpr int NSUB = D / SUBK;                          // 64-wide sub-tiles along d
     constexpr int kQBytes = NSUB * kSubBytes;               // Q tile / K tile: [128 x D]
-    constexpr int kVBytes = 2 * (D * SUBK * 2);             // V^T tile: [D rows x 128 keys] = 2 sub-tiles of [D x 64]
-    constexpr int kVSub = D * SUBK * 2;
+    constexpr int kVSub = D * SUBK * 2;                     // V^T sub-tile: [D rows x 64 keys]
+    constexpr int kVBytes = 2 * kVSub;                      // V^T tile: [D x 128 keys]
     constexpr int kPBytes = 2 * kSubBytes;                  // P tile: [128 x 128 keys]
     constexpr int kStageBytes = kQBytes + kVBytes;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const uint32_t q_s = smem_u32(smem);
-    const uint32_t kv_s = q_s + kQBytes;                    // stage s: K at kv_s + s * kStageBytes, V^T right after it
+    const uint32_t q_s = smem_u32(smem);                    // Q buffer i at q_s + i * kQBytes
+    const uint32_t kv_s = q_s + 2 * kQBytes;                // stage s: K at kv_s + s * kStageBytes, V^T right after it
     const uint32_t p_s = kv_s + 2 * kStageBytes;
     const uint32_t bars = p_s + kPBytes;
-    // barriers: q_full, kv_full[2], kv_empty[2], s_full[2], s_empty[2], p_full, p_free
-    const uint32_t bar_q = bars, bar_kvf = bars + 8, bar_kve = bars + 24, bar_sf = bars + 40, bar_se = bars + 56, bar_pf = bars + 72,
-                   bar_pfree = bars + 80;
-    uint32_t* tmem_slot = (uint32_t*)(smem + kQBytes + 2 * kStageBytes + kPBytes + 96);
+    // barriers: q_full[2], q_empty[2], kv_full[2], kv_empty[2], s_full[2], s_empty[2], o_empty[2], p_full, p_free
+    const uint32_t bar_qf = bars, bar_qe = bars + 16, bar_kvf = bars + 32, bar_kve = bars + 48, bar_sf = bars + 64, bar_se = bars + 80,
+                   bar_oe = bars + 96, bar_pf = bars + 112, bar_pfree = bars + 120;
+    uint32_t* tmem_slot = (uint32_t*)(smem + 2 * kQBytes + 2 * kStageBytes + kPBytes + 136);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // work item
-    const int qb = p.q_blocks - 1 - (int)(blockIdx.x % p.q_blocks);   // long (late) query blocks first
-    const int bh = blockIdx.x / p.q_blocks;
-    const int b = bh / p.n_heads, h = bh - b * p.n_heads;
-    const int hk = h / (p.n_heads / p.n_kv);
-    const int q0 = qb * BQ;
-    const int n_blocks = min(qb + 1, (p.seq_len + BKEY - 1) / BKEY);
-    const int row0 = b * p.seq_len;                          // first token row of the sample
-
     if (threadIdx.x == 0) {
-        mbar_init(bar_q, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(bar_kvf + 8 * s, 1); mbar_init(bar_kve + 8 * s, 1); mbar_init(bar_sf + 8 * s, 1); mbar_init(bar_se + 8 * s, 4); }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(bar_qf + 8 * s, 1); mbar_init(bar_qe + 8 * s, 1); mbar_init(bar_kvf + 8 * s, 1); mbar_init(bar_kve + 8 * s, 1);
+            mbar_init(bar_sf + 8 * s, 1); mbar_init(bar_se + 8 * s, 4); mbar_init(bar_oe + 8 * s, 4);
+        }
         mbar_init(bar_pf, 4);
         mbar_init(bar_pfree, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -170,60 +195,99 @@ attn_core_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_o = tmem_base + 256;
+
+    ItemIter iter;
+    iter.t = (int)blockIdx.x; iter.stride = (int)gridDim.x;
+    iter.heads_total = p.samples * p.n_heads; iter.end = iter.heads_total * p.q_blocks;
+    iter.q_blocks = p.q_blocks; iter.n_heads = p.n_heads; iter.n_kv = p.n_kv; iter.seq_len = p.seq_len;
+    const int kv_rep = p.n_heads / p.n_kv;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            mbar_arrive_expect_tx(bar_q, kQBytes);
+            uint32_t it = 0, g = 0;
+            for (; iter.valid(); iter.next(), it++) {
+                int b, h, qb, nb;
+                iter.decode(b, h, qb, nb);
+                const int hk = h / kv_rep, row0 = b * p.seq_len, qbuf = (int)(it & 1u);
+                mbar_wait(bar_qe + 8 * qbuf, ((it >> 1) & 1u) ^ 1u);           // the S MMAs of item it - 2 have retired
+                mbar_arrive_expect_tx(bar_qf + 8 * qbuf, kQBytes);
 #pragma unroll
-            for (int t = 0; t < NSUB; t++) tma_load_2d(q_s + t * kSubBytes, &map_qk, h * D + t * SUBK, row0 + q0, bar_q);
-            for (int j = 0; j < n_blocks; j++) {
-                const int s = j & 1;
-                mbar_wait(bar_kve + 8 * s, (uint32_t)((j >> 1) & 1) ^ 1u);
-                mbar_arrive_expect_tx(bar_kvf + 8 * s, kStageBytes);
-                const uint32_t k_dst = kv_s + s * kStageBytes, v_dst = k_dst + kQBytes;
+                for (int t = 0; t < NSUB; t++) tma_load_2d(q_s + qbuf * kQBytes + t * kSubBytes, &map_qk, h * D + t * SUBK, row0 + qb * BQ, bar_qf + 8 * qbuf);
+                for (int j = 0; j < nb; j++, g++) {
+                    const uint32_t s = g & 1u;
+                    mbar_wait(bar_kve + 8 * s, ((g >> 1) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(bar_kvf + 8 * s, kStageBytes);
+                    const uint32_t k_dst = kv_s + s * kStageBytes, v_dst = k_dst + kQBytes;
 #pragma unroll
-                for (int t = 0; t < NSUB; t++)
-                    tma_load_2d(k_dst + t * kSubBytes, &map_qk, (p.n_heads + hk) * D + t * SUBK, row0 + j * BKEY, bar_kvf + 8 * s);
+                    for (int t = 0; t < NSUB; t++)
+                        tma_load_2d(k_dst + t * kSubBytes, &map_qk, (p.n_heads + hk) * D + t * SUBK, row0 + j * BKEY, bar_kvf + 8 * s);
 #pragma unroll
-                for (int t = 0; t < 2; t++)
-                    tma_load_2d(v_dst + t * kVSub, &map_vt, j * BKEY + t * SUBK, (b * p.n_kv + hk) * D, bar_kvf + 8 * s);
+                    for (int t = 0; t < 2; t++)
+                        tma_load_2d(v_dst + t * kVSub, &map_vt, j * BKEY + t * SUBK, (b * p.n_kv + hk) * D, bar_kvf + 8 * s);
+                }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
+        // ------------------------------------------------------------------ MMA issuer: a flat stream of key blocks, S one block ahead of P V
         if (lane == 0) {
-            auto issue_s = [&](int j) {
-                const int s = j & 1;
-                mbar_wait(bar_kvf + 8 * s, (uint32_t)((j >> 1) & 1));
-                mbar_wait(bar_se + 8 * s, (uint32_t)((j >> 1) & 1) ^ 1u);   // softmax has drained this S slot
+            // "ahead" cursor (issues S) and "behind" cursor (issues P V) over the same item sequence
+            ItemIter ia = iter, ib = iter;
+            uint32_t it_a = 0, g_a = 0, it_b = 0, g_b = 0;
+            int ja = 0, nba = 0, jb = 0, nbb = 0;
+            bool a_open = false;                                   // cursor a positioned inside an item?
+            auto advance_a = [&]() -> bool {                        // issue S of the next block of the stream; false when the stream is exhausted
+                if (!a_open) {
+                    if (!ia.valid()) return false;
+                    int b, h, qb;
+                    ia.decode(b, h, qb, nba);
+                    ja = 0;
+                    a_open = true;
+                    mbar_wait(bar_qf + 8 * (it_a & 1u), (it_a >> 1) & 1u);
+                }
+                const uint32_t s = g_a & 1u, qbuf = it_a & 1u;
+                mbar_wait(bar_kvf + 8 * s, (g_a >> 1) & 1u);
+                mbar_wait(bar_se + 8 * s, ((g_a >> 1) & 1u) ^ 1u);  // softmax has drained this S slot
                 tc_fence_after();
-                const uint32_t k_addr = kv_s + s * kStageBytes;
+                const uint32_t k_addr = kv_s + s * kStageBytes, q_addr = q_s + qbuf * kQBytes;
 #pragma unroll
                 for (int k = 0; k < D / 16; k++) {
-                    const uint64_t ad = make_desc(q_s + (k / 4) * kSubBytes) + 2 * (k % 4);
+                    const uint64_t ad = make_desc(q_addr + (k / 4) * kSubBytes) + 2 * (k % 4);
                     const uint64_t bd = make_desc(k_addr + (k / 4) * kSubBytes) + 2 * (k % 4);
                     tc_mma(tmem_base + s * BKEY, ad, bd, idesc_n(BKEY), k ? 1u : 0u);
                 }
                 tc_commit(bar_sf + 8 * s);
-            };
-            mbar_wait(bar_q, 0);
-            issue_s(0);
-            for (int j = 0; j < n_blocks; j++) {
-                if (j + 1 < n_blocks) issue_s(j + 1);
-                const int s = j & 1;
-                mbar_wait(bar_pf, (uint32_t)(j & 1));                        // P_j in shared memory, O rescaled
-                tc_fence_after();
-                const uint32_t v_addr = kv_s + s * kStageBytes + kQBytes;
-#pragma unroll
-                for (int k = 0; k < BKEY / 16; k++) {
-                    const uint64_t ad = make_desc(p_s + (k / 4) * kSubBytes) + 2 * (k % 4);
-                    const uint64_t bd = make_desc(v_addr + (k / 4) * kVSub) + 2 * (k % 4);
-                    tc_mma(tmem_o, ad, bd, idesc_n(D), (j | k) ? 1u : 0u);
+                g_a++;
+                if (++ja == nba) {                                  // last S of the item: its Q buffer is free once these MMAs retire
+                    tc_commit(bar_qe + 8 * qbuf);
+                    a_open = false;
+                    ia.next();
+                    it_a++;
                 }
-                tc_commit(bar_kve + 8 * s);      // K_j / V_j stage free
-                tc_commit(bar_pfree);            // P buffer free, O updated
+                return true;
+            };
+            advance_a();
+            for (; ib.valid(); ib.next(), it_b++) {
+                int b, h, qb;
+                ib.decode(b, h, qb, nbb);
+                const uint32_t obuf = it_b & 1u;
+                const uint32_t tmem_o = tmem_base + 256 + obuf * 128;
+                for (jb = 0; jb < nbb; jb++, g_b++) {
+                    advance_a();                                    // S of block g_b + 1 (possibly the next item's first block)
+                    const uint32_t s = g_b & 1u;
+                    mbar_wait(bar_pf, g_b & 1u);                    // P ready in shared memory, O rescaled
+                    if (jb == 0) mbar_wait(bar_oe + 8 * obuf, ((it_b >> 1) & 1u) ^ 1u);   // epilogue of item it_b - 2 has read this O buffer
+                    tc_fence_after();
+                    const uint32_t v_addr = kv_s + s * kStageBytes + kQBytes;
+#pragma unroll
+                    for (int k = 0; k < BKEY / 16; k++) {
+                        const uint64_t ad = make_desc(p_s + (k / 4) * kSubBytes) + 2 * (k % 4);
+                        const uint64_t bd = make_desc(v_addr + (k / 4) * kVSub) + 2 * (k % 4);
+                        tc_mma(tmem_o, ad, bd, idesc_n(D), (jb | k) ? 1u : 0u);
+                    }
+                    tc_commit(bar_kve + 8 * s);      // K / V stage free
+                    tc_commit(bar_pfree);            // P buffer free, O updated
+                }
             }
         }
     } else {
@@ -231,109 +295,114 @@ attn_core_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_consta
         const uint32_t quad = (uint32_t)warp & 3u;
         const int row = (int)quad * 32 + lane;               // row inside the query block == TMEM lane
         const uint32_t t_lane = (quad * 32u) << 16;
-        const int q_idx = q0 + row;
-        float m = -INFINITY, l = 0.0f;
         const uint32_t p_row = p_s + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
-        for (int j = 0; j < n_blocks; j++) {
-            const int s = j & 1;
-            const uint32_t t_s = tmem_base + t_lane + s * BKEY;
-            const int key0 = j * BKEY;
-            const bool diag = key0 + BKEY - 1 > q0;           // block touches the causal boundary (or the sequence end)
-            mbar_wait(bar_sf + 8 * s, (uint32_t)((j >> 1) & 1));
-            tc_fence_after();
-            // ---- pass 1: row max of the scaled, masked scores
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < BKEY / 32; c++) {
-                uint32_t v[32];
-                tc_ld32(t_s + c * 32, v);
-#pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const int key = key0 + c * 32 + i;
-                    float x = __uint_as_float(v[i]) * p.scale_log2e;
-                    if (diag && (key > q_idx || key >= p.seq_len)) x = -INFINITY;
-                    mx = fmaxf(mx, x);
-                }
-            }
-            const float m_new = fmaxf(m, mx);
-            const float m_use = m_new == -INFINITY ? 0.0f : m_new;   // fully masked row (query beyond the sequence): keep exp2 finite
-            const float alpha = ex2(m - m_use);                       // m = -inf on the first block -> 0
-            // ---- O rescale (needs O += P_{j-1} V_{j-1} retired) and the P buffer free
-            if (j > 0) {
-                mbar_wait(bar_pfree, (uint32_t)((j - 1) & 1));
+        uint32_t it = 0, g = 0;
+        for (; iter.valid(); iter.next(), it++) {
+            int b, h, qb, n_blocks;
+            iter.decode(b, h, qb, n_blocks);
+            const int q0 = qb * BQ, q_idx = q0 + row, row0 = b * p.seq_len;
+            const uint32_t obuf = it & 1u;
+            const uint32_t tmem_o = tmem_base + 256 + obuf * 128;
+            float m = -INFINITY, l = 0.0f;
+            for (int j = 0; j < n_blocks; j++, g++) {
+                const uint32_t s = g & 1u;
+                const uint32_t t_s = tmem_base + t_lane + s * BKEY;
+                const int key0 = j * BKEY;
+                const bool diag = key0 + BKEY - 1 > q0;           // block touches the causal boundary (or the sequence end)
+                mbar_wait(bar_sf + 8 * s, (g >> 1) & 1u);
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-                    for (int c = 0; c < D / 32; c++) {
-                        uint32_t o[32];
-                        tc_ld32(tmem_o + t_lane + c * 32, o);
+                // ---- the whole score row in registers: four x32 TMEM loads in flight, one wait
+                uint32_t sv[BKEY];
 #pragma unroll
-                        for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tc_st32(tmem_o + t_lane + c * 32, o);
+                for (int c = 0; c < BKEY / 32; c++) tc_ld32_nowait(t_s + c * 32, sv + c * 32);
+                tc_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_se + 8 * s);       // S slot drained: the MMA warp may overwrite it with block g + 2
+                // four independent max / sum chains: one softmax warp per scheduler has no other warp to hide a 128-long dependent chain
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                for (int i = 0; i < BKEY; i++) {
+                    float x = __uint_as_float(sv[i]) * p.scale_log2e;
+                    if (diag && (key0 + i > q_idx || key0 + i >= p.seq_len)) x = -INFINITY;
+                    sv[i] = __float_as_uint(x);
+                    mx4[i & 3] = fmaxf(mx4[i & 3], x);
+                }
+                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+                // Lazy running maximum: the reference point only moves when the row maximum grew by more than 2^8 (exp2 of anything
+                // below m + 8 is < 256: no overflow in fp32 or bf16, and the normalisation by l cancels the offset exactly), so the O
+                // accumulator in TMEM is almost never rescaled after the first block
+                float m_new = m;
+                if (mx > m + 8.0f) m_new = mx;
+                const float m_use = m_new == -INFINITY ? 0.0f : m_new;   // fully masked row (query beyond the sequence): keep exp2 finite
+                const float alpha = ex2(m - m_use);                       // m = -inf on the first block -> 0; unchanged reference -> 1
+                // ---- O rescale (needs O += P V of the previous block retired) and the P buffer free
+                if (j > 0) {
+                    mbar_wait(bar_pfree, (g - 1) & 1u);
+                    tc_fence_after();
+                    if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+                        for (int c = 0; c < D / 32; c++) {
+                            uint32_t o[32];
+                            tc_ld32(tmem_o + t_lane + c * 32, o);
+#pragma unroll
+                            for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tc_st32(tmem_o + t_lane + c * 32, o);
+                        }
                     }
                 }
-            }
-            // ---- pass 2: probabilities -> bf16 A tile (SWIZZLE_128B, K-major over the keys), row sum
-            float sum = 0.0f;
-#pragma unroll 1
-            for (int c = 0; c < BKEY / 32; c++) {
-                uint32_t v[32];
-                tc_ld32(t_s + c * 32, v);
-                uint32_t pk[16];
+                // ---- probabilities -> bf16 A tile (SWIZZLE_128B, K-major over the keys), row sum
+                float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    float e[2];
+                for (int c = 0; c < BKEY / 32; c++) {
+                    uint32_t pk[16];
 #pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const int key = key0 + c * 32 + 2 * i + u;
-                        float x = __uint_as_float(v[2 * i + u]) * p.scale_log2e - m_use;
-                        if (diag && (key > q_idx || key >= p.seq_len)) x = -INFINITY;
-                        e[u] = ex2(x);
+                    for (int i = 0; i < 16; i++) {
+                        const float e0 = ex2(__uint_as_float(sv[c * 32 + 2 * i]) - m_use), e1 = ex2(__uint_as_float(sv[c * 32 + 2 * i + 1]) - m_use);
+                        pk[i] = cvt_bf16x2(e1, e0);
+                        // the row sum uses the ROUNDED probabilities, so that O / l normalises exactly what P V accumulated
+                        sum4[(2 * i) & 3] += __uint_as_float(pk[i] << 16);
+                        sum4[(2 * i + 1) & 3] += __uint_as_float(pk[i] & 0xffff0000u);
                     }
-                    pk[i] = cvt_bf16x2(e[1], e[0]);
-                    // the row sum uses the ROUNDED probabilities, so that O / l normalises exactly what P V accumulated
-                    sum += __uint_as_float(pk[i] << 16) + __uint_as_float(pk[i] & 0xffff0000u);
-                }
-                // 32 keys = 4 chunks of 16 bytes; chunk index inside the 64-key sub-tile, XOR-swizzled with the row
-                const uint32_t sub = (uint32_t)(c >> 1) * kSubBytes;
+                    // 32 keys = 4 chunks of 16 bytes; chunk index inside the 64-key sub-tile, XOR-swizzled with the row
+                    const uint32_t sub = (uint32_t)(c >> 1) * kSubBytes;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t chunk = (uint32_t)((c & 1) * 4 + q);
-                    const uint32_t addr = p_row + sub + ((chunk ^ (uint32_t)(row & 7)) << 4);
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t chunk = (uint32_t)((c & 1) * 4 + q);
+                        const uint32_t addr = p_row + sub + ((chunk ^ (uint32_t)(row & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                    }
                 }
+                l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+                m = m_new;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy P stores -> visible to the tensor core's async proxy
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_pf);   // P ready, O rescaled
             }
-            l = l * alpha + sum;
-            m = m_new;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy P stores -> visible to the tensor core's async proxy
+            // ---- epilogue: O / l -> bf16 (the MMA warp is already on the next item's S)
+            mbar_wait(bar_pfree, (g - 1) & 1u);
+            tc_fence_after();
+            const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+            uint16_t* orow = p.out + ((int64_t)(row0 + q_idx) * p.n_heads + h) * D;
+            uint32_t ov[D];
+#pragma unroll
+            for (int c = 0; c < D / 32; c++) tc_ld32_nowait(tmem_o + t_lane + c * 32, ov + c * 32);
+            tc_wait_ld();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(bar_se + 8 * s);     // S slot drained
-                mbar_arrive(bar_pf);             // P_j ready, O rescaled
-            }
-        }
-        // ---- epilogue: O / l -> bf16
-        mbar_wait(bar_pfree, (uint32_t)((n_blocks - 1) & 1));
-        tc_fence_after();
-        const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-        uint16_t* orow = p.out + ((int64_t)(row0 + q_idx) * p.n_heads + h) * D;
-#pragma unroll 1
-        for (int c = 0; c < D / 32; c++) {
-            uint32_t o[32];
-            tc_ld32(tmem_o + t_lane + c * 32, o);
+            if (lane == 0) mbar_arrive(bar_oe + 8 * obuf);      // this O buffer may be overwritten by item it + 2
             if (q_idx < p.seq_len) {
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
+                for (int q = 0; q < D / 8; q++) {
                     uint32_t w[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++)
-                        w[i] = cvt_bf16x2(__uint_as_float(o[8 * q + 2 * i + 1]) * inv, __uint_as_float(o[8 * q + 2 * i]) * inv);
-                    *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                        w[i] = cvt_bf16x2(__uint_as_float(ov[8 * q + 2 * i + 1]) * inv, __uint_as_float(ov[8 * q + 2 * i]) * inv);
+                    *reinterpret_cast<uint4*>(orow + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
         }
-        tc_fence_before();
     }
     tc_fence_before();
     __syncthreads();
@@ -368,9 +437,10 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64
 
 template <int D>
 int launch_attn(const CUtensorMap& mqk, const CUtensorMap& mvt, const AttnParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)(D / SUBK) * kSubBytes + 2 * ((size_t)(D / SUBK) * kSubBytes + 2 * (D * SUBK * 2)) + 2 * kSubBytes + 128 + 1024;
+    // 2 Q buffers + 2 x (K + V^T) stages + P + barriers / TMEM slot + 1 KB alignment slack: 225.25 KB for d = 128 (limit 227 KB)
+    constexpr size_t smem = 2 * (size_t)(D / SUBK) * kSubBytes + 2 * ((size_t)(D / SUBK) * kSubBytes + 2 * (D * SUBK * 2)) + 2 * kSubBytes + 256 + 1024;
     cudaFuncSetAttribute(attn_core_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int64_t grid = (int64_t)p.samples * p.n_heads * p.q_blocks;
+    const int64_t grid = min((int64_t)p.samples * p.n_heads * p.q_blocks, (int64_t)kNumSMs);
     attn_core_kernel<D><<<(unsigned)grid, kThreads, smem, st>>>(mqk, mvt, p);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;

@@ -493,7 +493,8 @@ __global__ void zp_pack_rows_kernel(const int8_t* __restrict__ zp, int64_t batch
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 if (j < nr) {
-                    const uint32_t v = ((*reinterpret_cast<const uint32_t*>(src + (int64_t)j * gpr)) + 0x08080808u) & 0x0f0f0f0fu;  // zp + 8 per byte (zp in [-8, 7])
+                    // (zp + 8) & 0xf per byte without carries between the bytes: zp in [-8, 7], so its low nibble XOR 8 is zp + 8
+                    const uint32_t v = ((*reinterpret_cast<const uint32_t*>(src + (int64_t)j * gpr)) & 0x0f0f0f0fu) ^ 0x08080808u;
                     w0 |= (v & 0xffu) << (4 * j);
                     w1 |= ((v >> 8) & 0xffu) << (4 * j);
                     w2 |= ((v >> 16) & 0xffu) << (4 * j);
