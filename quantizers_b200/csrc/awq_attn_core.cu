@@ -17,6 +17,7 @@
 //                              the row max grew by > 2^8, so O in TMEM is almost never rescaled: tcgen05.ld / st only then),
 //                              exp2 -> row sum, P as bf16 into the SWIZZLE_128B A tile in shared memory; epilogue O / l -> bf16.
 // fp32 scores, fp32 softmax statistics, bf16 probabilities, fp32 accumulation -- the arithmetic of a flash-attention forward.
+#include <cstdlib>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include "../../include/b200q.h"
@@ -36,6 +37,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+// (a spin on mbarrier.test_wait instead of try_wait was measured: no difference, 440 vs 427 us)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -114,6 +116,7 @@ struct AttnParams {
     int32_t n_heads, n_kv, seq_len, q_blocks;   // q_blocks = ceil(seq_len / 128)
     int32_t samples;
     float scale_log2e;                          // softmax scale * log2(e)
+    float lazy_raw;                             // 8 / scale_log2e: the lazy-maximum head-room (2^8) in raw score units
     uint16_t* out;                              // bf16 [T, n_heads * D]
 };
 
@@ -412,6 +415,267 @@ attn_core_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------------ attention core, two streams per SM
+// The persistent kernel above runs ONE softmax warpgroup per SM: every barrier hop of its chain (TMEM load, P store + proxy fence,
+// MMA issue, commit) is exposed -- ncu: issue slots 34 % busy, tensor pipe 19 %, 455 us per call vs cuDNN's 216 us.  This variant puts
+// TWO independent copies of that pipeline on an SM (producer warp + MMA warp + 4 softmax warps each, 12 warps), each walking its own
+// item stream with its own Q / K / V^T / P buffers, S slots and O accumulator, with 64-key blocks so that both fit: per stream
+// Q 32 KB + 2 x (K 16 KB + V^T 16 KB) + P 16 KB = 112 KB of shared memory and S 2 x 64 + O 128 = 256 TMEM columns.  While one
+// stream waits on a hop the other computes; tcgen05.mma / commit are issued by one thread per stream on disjoint accumulators.
+constexpr int BK2 = 64;
+constexpr int kThreads2 = 384;
+
+template <int D>
+__global__ void __launch_bounds__(kThreads2, 1)
+attn_core2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_vt,
+                  const AttnParams p) {
+    constexpr int NSUB = D / SUBK;
+    constexpr int kQBytes = NSUB * kSubBytes;               // Q tile [128 x D]
+    constexpr int kKSub = BK2 * SUBK * 2;                   // K sub-tile [64 keys x 64] = 8 KB
+    constexpr int kKBytes = NSUB * kKSub;                   // K tile [64 keys x D]
+    constexpr int kVBytes = D * SUBK * 2;                   // V^T tile [D x 64 keys]
+    constexpr int kPBytes = kSubBytes;                      // P tile [128 x 64 keys]
+    constexpr int kStageBytes = kKBytes + kVBytes;
+    constexpr int kStreamBytes = kQBytes + 2 * kStageBytes + kPBytes;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = warp / 6, role = warp - 6 * w;            // stream, role inside the stream (0 producer, 1 MMA, 2..5 softmax)
+    const uint32_t base = smem_u32(smem) + (uint32_t)w * kStreamBytes;
+    const uint32_t q_s = base, kv_s = base + kQBytes, p_s = kv_s + 2 * kStageBytes;
+    const uint32_t bars = smem_u32(smem) + 2 * kStreamBytes + (uint32_t)w * 128;
+    // per stream: q_full, q_empty, kv_full[2], kv_empty[2], s_full[2], s_empty[2], o_empty, p_full, p_free
+    const uint32_t bar_qf = bars, bar_qe = bars + 8, bar_kvf = bars + 16, bar_kve = bars + 32, bar_sf = bars + 48, bar_se = bars + 64,
+                   bar_oe = bars + 80, bar_pf = bars + 88, bar_pfree = bars + 96;
+    uint32_t* tmem_slot = (uint32_t*)(smem + 2 * kStreamBytes + 256);
+
+    if (lane == 0 && role == 0) {
+        mbar_init(bar_qf, 1); mbar_init(bar_qe, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(bar_kvf + 8 * s, 1); mbar_init(bar_kve + 8 * s, 1); mbar_init(bar_sf + 8 * s, 1); mbar_init(bar_se + 8 * s, 4); }
+        mbar_init(bar_oe, 4); mbar_init(bar_pf, 4); mbar_init(bar_pfree, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot + (uint32_t)w * 256;   // this stream's 256 columns: S slots [0, 64) / [64, 128), O [128, 128 + D)
+    const uint32_t tmem_o = tmem_base + 128;
+
+    ItemIter iter;
+    iter.t = 2 * (int)blockIdx.x + w; iter.stride = 2 * (int)gridDim.x;
+    iter.heads_total = p.samples * p.n_heads; iter.end = iter.heads_total * p.q_blocks;
+    iter.q_blocks = p.q_blocks; iter.n_heads = p.n_heads; iter.n_kv = p.n_kv; iter.seq_len = p.seq_len;
+    const int kv_rep = p.n_heads / p.n_kv;
+    const int key_blocks_total = (p.seq_len + BK2 - 1) / BK2;
+    auto blocks_of = [&](int qb) { return min(2 * (qb + 1), key_blocks_total); };   // 64-key blocks up to the end of the 128-query block
+
+    if (role == 0) {
+        // ------------------------------------------------------------------ TMA producer of this stream
+        if (lane == 0) {
+            uint32_t it = 0, g = 0;
+            for (; iter.valid(); iter.next(), it++) {
+                int b, h, qb, nb_unused;
+                iter.decode(b, h, qb, nb_unused);
+                const int nb = blocks_of(qb);
+                const int hk = h / kv_rep, row0 = b * p.seq_len;
+                mbar_wait(bar_qe, (it & 1u) ^ 1u);                            // the S MMAs of the previous item have retired
+                mbar_arrive_expect_tx(bar_qf, kQBytes);
+#pragma unroll
+                for (int t = 0; t < NSUB; t++) tma_load_2d(q_s + t * kSubBytes, &map_q, h * D + t * SUBK, row0 + qb * BQ, bar_qf);
+                for (int j = 0; j < nb; j++, g++) {
+                    const uint32_t s = g & 1u;
+                    mbar_wait(bar_kve + 8 * s, ((g >> 1) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(bar_kvf + 8 * s, kStageBytes);
+                    const uint32_t k_dst = kv_s + s * kStageBytes, v_dst = k_dst + kKBytes;
+#pragma unroll
+                    for (int t = 0; t < NSUB; t++)
+                        tma_load_2d(k_dst + t * kKSub, &map_k, (p.n_heads + hk) * D + t * SUBK, row0 + j * BK2, bar_kvf + 8 * s);
+                    tma_load_2d(v_dst, &map_vt, j * BK2, (b * p.n_kv + hk) * D, bar_kvf + 8 * s);
+                }
+            }
+        }
+    } else if (role == 1) {
+        // ------------------------------------------------------------------ MMA issuer of this stream
+        if (lane == 0) {
+            ItemIter ia = iter, ib = iter;
+            uint32_t it_a = 0, g_a = 0, it_b = 0, g_b = 0;
+            int ja = 0, nba = 0;
+            bool a_open = false;
+            auto advance_a = [&]() -> bool {
+                if (!a_open) {
+                    if (!ia.valid()) return false;
+                    int b, h, qb, nb_unused;
+                    ia.decode(b, h, qb, nb_unused);
+                    nba = blocks_of(qb);
+                    ja = 0;
+                    a_open = true;
+                    mbar_wait(bar_qf, it_a & 1u);
+                }
+                const uint32_t s = g_a & 1u;
+                mbar_wait(bar_kvf + 8 * s, (g_a >> 1) & 1u);
+                mbar_wait(bar_se + 8 * s, ((g_a >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t k_addr = kv_s + s * kStageBytes;
+#pragma unroll
+                for (int k = 0; k < D / 16; k++) {
+                    const uint64_t ad = make_desc(q_s + (k / 4) * kSubBytes) + 2 * (k % 4);
+                    const uint64_t bd = make_desc(k_addr + (k / 4) * kKSub) + 2 * (k % 4);
+                    tc_mma(tmem_base + s * BK2, ad, bd, idesc_n(BK2), k ? 1u : 0u);
+                }
+                tc_commit(bar_sf + 8 * s);
+                g_a++;
+                if (++ja == nba) {
+                    tc_commit(bar_qe);
+                    a_open = false;
+                    ia.next();
+                    it_a++;
+                }
+                return true;
+            };
+            advance_a();
+            for (; ib.valid(); ib.next(), it_b++) {
+                int b, h, qb, nb_unused;
+                ib.decode(b, h, qb, nb_unused);
+                const int nbb = blocks_of(qb);
+                for (int jb = 0; jb < nbb; jb++, g_b++) {
+                    // exactly ONE block of look-ahead: S of block g_b + 1 (the next item's first block at an item boundary) before
+                    // P V of block g_b.  More would need the ring stage that block g_b still holds (its P V frees it) -- a
+                    // two-block look-ahead at item boundaries dead-locked the first version of this kernel on multi-item streams.
+                    advance_a();
+                    const uint32_t s = g_b & 1u;
+                    mbar_wait(bar_pf, g_b & 1u);
+                    if (jb == 0) mbar_wait(bar_oe, (it_b & 1u) ^ 1u);   // the previous item's epilogue has read O
+                    tc_fence_after();
+                    const uint32_t v_addr = kv_s + s * kStageBytes + kKBytes;
+#pragma unroll
+                    for (int k = 0; k < BK2 / 16; k++)
+                        tc_mma(tmem_o, make_desc(p_s) + 2 * k, make_desc(v_addr) + 2 * k, idesc_n(D), (jb | k) ? 1u : 0u);
+                    tc_commit(bar_kve + 8 * s);
+                    tc_commit(bar_pfree);
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax + epilogue of this stream: one query row per thread
+        const uint32_t quad = (uint32_t)warp & 3u;
+        const int row = (int)quad * 32 + lane;
+        const uint32_t t_lane = (quad * 32u) << 16;
+        const uint32_t p_row = p_s + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+        uint32_t it = 0, g = 0;
+        for (; iter.valid(); iter.next(), it++) {
+            int b, h, qb, nb_unused;
+            iter.decode(b, h, qb, nb_unused);
+            const int n_blocks = blocks_of(qb);
+            const int q0 = qb * BQ, q_idx = q0 + row, row0 = b * p.seq_len;
+            float m = -INFINITY, l = 0.0f;
+            for (int j = 0; j < n_blocks; j++, g++) {
+                const uint32_t s = g & 1u;
+                const uint32_t t_s = tmem_base + t_lane + s * BK2;
+                const int key0 = j * BK2;
+                const bool diag = key0 + BK2 - 1 > q0;
+                mbar_wait(bar_sf + 8 * s, (g >> 1) & 1u);
+                tc_fence_after();
+                uint32_t sv[BK2];
+                tc_ld32_nowait(t_s, sv);
+                tc_ld32_nowait(t_s + 32, sv + 32);
+                tc_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_se + 8 * s);
+                // Lean softmax (ncu on the first version: ~14 issued instructions per score; one softmax warp per scheduler and
+                // stream cannot afford that): the maximum is taken on the RAW scores (the scale is positive), the scale and the
+                // reference point fold into one FFMA in front of ex2, the causal / tail mask only runs on the blocks that need it,
+                // and the row sum adds the fp32 probabilities (4 chains): max + FFMA + MUFU + 1/2 cvt + add = 4.5 per score.
+                if (diag) {
+#pragma unroll
+                    for (int i = 0; i < BK2; i++)
+                        if (key0 + i > q_idx || key0 + i >= p.seq_len) sv[i] = 0xff800000u;   // -inf
+                }
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                for (int i = 0; i < BK2; i++) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[i]));
+                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));   // raw score units
+                float m_new = m;
+                if (mx > m + p.lazy_raw) m_new = mx;                   // lazy running maximum: 2^8 of head-room (see attn_core_kernel)
+                const float mc = (m_new == -INFINITY ? 0.0f : m_new) * p.scale_log2e;
+                const float alpha = ex2(m * p.scale_log2e - mc);       // m = -inf on the first block -> 0; unchanged reference -> 1
+                if (j > 0) {
+                    mbar_wait(bar_pfree, (g - 1) & 1u);
+                    tc_fence_after();
+                    if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+                        for (int c = 0; c < D / 32; c++) {
+                            uint32_t o[32];
+                            tc_ld32(tmem_o + t_lane + c * 32, o);
+#pragma unroll
+                            for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tc_st32(tmem_o + t_lane + c * 32, o);
+                        }
+                    }
+                }
+                float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                uint32_t pk[BK2 / 2];
+#pragma unroll
+                for (int i = 0; i < BK2 / 2; i++) {
+                    const float e0 = ex2(fmaf(__uint_as_float(sv[2 * i]), p.scale_log2e, -mc));
+                    const float e1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), p.scale_log2e, -mc));
+                    pk[i] = cvt_bf16x2(e1, e0);
+                    sum4[(2 * i) & 3] += e0;
+                    sum4[(2 * i + 1) & 3] += e1;
+                }
+#pragma unroll
+                for (int q = 0; q < BK2 / 8; q++) {                    // 8 chunks of 16 bytes, XOR-swizzled with the row
+                    const uint32_t addr = p_row + (((uint32_t)q ^ (uint32_t)(row & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                }
+                l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+                m = m_new;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_pf);
+            }
+            // ---- epilogue: O / l -> bf16, in two halves (register budget of a 12-warp CTA)
+            mbar_wait(bar_pfree, (g - 1) & 1u);
+            tc_fence_after();
+            const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+            uint16_t* orow = p.out + ((int64_t)(row0 + q_idx) * p.n_heads + h) * D;
+#pragma unroll
+            for (int hf = 0; hf < D / 64; hf++) {
+                uint32_t ov[64];
+                tc_ld32_nowait(tmem_o + t_lane + hf * 64, ov);
+                tc_ld32_nowait(tmem_o + t_lane + hf * 64 + 32, ov + 32);
+                tc_wait_ld();
+                if (hf == D / 64 - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_oe);               // O may be overwritten by the next item
+                }
+                if (q_idx < p.seq_len) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        uint32_t wv[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            wv[i] = cvt_bf16x2(__uint_as_float(ov[8 * q + 2 * i + 1]) * inv, __uint_as_float(ov[8 * q + 2 * i]) * inv);
+                        *reinterpret_cast<uint4*>(orow + hf * 64 + q * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
+    }
+}
+
 PFN_cuTensorMapEncodeTiled get_encode() {
     static PFN_cuTensorMapEncodeTiled fn = nullptr;
     if (!fn) {
@@ -442,6 +706,18 @@ int launch_attn(const CUtensorMap& mqk, const CUtensorMap& mvt, const AttnParams
     cudaFuncSetAttribute(attn_core_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t grid = min((int64_t)p.samples * p.n_heads * p.q_blocks, (int64_t)kNumSMs);
     attn_core_kernel<D><<<(unsigned)grid, kThreads, smem, st>>>(mqk, mvt, p);
+    B200Q_CHECK_LAUNCH();
+    return B200Q_OK;
+}
+
+template <int D>
+int launch_attn2(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mvt, const AttnParams& p, cudaStream_t st) {
+    constexpr size_t stream = (size_t)(D / SUBK) * kSubBytes + 2 * ((size_t)(D / SUBK) * (BK2 * SUBK * 2) + (size_t)D * SUBK * 2) + kSubBytes;
+    constexpr size_t smem = 2 * stream + 512 + 1024;
+    cudaFuncSetAttribute(attn_core2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t items = (int64_t)p.samples * p.n_heads * p.q_blocks;
+    const int64_t grid = min((items + 1) / 2, (int64_t)kNumSMs);
+    attn_core2_kernel<D><<<(unsigned)grid, kThreads2, smem, st>>>(mq, mk, mvt, p);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }
@@ -480,14 +756,19 @@ int b200q_attention_core(const void* qkv, int64_t tokens, int32_t n_heads, int32
                                                               n_kv, (uint16_t*)workspace);
         B200Q_CHECK_LAUNCH();
     }
-    CUtensorMap mqk, mvt;
+    CUtensorMap mqk, mk64, mvt;
     if (int rc = make_map(&mqk, qkv, tokens, row_elems, row_elems, 128)) return rc;
+    if (int rc = make_map(&mk64, qkv, tokens, row_elems, row_elems, BK2)) return rc;
     if (int rc = make_map(&mvt, workspace, (int64_t)samples * n_kv * head_dim, s_pad, s_pad, head_dim)) return rc;
     AttnParams p;
     p.n_heads = n_heads; p.n_kv = n_kv; p.seq_len = seq_len; p.q_blocks = (seq_len + BQ - 1) / BQ; p.samples = samples;
     p.scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
+    p.lazy_raw = 8.0f / p.scale_log2e;
     p.out = (uint16_t*)out;
-    return head_dim == 128 ? launch_attn<128>(mqk, mvt, p, st) : launch_attn<64>(mqk, mvt, p, st);
+    // default: two pipelines per SM on 64-key blocks; B200Q_ATTN_ONE_STREAM=1 selects the single-stream kernel (128-key blocks) for A/B
+    static const bool one_stream = getenv("B200Q_ATTN_ONE_STREAM") != nullptr;
+    if (one_stream) return head_dim == 128 ? launch_attn<128>(mqk, mvt, p, st) : launch_attn<64>(mqk, mvt, p, st);
+    return head_dim == 128 ? launch_attn2<128>(mqk, mk64, mvt, p, st) : launch_attn2<64>(mqk, mk64, mvt, p, st);
 }
 
 }  // extern "C"

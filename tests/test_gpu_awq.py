@@ -392,7 +392,8 @@ def test_scaled_fake_quantize_grid_fast_kernel_bit_exact(name, geom, sym):
         assert_bits_equal(one, R.scaled_fake_quantize(w, scales[4], geom, O.INT, 4, sym), f"{name} single")
 
 
-@pytest.mark.parametrize("H,HKV,D,S,B", [(32, 8, 128, 512, 2), (4, 2, 64, 64, 3), (5, 1, 128, 70, 1), (8, 8, 128, 300, 2), (6, 3, 64, 257, 2)])
+@pytest.mark.parametrize("H,HKV,D,S,B", [(32, 8, 128, 512, 2), (4, 2, 64, 64, 3), (5, 1, 128, 70, 1), (8, 8, 128, 300, 2), (6, 3, 64, 257, 2),
+                                         (32, 8, 128, 512, 12), (16, 4, 64, 384, 24)])   # the last two: several items per persistent stream
 def test_attention_core_tcgen05_vs_reference(H, HKV, D, S, B):
     """csrc/awq_attn_core.cu (causal GQA attention of every sample on tcgen05: fp32 scores / statistics, bf16 probabilities, fp32
     accumulation) against an fp32 reference of the same batch-1 causal attention and against torch SDPA: within bf16 output
