@@ -16,6 +16,8 @@ namespace b200q {
 namespace {
 using namespace fast;
 using namespace fp4;
+using async::lds128;
+using async::smem_u32;
 
 // ------------------------------------------------------------------------------------------------ FP8 block
 constexpr int NC = 8;
@@ -367,7 +369,12 @@ struct Fp4FusedParams {
     uint32_t* sync;
     float* gs_out;  // [batch]
     uint16_t* loc;  // optional scratch, bf16 bits of T(group |max| / 6) for every group [batch * groups_per_mat] (written by the |max| pass)
+    // n / d for n < 2^31 as (n * magic) >> shift (Granlund-Montgomery, 31-bit dividends: the magic fits 32 bits): the CTA-index decode
+    // runs in every thread of every CTA, and three hardware-emulated divisions were ~0.5 instructions per weight
+    uint32_t nblk_magic, nblk_shift, ipm_magic, ipm_shift;
+    int32_t force_fallback;  // tests: every compress CTA reduces its span itself (B200Q_FP4_FORCE_FALLBACK=1)
 };
+__device__ __forceinline__ uint32_t fastdiv31(uint32_t n, uint32_t magic, uint32_t shift) { return (uint32_t)(((uint64_t)n * magic) >> shift); }
 
 // |max| bits of tiles [tile0, tile1) of one matrix, reduced over the CTA (valid in thread 0)
 __device__ __forceinline__ uint32_t fp4_absmax_tiles(const uint4* wbase, int tile0, int tile1, int64_t groups_per_mat, uint32_t* s_red,
@@ -480,6 +487,274 @@ __global__ void __launch_bounds__(FP4_THREADS, 6) nvfp4_fused_kernel(const Group
 }
 
 
+// ------------------------------------------------------------------------------------------------ fused kernel, round-2 diet
+// ncu on nvfp4_fused_kernel (profiles/r2_ncu_kernels.txt): 16 issued instructions per weight at 66 % issue utilisation, of which
+// only ~3 are the conversion itself (unpack, two FFMA2 bracket ends, two F2FP per element pair).  The rest was bookkeeping:
+// 64-bit group indices and bounds tests per group, spilled base pointers (40-register cap), a run-time "scratch?" branch, the
+// bracketed /6 with its range test, a clamp the saturating conversion already performs.  This version keeps the math and drops
+// the bookkeeping: per-thread pointers advanced by a constant per tile, one 32-bit "groups left" counter, T(absmax / 6) as a
+// single multiply (exhaustively exact over all 32 641 non-negative bf16 values, tests/test_exact_reciprocal.py), no clamp.
+__device__ __forceinline__ float fp4_loc_scale1(uint32_t abits) {
+    return __uint_as_float(cvt_bf16x2(0.0f, __fmul_rn(__uint_as_float(abits), 1.0f / 6.0f)) << 16);
+}
+
+template <bool KEEP>
+__device__ __forceinline__ void fp4_load2(uint4 (&raw)[FP4_UF][2], const uint4* wp, int rem, uint64_t policy = 0) {
+#pragma unroll
+    for (int u = 0; u < FP4_UF; u++) {
+        if (u * FP4_THREADS < rem) {
+            raw[u][0] = KEEP ? ldg_keep(wp + 2 * u * FP4_THREADS, policy) : ldg_stream(wp + 2 * u * FP4_THREADS);
+            raw[u][1] = KEEP ? ldg_keep(wp + 2 * u * FP4_THREADS + 1, policy) : ldg_stream(wp + 2 * u * FP4_THREADS + 1);
+        } else {
+            raw[u][0] = raw[u][1] = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+// lean table for the fused kernel: the hot path fetches 8 bytes {r_lo, r_hi}; the repair path re-reads s_eff by code.  An entry whose
+// scale is outside the fast range gets the bracket (0, +inf): the two ends then differ for every input (0 vs +-6; NaN for a
+// zero), so the ordinary "ends differ" test routes the whole group to the exact chain and the hot loop carries no extra flag.
+struct Fp4Lean { float2 r[128]; float s_eff[128]; };
+__device__ __forceinline__ void fp4_build_lean(Fp4Lean* t, float gs) {
+    if (threadIdx.x < 128) {
+        const uint32_t code = threadIdx.x == 0 ? 0x20u : threadIdx.x;       // see fp4_build_table
+        const float s_eff = fdiv(e4m3_decode((uint8_t)code), gs);
+        const float r = rcp_approx(s_eff);
+        const bool safe = fp4_scale_is_safe(s_eff);
+        t->r[threadIdx.x] = make_float2(safe ? __fmul_rn(r, 0.99999952316284179688f) : 0.0f,
+                                        safe ? __fmul_rn(r, 1.00000047683715820312f) : __uint_as_float(0x7f800000u));
+        t->s_eff[threadIdx.x] = s_eff;
+    }
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t cvt_e4m3_code(float sf) {   // e4m3 code of a non-negative scale, zero-extended
+    uint32_t r;
+    asm("{ .reg .b16 t; cvt.rn.satfinite.e4m3x2.f32 t, %1, %2; cvt.u32.u16 %0, t; }" : "=r"(r) : "f"(0.0f), "f"(sf));
+    return r;
+}
+// repair path of one 16-element group (both halves): s_eff is re-read from the table by entry address
+static __device__ __noinline__ uint2 fix_group16_fp4(const uint4 a, const uint4 b, uint32_t table_smem, uint32_t code, uint2 packed) {
+    const float s_eff = lds_f1(table_smem + 1024 + 4 * code);
+    packed.x = fix_group_fp4(a, s_eff, packed.x);
+    packed.y = fix_group_fp4(b, s_eff, packed.y);
+    return packed;
+}
+
+// one 16-element group (two 128-bit words of bf16): scale code + packed e2m1 out
+template <bool FMA>
+__device__ __forceinline__ void fp4_compress_group(const uint4 r0, const uint4 r1, uint32_t table_smem, float gs, uint8_t* sp, uint2* op) {
+    uint32_t m = hmaxabs2(hmaxabs2(hmaxabs2(r0.x, r0.y), hmaxabs2(r0.z, r0.w)), hmaxabs2(hmaxabs2(r1.x, r1.y), hmaxabs2(r1.z, r1.w)));
+    m = hmaxabs2(m, prmt(m, m, 0x1032));
+    // T(absmax / 6): one multiply (fp4_loc_scale1); |.| is an operand modifier, the bf16 result lands in the high half
+    const float loc = __uint_as_float(cvt_bf16x2(__fmul_rn(fabsf(__uint_as_float(m << 16)), 1.0f / 6.0f), 0.0f));
+    // satfinite is the reference's clamp to +-448 (the product is non-negative)
+    const uint32_t code = cvt_e4m3_code(__fmul_rn(gs, loc));
+    const float2 rr = lds_f2(table_smem + 8 * code);
+    *sp = (uint8_t)(code == 0 ? 0x20u : code);
+    const f32x2 rl = pack2(rr.x, rr.x), rh = pack2(rr.y, rr.y);
+    uint2 out, other;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint4 r = h ? r1 : r0;
+        const f32x2 x0 = FMA ? bf16x2_to_f32x2_fma(r.x) : bf16x2_to_f32x2(r.x);
+        const f32x2 x1 = FMA ? bf16x2_to_f32x2_fma(r.y) : bf16x2_to_f32x2(r.y);
+        const f32x2 x2 = FMA ? bf16x2_to_f32x2_fma(r.z) : bf16x2_to_f32x2(r.z);
+        const f32x2 x3 = FMA ? bf16x2_to_f32x2_fma(r.w) : bf16x2_to_f32x2(r.w);
+        (h ? out.y : out.x) = cvt_e2m1x8(mul2_plus0(x0, rl), mul2_plus0(x1, rl), mul2_plus0(x2, rl), mul2_plus0(x3, rl));
+        (h ? other.y : other.x) = cvt_e2m1x8(mul2_plus0(x0, rh), mul2_plus0(x1, rh), mul2_plus0(x2, rh), mul2_plus0(x3, rh));
+    }
+    // one test per group: the two bracket ends agree on all 16 codes (p(differ) ~ 1e-3 per group)
+    if (((out.x ^ other.x) | (out.y ^ other.y)) != 0) out = fix_group16_fp4(r0, r1, table_smem, code, out);
+    stg_stream(op, out);
+}
+
+template <bool FMA, bool FULL>
+__device__ __forceinline__ void fp4_compress2(const uint4 (&raw)[FP4_UF][2], uint32_t table_smem, float gs, uint8_t* sp, uint2* op, int rem) {
+#pragma unroll
+    for (int u = 0; u < FP4_UF; u++) {
+        if (!FULL && u * FP4_THREADS >= rem) continue;
+        fp4_compress_group<FMA>(raw[u][0], raw[u][1], table_smem, gs, sp + u * FP4_THREADS, op + u * FP4_THREADS);
+    }
+}
+
+// |max| bits of `ntiles` tiles starting at the thread's pointer (the first `nfull` of them whole), reduced over the CTA (valid in
+// thread 0).  This pass only waits on HBM, so what matters is bytes in flight: whole tiles go two at a time (8 x 128 bit per thread
+// outstanding).  Measured on the expert stacks (scripts/ab_fp4_v2.py): one tile at a time 0.66-0.73 of the roofline, two drained
+// together 0.73-0.77, two "rotating" (a tile's registers refilled as soon as it is reduced) 0.68-0.71 -- kept the second.
+__device__ __forceinline__ uint32_t fp4_absmax2(const uint4* wp, int ntiles, int nfull, int rem, uint32_t* s_red) {
+    uint32_t mm = 0;
+    const uint64_t keep = l2_policy_evict_last();  // the compress pass re-reads these lines
+    int k = 0;
+    for (; k + 2 <= nfull; k += 2) {
+        uint4 a[FP4_UF][2], b[FP4_UF][2];
+        fp4_load2<true>(a, wp, FP4_TILE_GROUPS, keep);
+        fp4_load2<true>(b, wp + 2 * FP4_TILE_GROUPS, FP4_TILE_GROUPS, keep);
+#pragma unroll
+        for (int u = 0; u < FP4_UF; u++) mm = hmaxabs2(mm, hmaxabs2(fp4_group_absmax2(a[u]), fp4_group_absmax2(b[u])));
+        wp += 4 * FP4_TILE_GROUPS;
+        rem -= 2 * FP4_TILE_GROUPS;
+    }
+    for (; k < ntiles; k++) {
+        uint4 raw[FP4_UF][2];
+        if (k < nfull) fp4_load2<true>(raw, wp, FP4_TILE_GROUPS, keep);      // CTA-uniform: no per-group predicates on whole tiles
+        else fp4_load2<true>(raw, wp, rem, keep);
+#pragma unroll
+        for (int u = 0; u < FP4_UF; u++) mm = hmaxabs2(mm, fp4_group_absmax2(raw[u]));
+        wp += 2 * FP4_TILE_GROUPS;
+        rem -= FP4_TILE_GROUPS;
+    }
+    mm = hmaxabs2(mm, prmt(mm, mm, 0x1032));
+    uint32_t bits = (mm << 16) & 0x7fff0000u;                  // |max| as fp32 bits: non-negative floats order like uints
+    bits = __reduce_max_sync(0xffffffffu, bits);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 1; i < FP4_THREADS / 32; i++) bits = max(bits, s_red[i]);
+    }
+    return bits;
+}
+
+template <bool FMA, int MINB>
+__global__ void __launch_bounds__(FP4_THREADS, MINB) nvfp4_fused2_kernel(const GroupParams p, const Fp4FusedParams f) {
+    __shared__ Fp4Lean table;
+    __shared__ float s_gs;
+    __shared__ int s_need_fallback;
+    __shared__ uint32_t s_red[FP4_THREADS / 32];
+    // CTA order: see nvfp4_fused_kernel
+    const unsigned nblk = (unsigned)(f.items_per_mat * f.span);
+    const int S = f.n_spans, Lh = f.lookahead;
+    const unsigned head = (unsigned)Lh * nblk, mid = (unsigned)(S - Lh) * 2u * nblk;
+    bool is_b;
+    int s;
+    unsigned j;
+    if (blockIdx.x < head) {
+        is_b = false; s = (int)fastdiv31(blockIdx.x, f.nblk_magic, f.nblk_shift); j = blockIdx.x - (unsigned)s * nblk;
+    } else if (blockIdx.x < head + mid) {
+        const unsigned b = blockIdx.x - head, pair = fastdiv31(b >> 1, f.nblk_magic, f.nblk_shift), q = b - pair * 2u * nblk;
+        if (f.by_item) { is_b = (q & 1u) == 0; j = q >> 1; }
+        else { is_b = q < nblk; j = is_b ? q : q - nblk; }
+        s = is_b ? (int)pair : (int)pair + Lh;
+    } else {
+        const unsigned b = blockIdx.x - head - mid, t = fastdiv31(b, f.nblk_magic, f.nblk_shift);
+        is_b = true; s = S - Lh + (int)t; j = b - t * nblk;
+    }
+    const unsigned mi = f.span == 1 ? 0u : fastdiv31(j, f.ipm_magic, f.ipm_shift), item = j - mi * (unsigned)f.items_per_mat;
+    const int64_t m = (int64_t)s * f.span + mi;
+    const int tile0 = (int)item * f.nt, ntiles = min(f.nt, f.tiles_per_mat - tile0);
+    const int64_t g_first = (int64_t)tile0 * FP4_TILE_GROUPS;
+    const bool last_partial = g_first + (int64_t)ntiles * FP4_TILE_GROUPS > f.groups_per_mat;   // CTA-uniform: only a matrix's last tile
+    const int nfull = last_partial ? ntiles - 1 : ntiles;
+    // groups left from this thread's first group of the tile (<= nt * 512: fits 32 bits); group u of the tile exists iff u * 256 < rem
+    const int rem = (int)min(f.groups_per_mat - g_first, (int64_t)f.nt * FP4_TILE_GROUPS) - (int)threadIdx.x;
+    const int64_t g_thread = m * f.groups_per_mat + g_first + threadIdx.x;
+    uint32_t* st = f.sync + 2 * s;
+    const uint4* wp = reinterpret_cast<const uint4*>(p.w) + 2 * g_thread;
+    if (!is_b) {
+        const uint32_t bits = fp4_absmax2(wp, ntiles, nfull, rem, s_red);
+        if (threadIdx.x == 0) {
+            atomicMax(&st[0], bits);
+            __threadfence();
+            atomicAdd(&st[1], 1u);
+        }
+        return;
+    }
+    // the first tile is in flight while we poll
+    uint4 raw[FP4_UF][2];
+    fp4_load2<false>(raw, wp, rem);
+    if (threadIdx.x == 0) {
+        int spins = f.force_fallback ? 20000 : 0;
+        while (ld_acquire(&st[1]) < nblk && spins < 20000) { __nanosleep(64); spins++; }
+        const bool fallback = f.force_fallback || ld_acquire(&st[1]) < nblk;
+        s_need_fallback = fallback;
+        if (!fallback) {
+            const float gs0 = gparam<DT_BF16>(__uint_as_float(ld_acquire(&st[0])));
+            s_gs = gs0;
+            if (item == 0) f.gs_out[m] = gs0;
+        }
+    }
+    __syncthreads();
+    if (s_need_fallback) {  // never taken when CTAs start in blockIdx order; keeps the kernel independent of that assumption
+        uint32_t bits = 0;
+        for (int q = 0; q < f.span; q++) {
+            const uint4* wq = reinterpret_cast<const uint4*>(p.w) + 2 * (((int64_t)s * f.span + q) * f.groups_per_mat + threadIdx.x);
+            const int64_t left = f.groups_per_mat - threadIdx.x;
+            // whole matrix, in pieces whose group count fits the 32-bit counter
+            for (int64_t t0 = 0; t0 < f.tiles_per_mat; t0 += 1 << 16) {
+                const int nt2 = (int)min((int64_t)(1 << 16), (int64_t)f.tiles_per_mat - t0);
+                const int rem2 = (int)min(left - t0 * FP4_TILE_GROUPS, (int64_t)nt2 * FP4_TILE_GROUPS);
+                bits = max(bits, fp4_absmax2(wq + 2 * t0 * FP4_TILE_GROUPS, nt2, 0, rem2, s_red));
+                __syncthreads();
+            }
+        }
+        if (threadIdx.x == 0) {
+            const float gs0 = gparam<DT_BF16>(__uint_as_float(bits));
+            s_gs = gs0;
+            if (item == 0) f.gs_out[m] = gs0;
+        }
+        __syncthreads();
+    }
+    const float gs = s_gs;
+    fp4_build_lean(&table, gs);
+    __syncthreads();
+    uint32_t tb = smem_u32(&table);
+    asm volatile("" : "+r"(tb));   // keep it in a register: rematerialising the shared-window base costs 3 uniform instructions per group
+    uint8_t* sp = (uint8_t*)p.scale + g_thread;
+    uint2* op = reinterpret_cast<uint2*>(p.out) + g_thread;
+    int r = rem;
+    // (refilling a group's registers with the next tile's group right after its conversion -- one group's loads always in flight --
+    // was tried: ptxas then keeps the tile in local memory at 48 registers, and 64 registers cost more residency than it gained)
+    // Latency hiding is left to the 40 resident warps.  Tried and measured slower (scripts/ab_fp4_v2.py, expert stacks, fraction of
+    // the 6.55 TB/s copy peak; this loop: 0.72-0.76): issuing the next tile's loads before converting the current one (two register
+    // tiles, 64 registers, 4 CTAs/SM: 0.66-0.71); refilling a group's registers right after its conversion (ptxas keeps the tile in
+    // local memory at 48 registers); per-thread cp.async double buffering through shared memory (0.47-0.50).
+    for (int k = 0; k < nfull; k++) {
+        if (k) fp4_load2<false>(raw, wp, FP4_TILE_GROUPS);
+        fp4_compress2<FMA, true>(raw, tb, gs, sp, op, r);
+        wp += 2 * FP4_TILE_GROUPS; sp += FP4_TILE_GROUPS; op += FP4_TILE_GROUPS; r -= FP4_TILE_GROUPS;
+    }
+    if (last_partial) {
+        if (nfull) fp4_load2<false>(raw, wp, r);
+        fp4_compress2<FMA, false>(raw, tb, gs, sp, op, r);
+    }
+}
+
+// caller-supplied global scales, lean version of nvfp4_flat_kernel: the compress pass of the fused kernel alone
+__global__ void __launch_bounds__(FP4_THREADS, 5) nvfp4_flat2_kernel(const GroupParams p, int64_t groups_per_mat, int tiles_per_mat) {
+    __shared__ Fp4Lean table;
+    const int64_t b = blockIdx.y;
+    const float gs = p.gs[p.gs_stride ? b : 0];
+    fp4_build_lean(&table, gs);
+    __syncthreads();
+    uint32_t tb = smem_u32(&table);
+    asm volatile("" : "+r"(tb));
+    for (int tile = blockIdx.x; tile < tiles_per_mat; tile += gridDim.x) {
+        const int64_t g_first = (int64_t)tile * FP4_TILE_GROUPS;
+        const int64_t g_thread = b * groups_per_mat + g_first + threadIdx.x;
+        const int rem = (int)min(groups_per_mat - g_first, (int64_t)FP4_TILE_GROUPS) - (int)threadIdx.x;
+        const uint4* wp = reinterpret_cast<const uint4*>(p.w) + 2 * g_thread;
+        uint8_t* sp = (uint8_t*)p.scale + g_thread;
+        uint2* op = reinterpret_cast<uint2*>(p.out) + g_thread;
+        uint4 raw[FP4_UF][2];
+        if (g_first + FP4_TILE_GROUPS <= groups_per_mat) {       // CTA-uniform
+            fp4_load2<false>(raw, wp, FP4_TILE_GROUPS);
+            fp4_compress2<false, true>(raw, tb, gs, sp, op, rem);
+        } else {
+            fp4_load2<false>(raw, wp, rem);
+            fp4_compress2<false, false>(raw, tb, gs, sp, op, rem);
+        }
+    }
+}
+
 }  // namespace
 
 // tuning knob read from the environment (development sweeps); `dflt` when unset
@@ -510,7 +785,9 @@ int launch_nvfp4_fast(const GroupParams& p, int64_t batch, cudaStream_t st) {
     const int64_t want = (int64_t)kNumSMs * 6;
     int64_t gx = tiles;
     if (batch * tiles > 4 * want) gx = max((int64_t)1, min(tiles, 4 * want / batch));
-    nvfp4_flat_kernel<<<dim3((unsigned)gx, (unsigned)batch), FP4_THREADS, 0, st>>>(p, groups_per_mat, (int)tiles);
+    static const bool flat_v1 = getenv("B200Q_FP4_FUSED_V1") != nullptr;   // round-1 kernel (A/B)
+    if (flat_v1) nvfp4_flat_kernel<<<dim3((unsigned)gx, (unsigned)batch), FP4_THREADS, 0, st>>>(p, groups_per_mat, (int)tiles);
+    else nvfp4_flat2_kernel<<<dim3((unsigned)gx, (unsigned)batch), FP4_THREADS, 0, st>>>(p, groups_per_mat, (int)tiles);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }
@@ -540,7 +817,14 @@ int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_
     if (span < 1 || batch % span != 0) return B200Q_ENOSYS;
     const int64_t groups_per_mat = p.rows * (p.cols >> 4);
     const int64_t tiles = (groups_per_mat + FP4_TILE_GROUPS - 1) / FP4_TILE_GROUPS;
-    const int nt = tune_env("B200Q_FP4_NT", 4);
+    // tiles per CTA: the CTA prologue (index decode, poll, table build) is ~100 instructions per thread, i.e. 0.8 per weight at 4 tiles;
+    // 6 tiles measured best on the expert stacks (scripts/ab_fp4_v2.py), fewer when the launch would not fill two waves
+    static const bool v1 = getenv("B200Q_FP4_FUSED_V1") != nullptr;   // round-1 kernel (A/B)
+    int nt = tune_env("B200Q_FP4_NT", 0);
+    if (nt <= 0) {
+        nt = v1 ? 4 : 6;
+        while (!v1 && nt > 2 && 2 * batch * ((tiles + nt - 1) / nt) < 2 * (int64_t)kNumSMs * 5) nt = nt == 6 ? 3 : 2;
+    }
     const int64_t items = (tiles + nt - 1) / nt;
     const int64_t n_spans = batch / span;
     const int64_t grid = 2 * n_spans * items * span;
@@ -558,12 +842,34 @@ int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_
     f.by_item = by_item >= 0 ? by_item : (f.lookahead == 1 ? 1 : 0);
     f.sync = sync;
     f.gs_out = gs_out;
+    auto magic31 = [](uint32_t d, uint32_t& magic, uint32_t& shift) {   // floor(n / d) == (n * magic) >> shift for every n < 2^31
+        uint32_t l = 0;
+        while ((1ull << l) < d) l++;
+        shift = 31 + l;
+        magic = (uint32_t)(((1ull << shift) + d - 1) / d);
+    };
+    magic31((uint32_t)(items * span), f.nblk_magic, f.nblk_shift);
+    magic31((uint32_t)items, f.ipm_magic, f.ipm_shift);
+    f.force_fallback = tune_env("B200Q_FP4_FORCE_FALLBACK", 0);
     static const bool no_loc = getenv("B200Q_FP4_NO_LOC") != nullptr;   // A/B: recompute the group statistics in the compress pass (round 1)
     f.loc = no_loc ? nullptr : loc_scratch;
     cudaMemsetAsync(sync, 0, sizeof(uint32_t) * 2 * n_spans, st);
     static const bool fma = getenv("B200Q_FP4_FMA") != nullptr;  // FHFMA unpack (ALU-pipe relief), A/B switch
-    if (fma) nvfp4_fused_kernel<true><<<(unsigned)grid, FP4_THREADS, 0, st>>>(p, f);
-    else nvfp4_fused_kernel<false><<<(unsigned)grid, FP4_THREADS, 0, st>>>(p, f);
+    if (v1 || f.loc != nullptr) {   // the opt-in group-statistics scratch (B200Q_FP4_LOC) only exists in the round-1 kernel
+        if (fma) nvfp4_fused_kernel<true><<<(unsigned)grid, FP4_THREADS, 0, st>>>(p, f);
+        else nvfp4_fused_kernel<false><<<(unsigned)grid, FP4_THREADS, 0, st>>>(p, f);
+    } else {
+        // resident CTAs per SM the register budget is set for: 5 = 48 registers, no spills, 193 instructions per tile; 6 = 40 registers
+        // with spilled pointers, 213 (measured 3-6 % slower); 4 = 64 registers, slower
+        static const int minb = tune_env("B200Q_FP4_MINB", 5);
+        const unsigned g = (unsigned)grid;
+#define B200Q_FP4_LAUNCH(FMA_) do { \
+            if (minb == 6) nvfp4_fused2_kernel<FMA_, 6><<<g, FP4_THREADS, 0, st>>>(p, f); \
+            else if (minb == 4) nvfp4_fused2_kernel<FMA_, 4><<<g, FP4_THREADS, 0, st>>>(p, f); \
+            else nvfp4_fused2_kernel<FMA_, 5><<<g, FP4_THREADS, 0, st>>>(p, f); } while (0)
+        if (fma) B200Q_FP4_LAUNCH(true); else B200Q_FP4_LAUNCH(false);
+#undef B200Q_FP4_LAUNCH
+    }
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }

@@ -52,3 +52,16 @@ def test_reciprocal_multiply_equals_division_on_random_operands():
     for perturb in (1.0, 1 - 2.0 ** -22, 1 + 2.0 ** -22):             # rcp.approx is within 1 ulp of this
         got = _bf16_rne((x * (r * np.float32(perturb)).astype(np.float32)).astype(np.float32))
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_nvfp4_group_scale_is_one_multiply_for_every_bf16_statistic():
+    """NVFP4 local scale T(absmax / 6) (helpers.py calculate_qparams, TENSOR_GROUP): the fused kernel's compress pass computes it as
+    bf16(absmax * fp32(1/6)) with no range test (quant_tile_fast.cu fp4_compress_group).  Exhaustive over every non-negative bf16
+    including subnormals and +inf, against torch's bf16 division (fp32 divide, round to bf16)."""
+    import torch
+
+    bits = torch.arange(0, 0x7F81, dtype=torch.int32)                 # 0 .. +inf
+    a = (bits << 16).view(torch.float32)
+    ref = (a.to(torch.bfloat16) / 6).view(torch.int16)
+    one = (a * torch.tensor(1.0 / 6.0, dtype=torch.float32)).to(torch.bfloat16).view(torch.int16)
+    assert torch.equal(ref, one)

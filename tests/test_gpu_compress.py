@@ -89,15 +89,21 @@ def test_nvfp4_supplied_global_scale():
     _cmp_sd(got, want, "nvfp4 gs")
 
 
-@pytest.mark.parametrize("persistent", ["0", "1"])
+@pytest.mark.parametrize("persistent", ["0", "1", "fallback", "nt1", "nt8"])
 @pytest.mark.parametrize("E,R,C,span", [(6, 36, 512, 2), (64, 768, 2048, 2), (9, 200, 1040, 3), (3, 2048, 768, 1), (320, 256, 2048, 2)])
 def test_nvfp4_fused_sibling_global_scale(E, R, C, span, persistent, monkeypatch):
     """gate/up siblings stacked next to each other share min(global_scale) (LLMC update_fused_layer_weight_global_scales); both
     schedulings of the single-launch kernel (one CTA per item with the |max| pass running ahead; persistent warp-specialised CTA
-    per SM, B200Q_FP4_PERSISTENT=1) must equal the oracle run with that shared scale."""
+    per SM, B200Q_FP4_PERSISTENT=1) must equal the oracle run with that shared scale.  "fallback": every compress CTA takes the
+    never-observed branch that reduces the span itself (the launch must not depend on CTA dispatch order); "nt1" / "nt8": other
+    tiles-per-CTA counts than the default (whole-tile fast path vs the ragged last tile, the CTA-index decode)."""
     from quantizers_b200 import ops
 
-    monkeypatch.setenv("B200Q_FP4_PERSISTENT", persistent)
+    monkeypatch.setenv("B200Q_FP4_PERSISTENT", "1" if persistent == "1" else "0")
+    if persistent == "fallback":
+        monkeypatch.setenv("B200Q_FP4_FORCE_FALLBACK", "1")
+    if persistent.startswith("nt"):
+        monkeypatch.setenv("B200Q_FP4_NT", persistent[2:])
 
     ws = [(synth_weight(R, C, torch.bfloat16, 300 + e, edge=R >= 64) * (1.0 + 0.37 * e)).to(torch.bfloat16) for e in range(E)]
     got = ops.compress_weight(torch.stack(ws).cuda(), Args("nvfp4"), fuse_span=span)
