@@ -491,6 +491,7 @@ def run_moe_awq(args, dev, world, rank, peaks):
     copies = [(w2.clone(), w3.clone()) for _ in range(reps)]  # the search smooths the weights in place
     torch.cuda.synchronize()
     e0.record()
+    res = []
     for a, b in copies:
         res = awq.search_expert_mappings(xs, a, qargs, smooth_weight=b)
     e1.record()
@@ -519,9 +520,12 @@ def run_moe_awq(args, dev, world, rank, peaks):
 
 def run_moe_block(args, dev, world, rank, peak):
     """configs[4] kind (i): the layer-wide mapping post_attention_layernorm -> every expert's w1, w3 (one scale vector, parent =
-    the routed sparse-MoE block, top-8 routing) on a layer of ``--moe-block-experts`` experts (default: all 256 of MiniMax-M2.1).  All experts live on every
-    rank; the T calibration tokens are sharded across the ranks (strong scaling) and the |x| sums / [n_grid] loss accumulators
-    are all-reduced over NCCL -- the one real exchange step of the path."""
+    the routed sparse-MoE block, top-8 routing) on a layer of ``--moe-block-experts`` experts (default: all 256 of MiniMax-M2.1), strong
+    scaling.  N > 1: EXPERT-parallel (``awq.search_moe_block_mapping_ep``): rank r holds the ascending expert range r of the layer and
+    a token shard; the shards are all-gathered, every rank scales / fake-quantises / multiplies only its own experts, and the block
+    output is accumulated along the ring 0 -> .. -> N-1 over NCCL send/recv so that the reference's per-expert bf16 ``index_add_``
+    rounding sequence is kept bit for bit -- the real exchange step of this path.  ``--moe-block-token-sharded`` runs round 1's
+    token-sharded variant instead (all experts on every rank; |x| sums and loss accumulators all-reduced)."""
     import torch.distributed as dist
 
     from quantizers_b200 import awq
@@ -531,7 +535,9 @@ def run_moe_block(args, dev, world, rank, peak):
     K = min(8, E)
     T = args.awq_tokens
     qargs = S.PRESETS["INT4_G32_SYM"]
-    units = list(range(E))
+    ep = world > 1 and not args.moe_block_token_sharded and E >= world
+    mine = S.partition(E, world, rank) if ep else range(E)
+    units = list(mine)
     w1 = S.synth_stack(units, I, H, 0, dev)
     w3 = S.synth_stack(units, I, H, 1, dev)
     w2 = S.synth_stack(units, H, I, 2, dev)
@@ -545,29 +551,41 @@ def run_moe_block(args, dev, world, rank, peak):
     topk_w = topk_w / topk_w.sum(-1, keepdim=True)
     del x_all
     pg = dist.group.WORLD if world > 1 else None
-    awq.search_moe_block_mapping(x, w1, w3, w2, topk_idx, topk_w, qargs, process_group=pg)   # warm-up pass
+
+    def search():
+        if ep:
+            return awq.search_moe_block_mapping_ep(x, w1, w3, w2, topk_idx, topk_w, qargs, expert_offset=mine.start, process_group=pg)
+        return awq.search_moe_block_mapping(x, w1, w3, w2, topk_idx, topk_w, qargs, process_group=pg)
+
+    search()   # warm-up pass
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    s, ratio, losses = awq.search_moe_block_mapping(x, w1, w3, w2, topk_idx, topk_w, qargs, process_group=pg)
+    s, ratio, losses = search()
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    tf = awq.moe_block_flops(len(tok), K, H, I) / (ms * 1e-3) / 1e12
+    share = T // world if ep else len(tok)           # routed pairs a rank multiplies: all tokens x its experts == its share of the pairs
+    tf = awq.moe_block_flops(share, K, H, I) / (ms * 1e-3) / 1e12
     awq.workspace.release()
+    if world == 1:
+        coll = None
+    elif ep:
+        coll = "all-gather of the token shards; ring send/recv of the running bf16 block output (21 passes); all-reduce of w_mean sums and [n_grid] losses"
+    else:
+        coll = "all-reduce(SUM) of |x| sums and [n_grid] loss accumulators"
     return {"metric": "awq_layer_mappings_per_s", "value": 1e3 / ms, "unit": "mappings/s", "ms": ms, "scaling": "strong",
             "config": {"workload": "minimax-m2.1 layer-wide mapping (post_attention_layernorm -> all experts' w1/w3), routed block parent",
-                       "experts": E, "top_k": K, "tokens": T, "tokens_per_gpu": len(tok), "best_ratio": ratio,
-                       "collective": "all-reduce(SUM) of |x| sums and [n_grid] loss accumulators" if world > 1 else None},
+                       "experts": E, "top_k": K, "tokens": T, "sharding": "experts (ring-ordered combine)" if ep else ("tokens" if world > 1 else None),
+                       "experts_per_gpu": len(units), "tokens_per_gpu": T if ep else len(tok), "best_ratio": ratio, "collective": coll},
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
                          "kernel": "awq_gemm_project_kernel, grouped mode (tcgen05, TMEM): one launch per stage over all experts + bf16 combine kernel",
                          "note": "routed pairs sorted expert-major, rows padded to 128-row tiles; per-GPU figure of the slowest rank"}}
-
 
 # ----------------------------------------------------------------------------- strong-scaling headline, GLM leg, parity
 def run_headline_strong(args, dev, world, rank, peaks):
@@ -802,10 +820,32 @@ def run_parity(args, dev, world, rank):
         _, r_un, l_un = awq.compute_best_scale(x, [w], awq.linear_parent, qa)
         res["awq_token_sharded_same_argmin"] = bool(r_sh == r_un)
         res["awq_token_sharded_max_rel_loss_diff"] = max(abs(a - b) / b for a, b in zip(l_sh, l_un))
+    # ---- layer-wide MoE mapping, experts partitioned over the ranks, ring-ordered combine (16 experts, top-4, 4096 tokens)
+    if world > 1:
+        Em, Hm, Im, Km, Tm = 16, 512, 384, 4, 4096
+        g = torch.Generator(device=dev).manual_seed(777)
+        xm = (torch.randn(Tm, Hm, generator=g, device=dev) * (1 + 3 * torch.rand(Hm, generator=g, device=dev))).to(torch.bfloat16)
+        m1 = (torch.randn(Em, Im, Hm, generator=g, device=dev) * 0.05).to(torch.bfloat16)
+        m3 = (torch.randn(Em, Im, Hm, generator=g, device=dev) * 0.05).to(torch.bfloat16)
+        m2 = (torch.randn(Em, Hm, Im, generator=g, device=dev) * 0.05).to(torch.bfloat16)
+        pm = torch.softmax(torch.randn(Tm, Em, generator=g, device=dev), dim=-1)
+        tw, ti = torch.topk(pm, Km, dim=-1)
+        tw = tw / tw.sum(-1, keepdim=True)
+        qm = S.PRESETS["INT4_G32_SYM"]
+        ex, tk = S.partition(Em, world, rank), S.partition(Tm, world, rank)
+        _, r_ep, l_ep = awq.search_moe_block_mapping_ep(xm[tk.start:tk.stop].contiguous(), m1[ex.start:ex.stop].contiguous(), m3[ex.start:ex.stop].contiguous(),
+                                                        m2[ex.start:ex.stop].contiguous(), ti[tk.start:tk.stop].contiguous(), tw[tk.start:tk.stop].contiguous(),
+                                                        qm, expert_offset=ex.start, process_group=pg)
+        if rank == 0:
+            _, r_1, l_1 = awq.search_moe_block_mapping(xm, m1, m3, m2, ti, tw, qm)
+            res["moe_mapping_expert_parallel_same_argmin"] = bool(r_ep == r_1)
+            res["moe_mapping_expert_parallel_max_rel_loss_diff"] = max(abs(a - b) / b for a, b in zip(l_ep, l_1))
     awq.workspace.release()
     torch.cuda.empty_cache()
     if rank == 0:
-        res["ok"] = bool(res["rtn_layer_sharded_eq_unsharded"] and res["nvfp4_expert_sharded_eq_unsharded"] and res["awq_token_sharded_same_argmin"]
+        if world > 1:
+            res["ok_moe_mapping"] = bool(res["moe_mapping_expert_parallel_same_argmin"] and res["moe_mapping_expert_parallel_max_rel_loss_diff"] < 1e-3)
+        res["ok"] = bool(res.get("ok_moe_mapping", True) and res["rtn_layer_sharded_eq_unsharded"] and res["nvfp4_expert_sharded_eq_unsharded"] and res["awq_token_sharded_same_argmin"]
                          and res["awq_token_sharded_max_rel_loss_diff"] < 1e-3)
         res["world_size"] = world
     return res
@@ -827,6 +867,7 @@ def main():
     ap.add_argument("--moe-layers", type=int, default=8, help="layers of the Qwen3-30B-A3B NVFP4 expert-sharded leg (0 disables it)")
     ap.add_argument("--moe-steps", type=int, default=20)
     ap.add_argument("--moe-awq-experts", type=int, default=256, help="experts of the MiniMax-M2.1 per-expert AWQ leg (256 = one full layer; 0 disables it)")
+    ap.add_argument("--moe-block-token-sharded", action="store_true", help="N > 1: round 1's token-sharded layer-wide mapping instead of the expert-parallel ring")
     ap.add_argument("--moe-block-experts", type=int, default=256, help="experts of the layer-wide MoE mapping leg (256 = the full MiniMax-M2.1 layer; 0 disables it)")
     ap.add_argument("--cpu-awq-tokens", type=int, default=1024, help="calibration tokens of the CPU AWQ baseline (whole layer; 0 disables it); "
                                                                       "--impl reference uses max(this, 2048)")

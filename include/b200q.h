@@ -225,6 +225,12 @@ int b200q_awq_gemm_project_grouped(const void* x, int64_t tokens, int64_t k, con
  * [tokens, top_k], y T [padded rows, hidden], out T [tokens, hidden].  bf16 only. */
 int b200q_moe_combine(const void* y, const int32_t* row, const void* weight, int64_t tokens, int32_t top_k, int64_t hidden, void* out,
                       void* stream);
+/* ... continuing a running sum: out[t] = init[t] + (this call's rows, same order and rounding); init T [tokens, hidden] may alias out,
+ * NULL = zeros.  Expert-parallel ranks own ascending expert ranges, so rank r continues the sequence rank r - 1 left off (its partial
+ * output arrives over NCCL send/recv) and the last rank holds the block output bit-identical to the single-GPU one
+ * (quantizers_b200/awq.py search_moe_block_mapping_ep). */
+int b200q_moe_combine_acc(const void* y, const int32_t* row, const void* weight, int64_t tokens, int32_t top_k, int64_t hidden, const void* init,
+                          void* out, void* stream);
 
 /* SURVEY.md §8f rank 4 -- GPTQ Hessian accumulation (LLMC modifiers/gptq: accumulate_hessian; the reference's GPTQ recipes,
  * /root/reference/scripts/old_scripts/main_glm4-gptq.py:108-126): hessian fp32 [features, features] = alpha * hessian + beta * X^T X

@@ -68,6 +68,7 @@ _SIGS = {
     "b200q_compress_nvfp4_workspace": (c_int64, [c_int64, c_int64, c_int64, c_int32]),
     "b200q_awq_gemm_project_grouped": (_I, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int32, _P, _P, _P]),
     "b200q_moe_combine": (_I, [_P, _P, _P, c_int64, c_int32, c_int64, _P, _P]),
+    "b200q_moe_combine_acc": (_I, [_P, _P, _P, c_int64, c_int32, c_int64, _P, _P, _P]),
     "b200q_decompress_int_packed": (_I, [_P, _P, _P, c_int64, c_int64, c_int64, _S, _P, _P]),
     "b200q_decompress_nvfp4": (_I, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P]),
     "b200q_gptq_hessian_accumulate": (_I, [_P, c_int64, c_int64, c_float, c_float, _P, _P]),

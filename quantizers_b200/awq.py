@@ -16,6 +16,7 @@ the fused tcgen05 kernel ``b200q_awq_gemm_loss`` (csrc/awq_gemm.cu).
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
@@ -523,6 +524,8 @@ def search_expert_mappings(x_in: Sequence[torch.Tensor], balance: torch.Tensor, 
     Returns one (best_scales cpu fp32 [K], best_ratio, losses[n_grid]) per local expert."""
     if len(x_in) != balance.shape[0]:
         raise L.B200QError("search_expert_mappings: one input per stacked expert weight is needed")
+    if len(x_in) == 0:      # a rank that owns no expert of this layer (more ranks than experts)
+        return []
     # everything stays on the device until all experts are enqueued: no host round trip (and no idle GPU) between experts
     pend = []
     for e, x in enumerate(x_in):
@@ -565,24 +568,31 @@ class RoutedMoE:
 
     TILE = 128
 
-    def __init__(self, x: torch.Tensor, w2: torch.Tensor, topk_idx: torch.Tensor, topk_w: torch.Tensor):
+    def __init__(self, x: torch.Tensor, w2: torch.Tensor, topk_idx: torch.Tensor, topk_w: torch.Tensor, expert_offset: int = 0):
+        """``expert_offset``: expert-parallel use -- ``w2`` holds experts ``[expert_offset, expert_offset + w2.shape[0])`` of the layer
+        and only the pairs routed to them are laid out; a token's other slots get row -1 (skipped by the combine kernel)."""
         L.require_cuda(x, w2, topk_idx, topk_w)
         T, k = topk_idx.shape
         E = w2.shape[0]
         dev = x.device
-        flat = topk_idx.reshape(-1).to(torch.int64)
-        order = torch.argsort(flat, stable=True)                      # pairs expert-major, token order inside an expert
-        counts = torch.bincount(flat, minlength=E)
+        flat = topk_idx.reshape(-1).to(torch.int64) - int(expert_offset)
+        local = (flat >= 0) & (flat < E)
+        key = torch.where(local, flat, torch.full_like(flat, E))       # foreign pairs sort behind every local expert
+        order = torch.argsort(key, stable=True)                       # pairs expert-major, token order inside an expert
+        counts = torch.bincount(key, minlength=E + 1)[:E]
         padded = (counts + self.TILE - 1) // self.TILE * self.TILE
         starts = torch.cumsum(padded, 0) - padded                     # first padded row of each expert
         rows_total = int(padded.sum().item())                         # the one host round trip of the mapping
         rows_total = max(rows_total, self.TILE)
         excl = torch.cumsum(counts, 0) - counts
-        sorted_e = flat[order]
-        prow = starts[sorted_e] + (torch.arange(order.numel(), device=dev) - excl[sorted_e])   # padded row of each sorted pair
-        gather = torch.zeros(rows_total, dtype=torch.int64, device=dev)                          # padding rows read token 0
-        gather[prow] = order // k
-        self.xs = x.index_select(0, gather)                            # [rows_total, H] routed inputs
+        sorted_e = key[order]
+        sorted_local = sorted_e < E
+        se = sorted_e.clamp(max=E - 1)
+        prow = starts[se] + (torch.arange(order.numel(), device=dev) - excl[se])                 # padded row of each sorted pair
+        prow = torch.where(sorted_local, prow, torch.full_like(prow, -1))
+        gather = torch.zeros(rows_total + 1, dtype=torch.int64, device=dev)                      # padding rows read token 0
+        gather[torch.where(sorted_local, prow, torch.full_like(prow, rows_total))] = order // k   # foreign pairs land in the spare slot
+        self.xs = x.index_select(0, gather[:rows_total])               # [rows_total, H] routed inputs
         tile_e = torch.full((rows_total // self.TILE,), -1, dtype=torch.int32, device=dev)
         tile_ids = torch.arange(rows_total // self.TILE, device=dev) * self.TILE
         owner = torch.searchsorted(starts + padded, tile_ids, right=True).clamp(max=E - 1)
@@ -598,8 +608,8 @@ class RoutedMoE:
         self.pw = topk_w.to(x.dtype).gather(1, by_expert).contiguous()
         self.w2, self.T, self.H, self.k = w2.contiguous(), T, x.shape[1], k
 
-    def __call__(self, w13: torch.Tensor) -> torch.Tensor:
-        """w13 ``[E, 2 * I, H]`` (w1 rows, then w3 rows) -> block output ``[T, H]``."""
+    def project(self, w13: torch.Tensor, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The two grouped GEMM stages: w13 ``[E, 2 * I, H]`` -> per-pair expert outputs ``y [padded rows, H]``."""
         lib = L.lib()
         dev = self.xs.device
         st = L.stream_ptr(dev)
@@ -607,12 +617,24 @@ class RoutedMoE:
         I = two_i // 2
         R = self.xs.shape[0]
         h = workspace.get("moe_h", (R, I), self.xs.dtype, dev)
-        y = workspace.get("moe_y", (R, self.H), self.xs.dtype, dev)
+        if y is None:
+            y = workspace.get("moe_y", (R, self.H), self.xs.dtype, dev)
         L.check(lib.b200q_awq_gemm_project_grouped(L.ptr(self.xs), R, H, L.ptr(w13), E, I, 1, L.ptr(self.tile_expert), L.ptr(h), st))
         L.check(lib.b200q_awq_gemm_project_grouped(L.ptr(h), R, I, L.ptr(self.w2), E, self.H, 0, L.ptr(self.tile_expert), L.ptr(y), st))
-        out = torch.empty((self.T, self.H), dtype=self.xs.dtype, device=dev)
-        L.check(lib.b200q_moe_combine(L.ptr(y), L.ptr(self.rows), L.ptr(self.pw), self.T, self.k, self.H, L.ptr(out), st))
+        return y
+
+    def combine(self, y: torch.Tensor, out: Optional[torch.Tensor] = None, init: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``out[t] = init[t] + sum_j bf16(y[rows[t, j]] * p[t, j])`` in ascending expert order, bf16 rounding after every step
+        (``init`` None: zeros; it may be ``out`` itself)."""
+        if out is None:
+            out = torch.empty((self.T, self.H), dtype=self.xs.dtype, device=self.xs.device)
+        L.check(L.lib().b200q_moe_combine_acc(L.ptr(y), L.ptr(self.rows), L.ptr(self.pw), self.T, self.k, self.H, L.ptr(init), L.ptr(out),
+                                              L.stream_ptr(self.xs.device)))
         return out
+
+    def __call__(self, w13: torch.Tensor) -> torch.Tensor:
+        """w13 ``[E, 2 * I, H]`` (w1 rows, then w3 rows) -> block output ``[T, H]``."""
+        return self.combine(self.project(w13))
 
 
 @torch.no_grad()
@@ -664,3 +686,218 @@ def search_moe_block_mapping(x: torch.Tensor, w1: torch.Tensor, w3: torch.Tensor
     acc[n_grid:].fill_(float(ref.numel()))
     best_i, losses = reduce_and_select(acc, process_group if dist_on else None, dist_on)
     return scales[best_i].cpu(), ratios[best_i], losses
+
+
+def _all_gather_rows(t: torch.Tensor, group, sizes: Optional[List[int]] = None) -> torch.Tensor:
+    """Concatenate the ranks' row shards (rank order; shards may differ in length).  ``sizes``: the ranks' row counts when they are
+    already known (``_gather_sizes``), saving the exchange."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    if sizes is None:
+        sizes = _gather_sizes(t.shape[0], t.device, group)
+    m = max(sizes)
+    pad = t if t.shape[0] == m else torch.cat([t, t.new_zeros((m - t.shape[0],) + tuple(t.shape[1:]))])
+    if min(sizes) == m:
+        out = torch.empty((world * m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+        return out
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad.contiguous(), group=group)
+    return torch.cat([p[:k] for p, k in zip(parts, sizes)])
+
+
+def _gather_sizes(n_rows: int, device, group) -> List[int]:
+    import torch.distributed as dist
+
+    n = torch.tensor([n_rows], dtype=torch.int64, device=device)
+    sizes = torch.empty(dist.get_world_size(group), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(sizes, n, group=group)
+    return [int(v) for v in sizes.tolist()]
+
+
+@torch.no_grad()
+def search_moe_block_mapping_ep(x: torch.Tensor, w1: torch.Tensor, w3: torch.Tensor, w2: torch.Tensor, topk_idx: torch.Tensor,
+                                topk_w: torch.Tensor, args, expert_offset: int, process_group, n_grid: int = 20,
+                                duo_scaling: bool = True, max_variant_bytes: int = 16 << 30,
+                                ring_chunks: int = 4) -> Tuple[torch.Tensor, float, List[float]]:
+    """``search_moe_block_mapping`` with the EXPERTS partitioned over the ranks (rank r holds the ascending range
+    ``[expert_offset, expert_offset + w1.shape[0])``; ranges in rank order) and each rank's token shard ``x`` / ``topk_*`` all-gathered.
+
+    Why not token sharding: every rank would fake-quantise all 2E matrices for all ratios (replicated work: 49 of 96 ms on 8 GPUs at
+    256 experts).  Here a rank scales, fake-quantises and multiplies only its own experts, for all tokens.  The block output is a
+    per-token sum over the token's experts accumulated IN ASCENDING EXPERT ORDER with bf16 rounding after every step (transformers'
+    per-expert ``index_add_``), so the partial outputs are not summed by a reduction (a different rounding sequence: ~2 % loss noise)
+    but passed along the ring 0 -> 1 -> ... -> N-1: rank r receives the running bf16 output of the experts before its own, continues
+    the sequence with ``b200q_moe_combine_acc`` and sends it on; the last rank holds the output bit-identical to the single-GPU one
+    and takes the loss.  One ring pass per evaluated weight set (reference + n_grid ratios), NCCL send/recv on a side stream, the
+    GEMMs of later passes running ahead on the compute stream.  The [n_grid] losses are all-reduced (only the last rank's are non-zero).
+    Returns (best_scales cpu fp32 [H], best_ratio, losses[n_grid]) on every rank."""
+    import torch.distributed as dist
+
+    L.require_cuda(x, w1, w3, w2)
+    if x.dtype != torch.bfloat16:
+        raise L.B200QError("search_moe_block_mapping_ep runs on the bf16 tensor-core path")
+    if process_group is None or not dist.is_initialized() or dist.get_world_size(process_group) < 2:
+        raise L.B200QError("search_moe_block_mapping_ep needs a process group of at least 2 ranks (one rank: search_moe_block_mapping)")
+    world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+    prev_rank = dist.get_global_rank(process_group, rank - 1) if rank > 0 else None
+    next_rank = dist.get_global_rank(process_group, rank + 1) if rank + 1 < world else None
+    # hop r -> r + 1 runs on ring group r % 2: a rank's receive (from r - 1) and its send (to r + 1) then sit on different NCCL
+    # communicators / streams and overlap (unbatched P2P ops on ONE eagerly initialised group are serialised with each other)
+    hop_groups = _ring_groups(process_group) if os.environ.get("B200Q_EP_RING", "symm") == "nccl" else (process_group, process_group)
+    recv_group, send_group = hop_groups[(rank - 1) % 2], hop_groups[rank % 2]
+    E, I, H = w1.shape
+    dev = x.device
+    # ---- every rank sees all tokens (activations are small next to the weights: T x H bf16)
+    sizes = _gather_sizes(x.shape[0], dev, process_group)
+    x = _all_gather_rows(x.contiguous(), process_group, sizes)
+    topk_idx = _all_gather_rows(topk_idx.contiguous(), process_group, sizes)
+    topk_w = _all_gather_rows(topk_w.contiguous(), process_group, sizes)
+    T = x.shape[0]
+    w13 = torch.cat([w1, w3], dim=1).contiguous()              # [E, 2I, H], this rank's experts
+    x_mean = abs_sum_cols(x) / float(T)                         # the same bits on every rank, and the single-GPU bits
+    rows_per_call = 262144  # launch limit of the row-tiled kernels
+    flat = w13.view(-1, H)
+    w_mean = None
+    if duo_scaling:
+        acc64 = torch.zeros(H, dtype=torch.float64, device=dev)
+        for r0 in range(0, flat.shape[0], rows_per_call):
+            blk = flat[r0:r0 + rows_per_call]
+            L.check(L.lib().b200q_wmean_accumulate(L.ptr(blk), blk.shape[0], H, L.DTYPE_CODE[blk.dtype], args.group_size, L.ptr(acc64),
+                                                   L.stream_ptr(dev)))
+        n_rows = torch.tensor([float(flat.shape[0])], dtype=torch.float64, device=dev)
+        dist.all_reduce(acc64, op=dist.ReduceOp.SUM, group=process_group)
+        dist.all_reduce(n_rows, op=dist.ReduceOp.SUM, group=process_group)
+        w_mean = (acc64 / n_rows).float()
+    ratios = [i / n_grid for i in range(n_grid)]
+    scales = awq_scales(x_mean, w_mean, ratios, duo_scaling)
+    parent = RoutedMoE(x, w2, topk_idx, topk_w, expert_offset=expert_offset)
+    R = parent.xs.shape[0]
+    n_pass = n_grid + 1                                         # pass 0: the unquantised weights, pass 1 + i: ratio i
+    ys = workspace.get("moe_ep_y", (n_pass, R, H), x.dtype, dev)
+    # The running outputs live in symmetric memory when the ranks can map each other's buffers (one node, NVLink): the combine kernel
+    # then writes its result straight into the NEXT rank's buffer -- the transfer is the kernel's own stores over NVLink, overlapped
+    # with the GEMMs of later passes, and a flag in the peer's signal pad hands the chunk over.  Measured at N = 8 (256 experts, 32 768
+    # tokens): NCCL send/recv moved a 201 MB pass in ~2.2 ms per hop and bounded the search at 53 ms; B200Q_EP_RING=nccl keeps it.
+    symm = _ep_symm_buffer(n_pass * T * H, x.dtype, dev, process_group) if os.environ.get("B200Q_EP_RING", "symm") != "nccl" else None
+    if symm is not None:
+        outs = symm[0].view(n_pass, T, H)
+        peer_outs = symm[1].get_buffer(rank + 1, (n_pass, T, H), x.dtype) if rank + 1 < world else None
+    else:
+        outs = workspace.get("moe_ep_out", (n_pass, T, H), x.dtype, dev)
+    acc = torch.zeros(n_grid + 1, dtype=torch.float32, device=dev)
+    main = torch.cuda.current_stream(dev)
+    side = _ep_side_stream(dev)
+    side.wait_stream(main)
+    y_ready = [torch.cuda.Event() for _ in range(n_pass)]
+    sends = []
+
+    # a pass travels in token chunks: the ring's fill / drain time is (N - 1) hops of ONE chunk instead of the whole [T, H] output
+    n_chunks = max(1, min(ring_chunks, T // 1024))
+    cuts = [T * c // n_chunks for c in range(n_chunks + 1)]
+
+    def ring_step(p):
+        # runs on the side stream: wait for this pass's GEMMs, take over the running output, add our experts, pass it on
+        with torch.cuda.stream(side):
+            side.wait_event(y_ready[p])
+            for c in range(n_chunks):
+                t0, t1 = cuts[c], cuts[c + 1]
+                out = outs[p, t0:t1]
+                channel = (p * n_chunks + c) % 8
+                if prev_rank is not None:
+                    if symm is not None:
+                        symm[1].wait_signal(rank - 1, channel, 120000)
+                    else:
+                        dist.recv(out, src=prev_rank, group=recv_group)
+                dst = peer_outs[p, t0:t1] if (symm is not None and next_rank is not None) else out
+                L.check(L.lib().b200q_moe_combine_acc(L.ptr(ys[p]), L.ptr(parent.rows[t0:t1]), L.ptr(parent.pw[t0:t1]), t1 - t0, parent.k, H,
+                                                      L.ptr(out) if prev_rank is not None else None, L.ptr(dst), L.stream_ptr(dev)))
+                if next_rank is not None:
+                    if symm is not None:
+                        symm[1].put_signal(rank + 1, channel, 120000)
+                    else:
+                        sends.append(dist.isend(out, dst=next_rank, group=send_group))
+            if next_rank is None and p > 0:
+                sq_err_accumulate(outs[0], outs[p], acc[p - 1:p])
+
+    parent.project(w13, ys[0])
+    y_ready[0].record(main)
+    ring_step(0)
+    per_ratio = w13.numel() * w13.element_size()
+    chunk = max(1, min(n_grid, int(max_variant_bytes // max(per_ratio, 1))))
+    for r0 in range(0, n_grid, chunk):
+        r1 = min(n_grid, r0 + chunk)
+        variants = workspace.get("moe_w13", (r1 - r0, E, 2 * I, H), w13.dtype, dev)
+        vflat = variants.view(r1 - r0, E * 2 * I, H)
+        for q0 in range(0, flat.shape[0], rows_per_call):
+            scaled_fake_quantize_grid(flat[q0:q0 + rows_per_call], scales[r0:r1], args, vflat[:, q0:q0 + rows_per_call])
+        for r in range(r0, r1):
+            parent.project(variants[r - r0], ys[1 + r])
+            y_ready[1 + r].record(main)
+            ring_step(1 + r)
+    main.wait_stream(side)
+    for w in sends:
+        w.wait()
+    if next_rank is None:
+        acc[n_grid:].fill_(float(T * H))
+    best_i, losses = reduce_and_select(acc, process_group, True)
+    return scales[best_i].cpu(), ratios[best_i], losses
+
+
+_EP_SIDE = {}
+_RING_GROUPS = {}
+_EP_SYMM = {}
+
+
+def _ep_symm_buffer(numel: int, dtype, dev, process_group):
+    """(tensor, handle) of a symmetric-memory buffer of ``numel`` elements shared by the ranks of ``process_group`` (collective; cached
+    per group, re-made when the size changes), or None when the ranks cannot map each other's memory -- the caller then uses NCCL
+    send/recv.  Every rank takes the same branch: the outcome is agreed with a MIN all-reduce."""
+    import torch.distributed as dist
+
+    key = id(process_group)
+    hit = _EP_SYMM.get(key)
+    if hit is not None and hit[0].numel() == numel and hit[0].dtype == dtype:
+        return hit
+    _EP_SYMM.pop(key, None)
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    t = hdl = None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        t = symm_mem.empty((numel,), dtype=dtype, device=dev)
+    except Exception:
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+    if int(ok.item()) == 0:
+        return None
+    try:
+        hdl = symm_mem.rendezvous(t, process_group)
+        if hdl.world_size != dist.get_world_size(process_group) or hdl.rank != dist.get_rank(process_group):
+            raise RuntimeError("symmetric memory group mismatch")
+    except Exception:
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+    if int(ok.item()) == 0:
+        return None
+    _EP_SYMM[key] = (t, hdl)
+    return _EP_SYMM[key]
+
+
+def _ring_groups(process_group):
+    """Two extra process groups over the ranks of ``process_group`` (created once, collectively, in the same order on every rank)."""
+    import torch.distributed as dist
+
+    key = id(process_group)
+    if key not in _RING_GROUPS:
+        ranks = dist.get_process_group_ranks(process_group)
+        _RING_GROUPS[key] = (dist.new_group(ranks=ranks), dist.new_group(ranks=ranks))
+    return _RING_GROUPS[key]
+
+
+def _ep_side_stream(dev) -> "torch.cuda.Stream":
+    key = torch.device(dev).index
+    if key not in _EP_SIDE:
+        _EP_SIDE[key] = torch.cuda.Stream(dev)
+    return _EP_SIDE[key]

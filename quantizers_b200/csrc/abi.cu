@@ -426,7 +426,12 @@ int b200q_awq_scaled_fake_quantize_grid(const void* weight, int64_t rows, int64_
 }
 int b200q_moe_combine(const void* y, const int32_t* row, const void* weight, int64_t tokens, int32_t top_k, int64_t hidden, void* out, void* stream) {
     REQ_PTR(y); REQ_PTR(row); REQ_PTR(weight); REQ_PTR(out);
-    return launch_moe_combine(y, row, weight, tokens, top_k, hidden, out, (cudaStream_t)stream);
+    return launch_moe_combine(y, row, weight, tokens, top_k, hidden, nullptr, out, (cudaStream_t)stream);
+}
+int b200q_moe_combine_acc(const void* y, const int32_t* row, const void* weight, int64_t tokens, int32_t top_k, int64_t hidden, const void* init,
+                          void* out, void* stream) {
+    REQ_PTR(y); REQ_PTR(row); REQ_PTR(weight); REQ_PTR(out);
+    return launch_moe_combine(y, row, weight, tokens, top_k, hidden, init, out, (cudaStream_t)stream);
 }
 int b200q_sq_err_accumulate(const void* y_ref, const void* y_q, int64_t numel, int32_t dtype, float* acc, void* stream) {
     REQ_PTR(y_ref); REQ_PTR(y_q); REQ_PTR(acc);

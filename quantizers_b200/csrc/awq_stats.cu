@@ -247,16 +247,24 @@ int launch_awq_scales(const float* x_mean, const float* w_mean, int64_t k, const
 }
 
 // ---- routed MoE block output (W2 of the layer-wide MoE mapping): out[t] = sum_j bf16(y[row[t, j]] * w[t, j]) accumulated in bf16,
-// j in ascending expert order -- exactly the rounding sequence of transformers' per-expert ``index_add_`` into a bf16 tensor
+// j in ascending expert order -- exactly the rounding sequence of transformers' per-expert ``index_add_`` into a bf16 tensor.
+// `init` (may alias `out`): the running sum of the experts that come BEFORE this call's in that order (expert-parallel ring: rank r
+// continues the sequence rank r - 1 left off); null = the reference's zero-initialised output.
 __global__ void __launch_bounds__(256) moe_combine_kernel(const uint16_t* __restrict__ y, const int32_t* __restrict__ row, const uint16_t* __restrict__ w,
-                                                          int64_t tokens, int top_k, int64_t h, uint16_t* __restrict__ out) {
+                                                          int64_t tokens, int top_k, int64_t h, const uint16_t* init, uint16_t* out) {
     const int64_t chunks = h / 8;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= tokens * chunks) return;
     const int64_t t = i / chunks, c = i - t * chunks;
     float acc[8];
+    if (init != nullptr) {
+        Chunk8<DT_BF16> ch;
+        load_chunk<DT_BF16>(ch, init, t * h + c * 8);
+        chunk_to_float<DT_BF16>(ch, acc);
+    } else {
 #pragma unroll
-    for (int e = 0; e < 8; e++) acc[e] = 0.0f;
+        for (int e = 0; e < 8; e++) acc[e] = 0.0f;
+    }
     for (int j = 0; j < top_k; j++) {
         const int32_t r = row[t * top_k + j];
         if (r < 0) continue;
@@ -270,11 +278,13 @@ __global__ void __launch_bounds__(256) moe_combine_kernel(const uint16_t* __rest
     }
     store_chunk_T<DT_BF16>(out, t * h + c * 8, acc);
 }
-int launch_moe_combine(const void* y, const int32_t* row, const void* w, int64_t tokens, int top_k, int64_t h, void* out, cudaStream_t st) {
+int launch_moe_combine(const void* y, const int32_t* row, const void* w, int64_t tokens, int top_k, int64_t h, const void* init, void* out,
+                       cudaStream_t st) {
     B200Q_REQUIRE(h % 8 == 0 && top_k >= 1, "moe_combine: hidden size must be a multiple of 8");
     if (tokens == 0) return B200Q_OK;
     const int64_t n = tokens * (h / 8);
-    moe_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint16_t*)y, row, (const uint16_t*)w, tokens, top_k, h, (uint16_t*)out);
+    moe_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint16_t*)y, row, (const uint16_t*)w, tokens, top_k, h,
+                                                                    (const uint16_t*)init, (uint16_t*)out);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }

@@ -111,7 +111,8 @@ int launch_abs_sum_cols(int dt, const void* x, int64_t tokens, int64_t k, float*
 int launch_wmean(int dt, const void* w, int64_t rows, int64_t cols, int group, double* acc, cudaStream_t st);
 int launch_awq_scales(const float* x_mean, const float* w_mean, int64_t k, const float* ratios, int n_ratios, int duo,
                       float* scales, cudaStream_t st);
-int launch_moe_combine(const void* y, const int32_t* row, const void* w, int64_t tokens, int top_k, int64_t h, void* out, cudaStream_t st);
+int launch_moe_combine(const void* y, const int32_t* row, const void* w, int64_t tokens, int top_k, int64_t h, const void* init, void* out,
+                       cudaStream_t st);
 int launch_sq_err(int dt, const void* a, const void* b, int64_t n, float* acc, cudaStream_t st);
 
 }  // namespace b200q

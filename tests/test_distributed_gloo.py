@@ -137,3 +137,61 @@ def test_reduce_and_select_first_minimum_and_failure():
     assert i == 1 and losses == [0.3, 0.1, 0.1, 0.2]
     with pytest.raises(RuntimeError):
         awq.reduce_and_select(torch.tensor([float("nan"), float("inf"), 4.0]), distributed=False)
+
+
+# ------------------------------------------------------------------------------------------------ expert-parallel ring
+def _ring_problem():
+    g = torch.Generator().manual_seed(11)
+    T, E, K, H = 96, 9, 3, 16
+    contrib = (torch.randn(T, E, H, generator=g) * 3).to(torch.bfloat16)          # expert e's weighted output for token t
+    topk = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(T)])   # routing: K distinct experts per token
+    x = torch.randn(T, 5, generator=g)
+    return T, E, K, H, contrib, topk, x
+
+
+def _index_add_reference(T, H, contrib, topk, experts, start=None):
+    """transformers' sparse-MoE block: ``final.index_add_(0, tokens_of_e, out_e)`` per expert in ascending order, bf16 tensor."""
+    final = torch.zeros(T, H, dtype=torch.bfloat16) if start is None else start.clone()
+    for e in experts:
+        tok = (topk == e).any(dim=1).nonzero().squeeze(1)
+        if tok.numel():
+            final.index_add_(0, tok, contrib[tok, e])
+    return final
+
+
+def _ring_worker(rank, world):
+    """Each rank owns an ascending expert range and a token shard of unequal length; shards are all-gathered, the running output
+    travels 0 -> 1 -> ... -> N-1 (the exchange of awq.search_moe_block_mapping_ep with gloo send/recv)."""
+    from quantizers_b200 import awq
+    from quantizers_b200.scheduler import partition
+
+    T, E, K, H, contrib, topk, x = _ring_problem()
+    cuts = [0, 40, 96] if world == 2 else [0, 17, 50, 96]
+    mine = slice(cuts[rank], cuts[rank + 1])
+    x_all = awq._all_gather_rows(x[mine].contiguous(), dist.group.WORLD)
+    topk_all = awq._all_gather_rows(topk[mine].contiguous(), dist.group.WORLD)
+    assert torch.equal(x_all, x) and torch.equal(topk_all, topk)
+    experts = partition(E, world, rank)
+    running = None
+    if rank > 0:
+        running = torch.empty(T, H, dtype=torch.bfloat16)
+        dist.recv(running, src=rank - 1)
+    running = _index_add_reference(T, H, contrib, topk_all, experts, running)
+    if rank + 1 < world:
+        dist.send(running, dst=rank + 1)
+        return None
+    return running.view(torch.int16).tolist()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_expert_parallel_ring_reproduces_the_unsharded_rounding_sequence(world):
+    T, E, K, H, contrib, topk, _ = _ring_problem()
+    want = _index_add_reference(T, H, contrib, topk, range(E))
+    res = _run(_ring_worker, world)
+    got = torch.tensor(res[-1][1], dtype=torch.int16).view(torch.bfloat16)
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+    # the alternative exchange -- fp32 sum of per-rank partial outputs, rounded once -- is a different function
+    from quantizers_b200.scheduler import partition
+
+    parts = sum(_index_add_reference(T, H, contrib, topk, partition(E, world, r)).float() for r in range(world))
+    assert not torch.equal(parts.to(torch.bfloat16).view(torch.int16), want.view(torch.int16))

@@ -323,6 +323,38 @@ def test_search_moe_block_mapping_matches_oracle():
         assert torch.allclose(s, s_ref, rtol=1e-5)
 
 
+def test_routed_moe_expert_ranges_chain_to_the_single_gpu_output():
+    """The expert-parallel layer-wide mapping (awq.search_moe_block_mapping_ep) on one device: ranks own ascending expert ranges, rank r
+    continues rank r - 1's running bf16 output with b200q_moe_combine_acc.  Chaining the ranges (2, 3 and 6 "ranks", one range holding a
+    never-routed expert, one rank possibly holding no routed pair of some token) must reproduce the single-GPU block output bit for bit;
+    summing per-range outputs in fp32 and rounding once -- what a reduce-scatter would do -- must not (that is why the ring exists)."""
+    from quantizers_b200 import awq
+
+    E, T, H, I, K = 6, 640, 256, 384, 3
+    g = torch.Generator().manual_seed(29)
+    x = (torch.randn(T, H, generator=g) * (1 + 3 * torch.rand(H, generator=g))).to(torch.bfloat16).cuda()
+    w13 = (torch.randn(E, 2 * I, H, generator=g) * 0.05).to(torch.bfloat16).cuda()
+    w2 = (torch.randn(E, H, I, generator=g) * 0.05).to(torch.bfloat16).cuda()
+    logits = torch.randn(T, E, generator=g)
+    logits[:, 4] = -1e9                                           # expert 4 is never routed
+    p = torch.softmax(logits, dim=-1)
+    topk_w, topk_idx = torch.topk(p, K, dim=-1)
+    topk_w, topk_idx = (topk_w / topk_w.sum(-1, keepdim=True)).cuda(), topk_idx.cuda()
+    want = awq.RoutedMoE(x, w2, topk_idx, topk_w)(w13)
+    for world in (2, 3, 6):
+        per = E // world
+        running, partial_sum = None, torch.zeros(T, H, dtype=torch.float32, device="cuda")
+        for r in range(world):
+            e0 = r * per
+            part = awq.RoutedMoE(x, w2[e0:e0 + per], topk_idx, topk_w, expert_offset=e0)
+            y = part.project(w13[e0:e0 + per].contiguous())
+            partial_sum += part.combine(y.clone()).float()
+            running = part.combine(y, out=running if running is not None else None, init=running)
+        assert_bits_equal(running, want.cpu(), f"ring of {world}")
+        if world == 2:
+            assert not torch.equal(partial_sum.to(torch.bfloat16), want)
+
+
 def test_gptq_hessian_accumulation():
     """§8f rank 4: H = H n/(n+t) + (2/(n+t)) X^T X over three batches (one with a row count that is not a multiple of 8) on the
     tcgen05 fp32-accumulate epilogue against the restated fp32 reference.  Floating point: 2e-5 of max|H| (fp32 summation order)."""
