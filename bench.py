@@ -589,16 +589,17 @@ def run_moe_block(args, dev, world, rank, peak):
 
 # ----------------------------------------------------------------------------- strong-scaling headline, GLM leg, parity
 def run_headline_strong(args, dev, world, rank, peaks):
-    """The headline job with a FIXED size: the 36 decoder layers of Qwen3-4B partitioned over the ranks (scheduler.partition,
-    4.5 layers per GPU at N = 8, no data-path collective).  One step = this rank's layers; the 7 launches of a step are captured
+    """The headline job with a FIXED size: the matrices of the 36 decoder layers of Qwen3-4B partitioned over the ranks at (class,
+    layer) granularity, balanced by elements (scheduler.partition_balanced; whole layers would be 5 / 4 per GPU at N = 8, i.e. at
+    best 7.2x; no data-path collective).  One step = this rank's layers; the 7 launches of a step are captured
     once in a CUDA graph and replayed (at N = 8 a step is ~0.2 ms of kernels, launch-bound otherwise)."""
     import torch.distributed as dist
 
     from quantizers_b200 import scheduler as S
 
-    layers = S.partition(36, world, rank)
-    spec = S.qwen3_4b(layers=len(layers))
-    arena = S.build_arena(spec, list(layers), dev)
+    spec = S.qwen3_4b(layers=1)
+    mine = S.partition_balanced(spec, 36, world)[rank]        # {class: [layers]}: balanced by elements (whole layers: 5 / 4 at N = 8)
+    arena = S.build_arena_classes(spec, mine, dev)
     outs = S.alloc_outputs(spec, arena)
     for _ in range(3):
         S.quantize_arena(spec, arena, out=outs)
@@ -623,10 +624,11 @@ def run_headline_strong(args, dev, world, rank, peaks):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     total = 36 * S.qwen3_4b(layers=1).unit_bytes()
-    alg = sum(S.PRESETS[m.preset].bytes_per_element() * m.rows * m.cols * m.per_unit for m in spec.matrices) * len(layers)
+    alg = sum(S.PRESETS[m.preset].bytes_per_element() * m.rows * m.cols * m.per_unit * len(mine.get(m.name, ())) for m in spec.matrices)
     peak = float(peaks.get("hbm_gbs", 6650.0))
     return {"metric": METRIC, "value": total / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "scaling": "strong", "steps": steps,
-            "config": {"workload": "qwen3-4b mixed FP8_BLOCK + INT4 g128 asym, 36 layers partitioned over the ranks", "layers_per_gpu": len(layers),
+            "config": {"workload": "qwen3-4b mixed FP8_BLOCK + INT4 g128 asym, the 36 layers' matrices partitioned over the ranks by (class, layer), balanced by elements",
+                       "matrices_per_gpu": {k: len(v) for k, v in mine.items()},
                        "launch": "one CUDA graph replay per step"},
             "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "note": "whole step (all 5 classes) of the slowest rank"}}
@@ -654,14 +656,22 @@ def run_glm(args, dev, world, rank, peaks):
         for _ in range(3):
             S.quantize_arena(spec, arena, out=outs)
         torch.cuda.synchronize()
+        # one CUDA graph replay per step, like the strong headline leg: at N = 8 a step is ~0.1 ms of kernels in 4 launches
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            S.quantize_arena(spec, arena, out=outs)
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.moe_steps):
-            S.quantize_arena(spec, arena, out=outs)
+            graph.replay()
         e1.record()
         torch.cuda.synchronize()
+        del graph
         ms = torch.tensor([e0.elapsed_time(e1) / args.moe_steps], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -670,7 +680,8 @@ def run_glm(args, dev, world, rank, peaks):
         alg = S.PRESETS[preset].bytes_per_element() * len(units) * spec.unit_elements()
         out[preset.lower()] = {"metric": METRIC, "value": total / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "scaling": "strong",
                                "config": {"workload": f"glm-4.7-flash shapes {preset}: gate/up [1536,2048] x2, down [2048,1536], dense [10240,2048], "
-                                                      "ragged [2624,2048] per unit", "units": args.glm_units, "units_per_gpu": len(units)},
+                                                      "ragged [2624,2048] per unit", "units": args.glm_units, "units_per_gpu": len(units),
+                                          "launch": "one CUDA graph replay per step"},
                                "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                             "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None}}
         del arena, outs
@@ -782,6 +793,20 @@ def run_parity(args, dev, world, rank):
                 ref[layer, mi] = sum(_checksum(o[m.name][k][sl]) for k in keys if k in o[m.name])
         res["rtn_layer_sharded_eq_unsharded"] = bool(torch.equal(ref, sums))
         del o
+    # ---- the same 8 layers partitioned at (class, layer) granularity (the strong-scaling headline's partition)
+    sums = torch.zeros(n_layers, len(spec1.matrices), dtype=torch.int64, device=dev)
+    mine_c = S.partition_balanced(spec1, n_layers, world)[rank]
+    if mine_c:
+        o = S.quantize_arena(spec1, S.build_arena_classes(spec1, mine_c, dev))
+        for mi, m in enumerate(spec1.matrices):
+            for li, layer in enumerate(mine_c.get(m.name, ())):
+                sl = slice(li * m.per_unit, (li + 1) * m.per_unit)
+                sums[layer, mi] = sum(_checksum(o[m.name][k][sl]) for k in keys if k in o[m.name])
+        del o
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        res["rtn_class_balanced_eq_unsharded"] = bool(torch.equal(ref, sums))
     # ---- NVFP4, 16 experts of one layer partitioned by expert (gate/up siblings stay together)
     n_exp = 16
     sums = torch.zeros(n_exp, 2, dtype=torch.int64, device=dev)
@@ -845,7 +870,7 @@ def run_parity(args, dev, world, rank):
     if rank == 0:
         if world > 1:
             res["ok_moe_mapping"] = bool(res["moe_mapping_expert_parallel_same_argmin"] and res["moe_mapping_expert_parallel_max_rel_loss_diff"] < 1e-3)
-        res["ok"] = bool(res.get("ok_moe_mapping", True) and res["rtn_layer_sharded_eq_unsharded"] and res["nvfp4_expert_sharded_eq_unsharded"] and res["awq_token_sharded_same_argmin"]
+        res["ok"] = bool(res.get("ok_moe_mapping", True) and res["rtn_class_balanced_eq_unsharded"] and res["rtn_layer_sharded_eq_unsharded"] and res["nvfp4_expert_sharded_eq_unsharded"] and res["awq_token_sharded_same_argmin"]
                          and res["awq_token_sharded_max_rel_loss_diff"] < 1e-3)
         res["world_size"] = world
     return res

@@ -122,6 +122,51 @@ def partition(n_units: int, world_size: int, rank: int) -> range:
     return range(start, start + base + (1 if rank < extra else 0))
 
 
+def partition_balanced(spec: ModelSpec, n_units: int, world_size: int) -> List[Dict[str, List[int]]]:
+    """Strong-scaling partition at (matrix class, unit) granularity, balanced by elements: per rank {class name: [unit ids]}.
+
+    ``partition`` hands out whole units; 36 layers over 8 ranks is 5 / 4 layers, i.e. at best 7.2x.  The classes of a unit are
+    independent (RTN: no data-path exchange), so they can go to different ranks: items are sorted by size and each goes to the
+    least-loaded rank (LPT; deterministic, identical on every rank).  Classes whose NVFP4 siblings share min(global_scale) across
+    classes (``fuse_group``) stay on one rank."""
+    if world_size < 1:
+        raise ValueError(f"bad world_size {world_size}")
+    groups: Dict[str, List[MatrixSpec]] = {}
+    for m in spec.matrices:
+        a = PRESETS[m.preset]
+        tied = m.fuse_group is not None and a.type == "float" and a.num_bits == 4
+        groups.setdefault(m.fuse_group if tied else m.name, []).append(m)
+    items = []
+    for gname, members in groups.items():
+        wgt = sum(m.rows * m.cols * m.per_unit for m in members)
+        items.extend((wgt, gname, u) for u in range(n_units))
+    items.sort(key=lambda t: (-t[0], t[1], t[2]))
+    load = [0] * world_size
+    assign: List[Dict[str, List[int]]] = [{} for _ in range(world_size)]
+    for wgt, gname, u in items:
+        r = min(range(world_size), key=lambda i: (load[i], i))
+        load[r] += wgt
+        for m in groups[gname]:
+            assign[r].setdefault(m.name, []).append(u)
+    for a in assign:
+        for units in a.values():
+            units.sort()
+    return assign
+
+
+def build_arena_classes(spec: ModelSpec, units_by_class: Dict[str, Sequence[int]], device, dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
+    """``build_arena`` with a separate unit list per matrix class (``partition_balanced``); classes without units are left out --
+    ``alloc_outputs`` / ``quantize_arena`` skip them."""
+    arena = {}
+    for mi, m in enumerate(spec.matrices):
+        units = list(units_by_class.get(m.name, ()))
+        if not units:
+            continue
+        stacks = [synth_stack(units, m.rows, m.cols, mi * 8 + j, device, dtype) for j in range(m.per_unit)]
+        arena[m.name] = torch.stack(stacks, dim=1).reshape(len(units) * m.per_unit, m.rows, m.cols) if m.per_unit > 1 else stacks[0]
+    return arena
+
+
 def owner_of(unit: int, n_units: int, world_size: int) -> int:
     base, extra = divmod(n_units, world_size)
     cut = extra * (base + 1)
@@ -217,7 +262,7 @@ def alloc_outputs(spec: ModelSpec, arena: Dict[str, torch.Tensor]) -> Dict[str, 
     from . import ops
 
     return {m.name: ops.compress_outputs(arena[m.name].shape, PRESETS[m.preset], arena[m.name].dtype, arena[m.name].device,
-                                         fuse_span=_nvfp4_span(spec, m)) for m in spec.matrices}
+                                         fuse_span=_nvfp4_span(spec, m)) for m in spec.matrices if m.name in arena}
 
 
 def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Optional[list] = None,
@@ -234,7 +279,7 @@ def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Opt
 
     res = {}
     fused_gs: Dict[str, torch.Tensor] = {}
-    nv = [m for m in spec.matrices if PRESETS[m.preset].type == "float" and PRESETS[m.preset].num_bits == 4]
+    nv = [m for m in spec.matrices if m.name in arena and PRESETS[m.preset].type == "float" and PRESETS[m.preset].num_bits == 4]
     groups = {}
     for m in nv:
         groups.setdefault(m.fuse_group or m.name, []).append(m)
@@ -254,6 +299,8 @@ def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Opt
         for m in members:
             fused_gs[m.name] = per_unit_min.repeat_interleave(m.per_unit).contiguous()
     for m in spec.matrices:
+        if m.name not in arena:        # a class this rank holds no unit of (partition_balanced)
+            continue
         w = arena[m.name]
         args = PRESETS[m.preset]
         ev = None

@@ -64,6 +64,32 @@ def test_partition_covers_all_units_once():
         partition(4, 2, 2)
 
 
+def test_partition_balanced_covers_every_class_unit_once_and_balances_elements():
+    from quantizers_b200 import scheduler as S
+
+    for spec, n in ((S.qwen3_4b(layers=1), 36), (S.glm47_flash(units=1), 48), (S.qwen3_30b_a3b(layers=1, experts=1), 16)):
+        sizes = {m.name: m.rows * m.cols * m.per_unit for m in spec.matrices}
+        for w in (1, 2, 3, 5, 8):
+            parts = S.partition_balanced(spec, n, w)
+            assert len(parts) == w
+            for m in spec.matrices:
+                seen = sorted(u for p in parts for u in p.get(m.name, ()))
+                assert seen == list(range(n)), (spec.name, m.name, w)
+            loads = [sum(sizes[k] * len(v) for k, v in p.items()) for p in parts]
+            assert max(loads) - min(loads) <= max(sizes.values())          # LPT: within one largest item
+            assert parts == S.partition_balanced(spec, n, w)                # deterministic: every rank computes the same table
+    # NVFP4 siblings that share a global scale ACROSS classes stay on one rank
+    tied = S.ModelSpec("t", 4, "layer", [S.MatrixSpec("q", 64, 64, "NVFP4", 1, "qkv"), S.MatrixSpec("kv", 32, 64, "NVFP4", 2, "qkv"),
+                                         S.MatrixSpec("o", 64, 64, "NVFP4")])
+    for p in S.partition_balanced(tied, 4, 3):
+        assert p.get("q", []) == p.get("kv", [])
+    # Qwen3-4B on 8 ranks: whole layers give 5 / 4 (max / mean = 1.11); the class partition is within 0.5 %
+    spec = S.qwen3_4b(layers=1)
+    sizes = {m.name: m.rows * m.cols * m.per_unit for m in spec.matrices}
+    loads = [sum(sizes[k] * len(v) for k, v in p.items()) for p in S.partition_balanced(spec, 36, 8)]
+    assert max(loads) / (sum(loads) / 8) < 1.005
+
+
 def _stats_worker(rank, world):
     from quantizers_b200.scheduler import allreduce_stats
 
