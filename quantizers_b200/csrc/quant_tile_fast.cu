@@ -549,7 +549,14 @@ static __device__ __noinline__ uint2 fix_group16_fp4(const uint4 a, const uint4 
     return packed;
 }
 
-// one 16-element group (two 128-bit words of bf16): scale code + packed e2m1 out
+// one 16-element group (two 128-bit words of bf16): scale code + packed e2m1 out.
+// Why the bracket (two evaluations) stays while the INT4 kernels got away with one: there x and s are both bf16, so x / s is a ratio of
+// two 8-bit significands and can never come closer than 2^-17 to a rounding boundary.  Here s_eff = fp32(e4m3 / gs) is an arbitrary fp32
+// number; with gs a bf16 value the IDEAL quotient x * gs / c (X, G 8-bit, C 4-bit significands) either misses every e2m1 boundary
+// n * 2^j (n in 1, 3, 5, 7) by >= 2^-16 or hits it exactly (X * G == n * C * 2^j -- common: G = 128, or 3 | G with C = 12, ...).  In the
+// exact-hit case the reference's fp32(x / s_eff) lands on the boundary or one ulp to either side depending on the rounding error of
+// s_eff, i.e. on the table entry AND on n; no single multiplier reproduces all of those outcomes (an exact tie needs |c * r / gs - 1| <
+// 2^-25).  The bracket detects exactly these elements (the two ends straddle the boundary) and sends them to the IEEE chain.
 template <bool FMA>
 __device__ __forceinline__ void fp4_compress_group(const uint4 r0, const uint4 r1, uint32_t table_smem, float gs, uint8_t* sp, uint2* op) {
     uint32_t m = hmaxabs2(hmaxabs2(hmaxabs2(r0.x, r0.y), hmaxabs2(r0.z, r0.w)), hmaxabs2(hmaxabs2(r1.x, r1.y), hmaxabs2(r1.z, r1.w)));

@@ -6,6 +6,6 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127
 echo "rc=$?"; tail -5 gpurun_out/r2/bench_n$N.err
 python -c "
 import json
-d=json.load(open('gpurun_out/r2/bench_n$N.json')); print(json.dumps(d['legs'])); print(d['parity']); print(d['e2e'])
+d=[json.loads(l) for l in open('gpurun_out/r2/bench_n$N.json') if l.startswith('{\"metric\"')][-1]; print(json.dumps(d['legs'])); print(d['parity']); print(d['e2e'])
 "
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 5 --warmup 1 --cpu-awq-tokens 0 > gpurun_out/r2/bench_ref_n$N.json 2> gpurun_out/r2/bench_ref_n$N.err; echo "ref rc=$?"; head -c 400 gpurun_out/r2/bench_ref_n$N.json
