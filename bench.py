@@ -58,6 +58,37 @@ class ClockSampler:
         self._t = None
 
     def start(self):
+        # NVML in-process (nvidia_ml_py): a sample costs ~0.1 ms, so even a 30 ms timed region (20 steps) gets tens of samples;
+        # `nvidia-smi -lms` needs ~0.5 s to print its first line and often missed the region altogether.  Same counters as the recipe's
+        # nvidia-smi line (clocks.sm, clocks.max.sm, power.draw, clocks_event_reasons.*); nvidia-smi stays as the fallback.
+        try:
+            import pynvml as N
+
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            self._stop = threading.Event()
+
+            def rd():
+                while not self._stop.is_set():
+                    try:
+                        sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                        r = int(get_reasons(h))
+                        pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    except Exception:
+                        break
+                    f = [str(sm), str(mx), f"{pw:.1f}"] + ["Active" if r & bits[n] else "Not Active"
+                                                          for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
+                    self.samples.append((time.time(), ", ".join(f)))
+                    time.sleep(0.001)
+
+            self._t = threading.Thread(target=rd, daemon=True)
+            self._t.start()
+            return
+        except Exception:
+            self._stop = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("B200Q_BENCH_LMS", "50"),
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -76,6 +107,10 @@ class ClockSampler:
         self.marks[name] = time.time()
 
     def stop(self):
+        if getattr(self, "_stop", None) is not None:
+            self._stop.set()
+            if self._t is not None:
+                self._t.join(timeout=1)
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -99,7 +134,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if getattr(self, "_stop", None) is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- reference / CPU baseline
@@ -438,8 +473,17 @@ def run_moe_nvfp4(args, dev, world, rank, peaks):
     spec = S.qwen3_30b_a3b(layers=1, experts=len(units))
     arena = S.build_arena(spec, units, dev)
     nbytes_total = args.moe_layers * 128 * spec.unit_bytes()
+    outs = S.alloc_outputs(spec, arena)                  # caller-owned outputs: a step allocates nothing
     for _ in range(3):
-        S.quantize_arena(spec, arena)
+        S.quantize_arena(spec, arena, out=outs)
+    torch.cuda.synchronize()
+    # one CUDA graph replay per step (two kernel launches + their sync-word memsets), like the other strong legs: at N = 8 a step is
+    # 0.3 ms of kernels
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        S.quantize_arena(spec, arena, out=outs, concurrent=args.concurrent_classes)
+    for _ in range(3):
+        graph.replay()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -447,9 +491,10 @@ def run_moe_nvfp4(args, dev, world, rank, peaks):
     steps = args.moe_steps
     e0.record()
     for _ in range(steps):
-        S.quantize_arena(spec, arena)
+        graph.replay()
     e1.record()
     torch.cuda.synchronize()
+    del graph
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -464,7 +509,7 @@ def run_moe_nvfp4(args, dev, world, rank, peaks):
                        "experts_per_layer": 128, "experts_per_gpu_per_layer": len(experts), "bytes_total": nbytes_total,
                        "l2": f"inputs ({len(units) * spec.unit_bytes() / 1e9:.2f} GB/step/GPU) larger than the 126 MB L2"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "kernel": "nvfp4_fused_kernel (|max| -> global scale -> compress, one launch per stack)",
+                         "kernel": "nvfp4_fused2_kernel (|max| -> global scale -> compress, one launch per stack; one CUDA graph replay per step)",
                          "alg_bytes_per_element": a.bytes_per_element(), "note": "per-GPU figure of the slowest rank"}}
 
 
@@ -606,7 +651,7 @@ def run_headline_strong(args, dev, world, rank, peaks):
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
-        S.quantize_arena(spec, arena, out=outs)
+        S.quantize_arena(spec, arena, out=outs, concurrent=args.concurrent_classes)
     for _ in range(3):
         graph.replay()
     torch.cuda.synchronize()
@@ -629,7 +674,7 @@ def run_headline_strong(args, dev, world, rank, peaks):
     return {"metric": METRIC, "value": total / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "scaling": "strong", "steps": steps,
             "config": {"workload": "qwen3-4b mixed FP8_BLOCK + INT4 g128 asym, the 36 layers' matrices partitioned over the ranks by (class, layer), balanced by elements",
                        "matrices_per_gpu": {k: len(v) for k, v in mine.items()},
-                       "launch": "one CUDA graph replay per step"},
+                       "launch": "one CUDA graph replay per step" + (", classes on concurrent streams" if args.concurrent_classes else "")},
             "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "note": "whole step (all 5 classes) of the slowest rank"}}
 
@@ -659,7 +704,7 @@ def run_glm(args, dev, world, rank, peaks):
         # one CUDA graph replay per step, like the strong headline leg: at N = 8 a step is ~0.1 ms of kernels in 4 launches
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            S.quantize_arena(spec, arena, out=outs)
+            S.quantize_arena(spec, arena, out=outs, concurrent=args.concurrent_classes)
         for _ in range(3):
             graph.replay()
         torch.cuda.synchronize()
@@ -892,6 +937,7 @@ def main():
     ap.add_argument("--moe-layers", type=int, default=8, help="layers of the Qwen3-30B-A3B NVFP4 expert-sharded leg (0 disables it)")
     ap.add_argument("--moe-steps", type=int, default=20)
     ap.add_argument("--moe-awq-experts", type=int, default=256, help="experts of the MiniMax-M2.1 per-expert AWQ leg (256 = one full layer; 0 disables it)")
+    ap.add_argument("--concurrent-classes", type=int, default=1, help="strong legs: launch the independent matrix classes of a step on side streams inside the captured graph")
     ap.add_argument("--moe-block-token-sharded", action="store_true", help="N > 1: round 1's token-sharded layer-wide mapping instead of the expert-parallel ring")
     ap.add_argument("--moe-block-experts", type=int, default=256, help="experts of the layer-wide MoE mapping leg (256 = the full MiniMax-M2.1 layer; 0 disables it)")
     ap.add_argument("--cpu-awq-tokens", type=int, default=1024, help="calibration tokens of the CPU AWQ baseline (whole layer; 0 disables it); "

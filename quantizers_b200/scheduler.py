@@ -265,8 +265,19 @@ def alloc_outputs(spec: ModelSpec, arena: Dict[str, torch.Tensor]) -> Dict[str, 
                                          fuse_span=_nvfp4_span(spec, m)) for m in spec.matrices if m.name in arena}
 
 
+_CLASS_STREAMS: Dict[int, list] = {}
+
+
+def _class_streams(device, n: int) -> list:
+    key = torch.device(device).index or 0
+    pool = _CLASS_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device))
+    return pool[:n]
+
+
 def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Optional[list] = None,
-                   out: Optional[Dict[str, dict]] = None) -> Dict[str, dict]:
+                   out: Optional[Dict[str, dict]] = None, concurrent: bool = False) -> Dict[str, dict]:
     """Fused observe -> qparams -> quantize -> pack for every stacked weight class of this rank's shard.
 
     ``out``: buffers from :func:`alloc_outputs`; results are written in place (no allocation, no host sync).
@@ -274,6 +285,9 @@ def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Opt
     NVFP4: siblings in one ``fuse_group`` of a unit share min(global_scale) (LLMC
     update_fused_layer_weight_global_scales); the per-tensor scales come from one batched reduction per class.
     ``timings``: when a list is given, (class name, preset, elements, start_event, end_event) is appended per launch.
+    ``concurrent``: the classes are independent, so each is launched on its own side stream (fork / join on events around the pass;
+    capturable in a CUDA graph): when a rank's stacks are small (strong scaling at N = 8: 20-200 us per launch) one launch's tail
+    overlaps the next one's ramp-up.  Needs ``out`` (no allocation on side streams) and no ``timings``.
     """
     from . import ops
 
@@ -298,6 +312,21 @@ def quantize_arena(spec: ModelSpec, arena: Dict[str, torch.Tensor], timings: Opt
             per_unit_min = gs if per_unit_min is None else torch.minimum(per_unit_min, gs)
         for m in members:
             fused_gs[m.name] = per_unit_min.repeat_interleave(m.per_unit).contiguous()
+    present = [m for m in spec.matrices if m.name in arena]
+    if concurrent and out is not None and timings is None and len(present) > 1:
+        dev = arena[present[0].name].device
+        cur = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for m, st in zip(present, _class_streams(dev, len(present))):
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                res[m.name] = ops.compress_weight(arena[m.name], PRESETS[m.preset], global_scale=fused_gs.get(m.name),
+                                                  fuse_span=span_of.get(m.name, 1), out=out[m.name])
+            join = torch.cuda.Event()
+            join.record(st)
+            cur.wait_event(join)
+        return res
     for m in spec.matrices:
         if m.name not in arena:        # a class this rank holds no unit of (partition_balanced)
             continue

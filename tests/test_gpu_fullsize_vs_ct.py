@@ -166,3 +166,32 @@ def test_arena_pass_equals_ct_on_a_layer():
         for j in range(m.per_unit):
             want = L.compress(arena[m.name][j], fmt, a)
             _same({k: (v[j] if k != "weight_shape" else v) for k, v in res[m.name].items()}, want, f"arena {m.name}[{j}]")
+
+
+@pytest.mark.parametrize("model", ["qwen3_4b", "qwen3_30b_a3b", "glm47_flash"])
+def test_concurrent_class_launches_and_graph_replay_equal_the_sequential_pass(model):
+    """What the strong-scaling bench legs time: the classes of a shard launched on side streams (fork / join), captured once in a CUDA
+    graph and replayed -- must leave the same bytes as the plain sequential pass, for the (class, unit)-balanced partition of rank 1 of 3."""
+    from quantizers_b200 import scheduler as S
+
+    spec = {"qwen3_4b": S.qwen3_4b(layers=1), "qwen3_30b_a3b": S.qwen3_30b_a3b(layers=1, experts=1), "glm47_flash": S.glm47_flash(units=1)}[model]
+    mine = S.partition_balanced(spec, 5, 3)[1]
+    arena = S.build_arena_classes(spec, mine, "cuda")
+    want = S.quantize_arena(spec, arena)
+    bufs = S.alloc_outputs(spec, arena)
+    S.quantize_arena(spec, arena, out=bufs, concurrent=True)      # warm-up outside the capture
+    torch.cuda.synchronize()
+    for b in bufs.values():
+        for k, v in b.items():
+            if torch.is_tensor(v) and v.is_cuda and not k.startswith("_"):
+                v.view(torch.uint8).zero_()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        S.quantize_arena(spec, arena, out=bufs, concurrent=True)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert set(want) == set(mine)
+    for name, w in want.items():
+        for k, v in w.items():
+            if torch.is_tensor(v) and v.is_cuda:
+                assert torch.equal(bufs[name][k].view(torch.uint8), v.view(torch.uint8)), (name, k)
