@@ -749,6 +749,15 @@ def search_moe_block_mapping_ep(x: torch.Tensor, w1: torch.Tensor, w3: torch.Ten
     recv_group, send_group = hop_groups[(rank - 1) % 2], hop_groups[rank % 2]
     E, I, H = w1.shape
     dev = x.device
+    # the ring order must be the expert order: rank r's range starts where rank r - 1's ends
+    span = torch.tensor([int(expert_offset), int(expert_offset) + E], dtype=torch.int64, device=dev)
+    spans = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(spans, span, group=process_group)
+    spans = spans.view(world, 2).tolist()
+    if any(b <= a for a, b in spans):
+        raise L.B200QError(f"search_moe_block_mapping_ep: every rank needs at least one expert, got ranges {spans}")
+    if spans[0][0] != 0 or any(spans[r][0] != spans[r - 1][1] for r in range(1, world)):
+        raise L.B200QError(f"search_moe_block_mapping_ep: expert ranges must be contiguous and ascending in rank order, got {spans}")
     # ---- every rank sees all tokens (activations are small next to the weights: T x H bf16)
     sizes = _gather_sizes(x.shape[0], dev, process_group)
     x = _all_gather_rows(x.contiguous(), process_group, sizes)
