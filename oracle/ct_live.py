@@ -163,6 +163,7 @@ FORMATS = {
     "int4_channel_sym": ("pack-quantized", "int", 4, True, "channel", None, None),
     "int4_channel_asym": ("pack-quantized", "int", 4, False, "channel", None, None),
     "int8_g128_sym": ("pack-quantized", "int", 8, True, "group", 128, None),
+    "int8_channel_sym": ("pack-quantized", "int", 8, True, "channel", None, None),
     "fp8_channel": ("float-quantized", "float", 8, True, "channel", None, None),
     "fp8_g32": ("float-quantized", "float", 8, True, "group", 32, None),
     "fp8_g128": ("float-quantized", "float", 8, True, "group", 128, None),

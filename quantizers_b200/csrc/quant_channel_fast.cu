@@ -1,5 +1,6 @@
 // quant_channel_fast.cu -- issue-tuned bf16 CHANNEL (one scale per row) fused compress: FP8 float-quantized (the FP8_DYNAMIC
-// preset's weights, CT:quantization/quant_scheme.py:367-382) and INT4 pack-quantized, symmetric or asymmetric.
+// preset's weights, CT:quantization/quant_scheme.py:367-382), INT4 pack-quantized, symmetric or asymmetric, and symmetric INT8
+// pack-quantized (the W8A8 presets' weights, CT:quantization/quant_scheme.py INT8_W8A8).
 //
 // The generic kernel (quant_tile.cu) spends one 256-thread CTA, four block-wide barriers and an IEEE division per element on a
 // row; measured 0.23 of the HBM roofline on 2560-column rows.  Here a row belongs to a TEAM of TW warps (1, 2, 4 or 8, picked so
@@ -19,7 +20,7 @@ using fp4::cvt_e4m3x2;
 
 constexpr int NC = 8;  // 16-byte chunks per lane
 
-template <int QT, bool SYM>
+template <int QT, bool SYM, int NB>
 __device__ __noinline__ uint2 repair_row_chunk(const uint4 raw, float s, float z, bool add_zp, bool all, uint2 packed) {
     const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
     Bracket br;
@@ -34,7 +35,10 @@ __device__ __noinline__ uint2 repair_row_chunk(const uint4 raw, float s, float z
         const float x = __uint_as_float(half);
         const bool differ = __float2bfloat16_rn(__fmul_rn(x, rl)) != __float2bfloat16_rn(__fmul_rn(x, rh));
         if (all || differ) {
-            if (QT == QT_INT) {
+            if (QT == QT_INT && NB == 8) {
+                const uint32_t c = (uint32_t)(quant_int<DT_BF16>(x, s, z, !SYM, -128.0f, 127.0f) + 128) & 0xffu;
+                o[e >> 2] = (o[e >> 2] & ~(0xffu << (8 * (e & 3)))) | (c << (8 * (e & 3)));
+            } else if (QT == QT_INT) {
                 const uint32_t c = (uint32_t)(quant_int<DT_BF16>(x, s, z, !SYM, -8.0f, 7.0f) + 8) & 0xfu;
                 o[0] = (o[0] & ~(0xfu << (4 * e))) | (c << (4 * e));
             } else {
@@ -46,7 +50,15 @@ __device__ __noinline__ uint2 repair_row_chunk(const uint4 raw, float s, float z
     return make_uint2(o[0], o[1]);
 }
 
-template <int QT, bool SYM, int TW>
+// round-to-nearest-even to a saturated signed byte, +128: one pack-quantized INT8 code (clamp to [-128, 127] then round == round then
+// saturate, the bounds being integers; NaN -> 0 like quant_int)
+__device__ __forceinline__ uint32_t cvt_s8_biased(float v) {
+    int32_t r;
+    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return (uint32_t)r;
+}
+
+template <int QT, bool SYM, int TW, int NB = 4>
 __global__ void __launch_bounds__(256, 4) channel_fast_kernel(const TileParams p, const int64_t total_rows) {
     constexpr int RPC = 8 / TW;  // rows per CTA
     constexpr int TL = TW * 32;  // lanes per team
@@ -104,7 +116,7 @@ __global__ void __launch_bounds__(256, 4) channel_fast_kernel(const TileParams p
     float s, z = 0.0f;
     Bracket br;
     if (ABS) {
-        s = div_const_bf16(__uint_as_float((st_a << 16) & 0x7fff0000u), QT == QT_INT ? 7.5f : 448.0f);
+        s = div_const_bf16(__uint_as_float((st_a << 16) & 0x7fff0000u), QT == QT_INT ? (NB == 8 ? 127.5f : 7.5f) : 448.0f);
         if (s == 0.0f) s = eps_of<DT_BF16>();
         br.init(s);
     } else {
@@ -138,7 +150,8 @@ __global__ void __launch_bounds__(256, 4) channel_fast_kernel(const TileParams p
     const bool add_zp = (QT == QT_FP8) ? (p.has_zp != 0) : true;
     const uint32_t z2 = (__float_as_uint(z) >> 16) * 0x10001u;
     const uint32_t kMagic = 0x43484348u, kUnbias = 0xbcc0bcc0u;  // bf16x2 (200, 200) / s16x2 (-0x4340): RNE, clamp [-8, 7], + 8
-    uint8_t* out_row = (uint8_t*)p.out + (QT == QT_FP8 ? row * p.cols : row * (p.cols >> 1));
+    constexpr bool BYTE = (QT == QT_FP8) || NB == 8;   // one output byte per element (INT8: four codes per int32 = plain byte order)
+    uint8_t* out_row = (uint8_t*)p.out + (BYTE ? row * p.cols : row * (p.cols >> 1));
 #pragma unroll
     for (int j = 0; j < NC; j++) {
         const int c = j * TL + tl;
@@ -149,7 +162,15 @@ __global__ void __launch_bounds__(256, 4) channel_fast_kernel(const TileParams p
         for (int k = 0; k < 4; k++) {
             const f32x2 x = bf16x2_to_f32x2_fma(w[k]);
             float al, ah, bl, bh;
-            if (QT == QT_INT) {
+            if (QT == QT_INT && NB == 8) {
+                // T(x / s) in bf16 like the reference, then RNE + clamp + 128 per element (the bf16 magic-number trick of the 4-bit
+                // path needs the sum to stay below 256)
+                unpack2(mul2(x, br.lo), al, ah);
+                unpack2(mul2(x, br.hi), bl, bh);
+                const uint32_t u = cvt_bf16x2(ah, al);
+                diff |= u ^ cvt_bf16x2(bh, bl);
+                h[k] = prmt(cvt_s8_biased(__uint_as_float(u << 16)), cvt_s8_biased(__uint_as_float(u & 0xffff0000u)), 0x0040);
+            } else if (QT == QT_INT) {
                 unpack2(mul2(x, br.lo), al, ah);
                 unpack2(mul2(x, br.hi), bl, bh);
                 uint32_t u = cvt_bf16x2(ah, al);
@@ -167,38 +188,41 @@ __global__ void __launch_bounds__(256, 4) channel_fast_kernel(const TileParams p
             }
         }
         uint2 packed;
-        if (QT == QT_INT) {
+        if (QT == QT_INT && NB == 8) {
+            packed = make_uint2(prmt(h[0], h[1], 0x5410) ^ 0x80808080u, prmt(h[2], h[3], 0x5410) ^ 0x80808080u);
+        } else if (QT == QT_INT) {
             const uint32_t x01 = prmt(h[0], h[1], 0x6420), x23 = prmt(h[2], h[3], 0x6420);
             packed = make_uint2(prmt(fold_nibbles(x01), fold_nibbles(x23), 0x6420), 0u);
         } else {
             packed = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
         }
-        if (diff != 0 || unsafe) packed = repair_row_chunk<QT, SYM>(raw[j], s, z, add_zp, unsafe, packed);
-        if (QT == QT_FP8) stg_stream(out_row + (int64_t)c * 8, packed);
+        if (diff != 0 || unsafe) packed = repair_row_chunk<QT, SYM, NB>(raw[j], s, z, add_zp, unsafe, packed);
+        if (BYTE) stg_stream(out_row + (int64_t)c * 8, packed);
         else stg_stream(out_row + (int64_t)c * 4, packed.x);
     }
 }
 
-template <int QT, bool SYM>
+template <int QT, bool SYM, int NB = 4>
 int launch_rows(const TileParams& p, int64_t total_rows, cudaStream_t st) {
     const int64_t cap = p.cols;
     auto grid = [&](int rpc) { return (unsigned)((total_rows + rpc - 1) / rpc); };
-    if (cap <= 2048) channel_fast_kernel<QT, SYM, 1><<<grid(8), 256, 0, st>>>(p, total_rows);
-    else if (cap <= 4096) channel_fast_kernel<QT, SYM, 2><<<grid(4), 256, 0, st>>>(p, total_rows);
-    else if (cap <= 8192) channel_fast_kernel<QT, SYM, 4><<<grid(2), 256, 0, st>>>(p, total_rows);
-    else channel_fast_kernel<QT, SYM, 8><<<grid(1), 256, 0, st>>>(p, total_rows);
+    if (cap <= 2048) channel_fast_kernel<QT, SYM, 1, NB><<<grid(8), 256, 0, st>>>(p, total_rows);
+    else if (cap <= 4096) channel_fast_kernel<QT, SYM, 2, NB><<<grid(4), 256, 0, st>>>(p, total_rows);
+    else if (cap <= 8192) channel_fast_kernel<QT, SYM, 4, NB><<<grid(2), 256, 0, st>>>(p, total_rows);
+    else channel_fast_kernel<QT, SYM, 8, NB><<<grid(1), 256, 0, st>>>(p, total_rows);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }
 
 }  // namespace
 
-// bf16 only; FP8 or INT4.  Returns B200Q_ENOSYS when the scheme / shape is not covered (the generic kernel takes over).
+// bf16 only; FP8, INT4 or symmetric INT8.  Returns B200Q_ENOSYS when the scheme / shape is not covered (the generic kernel takes over).
 int launch_channel_fast(int qt, const TileParams& p, int64_t batch, cudaStream_t st) {
     if (p.cols % 8 != 0 || p.cols > 8 * 2048 || (((uintptr_t)p.w) & 15) != 0 || (((uintptr_t)p.out) & 7) != 0) return B200Q_ENOSYS;
     const int64_t total_rows = batch * p.rows;
     if (total_rows * p.cols == 0 || total_rows >= (1ll << 31)) return B200Q_ENOSYS;
     if (qt == QT_FP8) return launch_rows<QT_FP8, true>(p, total_rows, st);
+    if (qt == QT_INT && p.nbits == 8 && p.symmetric) return launch_rows<QT_INT, true, 8>(p, total_rows, st);   // W8A8 weights
     if (qt != QT_INT || p.nbits != 4) return B200Q_ENOSYS;
     if (p.symmetric) return launch_rows<QT_INT, true>(p, total_rows, st);
     if (p.zp_packed == nullptr) return B200Q_ENOSYS;

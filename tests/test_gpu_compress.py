@@ -296,7 +296,7 @@ def test_fast_int4_boundary_cases():
     _cmp_sd(got, want, "nvfp4 thresholds")
 
 
-@pytest.mark.parametrize("name", ["fp8_channel", "int4_channel_sym", "int4_channel_asym"])
+@pytest.mark.parametrize("name", ["fp8_channel", "int4_channel_sym", "int4_channel_asym", "int8_channel_sym"])
 def test_fast_channel_kernel_team_sizes_and_boundaries(name):
     """The bf16 CHANNEL kernel gives a row to a team of 1 / 2 / 4 / 8 warps depending on its length (rows longer than 16384
     fall back to the generic kernel): every team size, ragged row counts (last CTA partly empty), stacked matrices (zero-point

@@ -70,6 +70,9 @@ CASES = [
     ("fp8_channel", (2560, 4096)), ("fp8_channel", (2624, 2048)),
     # MiniMax mixed-precision AWQ recipe: FP8 g32
     ("fp8_g32", (1536, 3072)),
+    # W8A8 weights (REF:scripts/quantization_multiple_modifiers.py:55: self_attn to W8A8): symmetric INT8 per channel, one-, two- and
+    # four-warp row teams of channel_fast_kernel
+    ("int8_channel_sym", (4096, 2560)), ("int8_channel_sym", (2560, 4096)), ("int8_channel_sym", (2560, 9728)), ("int8_channel_sym", (1000, 2056)),
 ]
 
 

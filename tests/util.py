@@ -18,6 +18,7 @@ FORMATS = {
     "int4_channel_sym": ("pack-quantized", O.INT, 4, True, O.CHANNEL, 0, None),
     "int4_channel_asym": ("pack-quantized", O.INT, 4, False, O.CHANNEL, 0, None),
     "int8_g128_sym": ("pack-quantized", O.INT, 8, True, O.GROUP, 128, None),
+    "int8_channel_sym": ("pack-quantized", O.INT, 8, True, O.CHANNEL, 0, None),   # W8A8 presets' weights
     "fp8_channel": ("float-quantized", O.FP8, 8, True, O.CHANNEL, 0, None),
     "fp8_g32": ("float-quantized", O.FP8, 8, True, O.GROUP, 32, None),
     "fp8_g128": ("float-quantized", O.FP8, 8, True, O.GROUP, 128, None),
