@@ -8,6 +8,7 @@
 // the row stays in registers between the statistics and the conversion -> one HBM read, one barrier (none when TW == 1).  The
 // arithmetic is the same bit-exact chain as every other bf16 fast kernel: bracketed reciprocal (fastmath.cuh) with the IEEE
 // repair for the rare element whose bracket ends disagree, qparams as in quant_group_tma.cu.
+#include <cstdlib>
 #include "common.cuh"
 #include "fastmath.cuh"
 #include "fp4.cuh"
@@ -58,7 +59,10 @@ __device__ __forceinline__ uint32_t cvt_s8_biased(float v) {
     return (uint32_t)r;
 }
 
-template <int QT, bool SYM, int TW, int NB = 4>
+// ONE: single evaluation of the quotient (round 2).  x and the row scale are both bf16, so x / s is never closer than 2^-17 (relative) to a
+// bf16 rounding boundary and x * rcp.approx(s) rounds to the reference's T(x / s) -- the argument and brute-force check of
+// tests/test_exact_reciprocal.py, already used by group_tma_kernel.  Scales outside the safe range still take the IEEE repair path.
+template <int QT, bool SYM, int TW, int NB = 4, bool ONE = true>
 __global__ void __launch_bounds__(256, 4) channel_fast_kernel(const TileParams p, const int64_t total_rows) {
     constexpr int RPC = 8 / TW;  // rows per CTA
     constexpr int TL = TW * 32;  // lanes per team
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(256, 4) channel_fast_kernel(const TileParams p
     if (ABS) {
         s = div_const_bf16(__uint_as_float((st_a << 16) & 0x7fff0000u), QT == QT_INT ? (NB == 8 ? 127.5f : 7.5f) : 448.0f);
         if (s == 0.0f) s = eps_of<DT_BF16>();
-        br.init(s);
+        if (ONE) br.init1(s); else br.init(s);
     } else {
         const float mn = fminf(__uint_as_float(st_b << 16), 0.0f), mx = fmaxf(__uint_as_float(st_a << 16), 0.0f);
         const float d = round_to<DT_BF16>(__fadd_rn(mx, -mn));
@@ -136,7 +140,8 @@ __global__ void __launch_bounds__(256, 4) channel_fast_kernel(const TileParams p
         z = round_to<DT_BF16>(__fadd_rn(-8.0f, -t));
         z = (z == z) ? rintf(fminf(fmaxf(z, -8.0f), 7.0f)) : 0.0f;
         s = s0;
-        if (s0 == 0.0f) { s = eps_of<DT_BF16>(); br.init(s); }
+        if (s0 == 0.0f) s = eps_of<DT_BF16>();
+        if (ONE) br.init1(s); else if (s0 == 0.0f) br.init(s);
     }
     if (tl == 0) {
         ((uint16_t*)p.scale)[row] = (uint16_t)(__float_as_uint(s) >> 16);
@@ -166,22 +171,19 @@ __global__ void __launch_bounds__(256, 4) channel_fast_kernel(const TileParams p
                 // T(x / s) in bf16 like the reference, then RNE + clamp + 128 per element (the bf16 magic-number trick of the 4-bit
                 // path needs the sum to stay below 256)
                 unpack2(mul2(x, br.lo), al, ah);
-                unpack2(mul2(x, br.hi), bl, bh);
                 const uint32_t u = cvt_bf16x2(ah, al);
-                diff |= u ^ cvt_bf16x2(bh, bl);
+                if (!ONE) { unpack2(mul2(x, br.hi), bl, bh); diff |= u ^ cvt_bf16x2(bh, bl); }
                 h[k] = prmt(cvt_s8_biased(__uint_as_float(u << 16)), cvt_s8_biased(__uint_as_float(u & 0xffff0000u)), 0x0040);
             } else if (QT == QT_INT) {
                 unpack2(mul2(x, br.lo), al, ah);
-                unpack2(mul2(x, br.hi), bl, bh);
                 uint32_t u = cvt_bf16x2(ah, al);
-                diff |= u ^ cvt_bf16x2(bh, bl);
+                if (!ONE) { unpack2(mul2(x, br.hi), bl, bh); diff |= u ^ cvt_bf16x2(bh, bl); }
                 if (!SYM) u = hadd2(u, z2);
                 h[k] = __viaddmin_s16x2_relu(hadd2(u, kMagic), kUnbias, 0x000f000fu);
             } else {
                 unpack2(add_zp ? mul2_plus0(x, br.lo) : mul2(x, br.lo), al, ah);
-                unpack2(add_zp ? mul2_plus0(x, br.hi) : mul2(x, br.hi), bl, bh);
                 const uint32_t u = cvt_bf16x2(ah, al);
-                diff |= u ^ cvt_bf16x2(bh, bl);
+                if (!ONE) { unpack2(add_zp ? mul2_plus0(x, br.hi) : mul2(x, br.hi), bl, bh); diff |= u ^ cvt_bf16x2(bh, bl); }
                 float ul, uh;
                 unpack2(bf16x2_to_f32x2_fma(u), ul, uh);
                 h[k] = cvt_e4m3x2(uh, ul);
@@ -202,14 +204,20 @@ __global__ void __launch_bounds__(256, 4) channel_fast_kernel(const TileParams p
     }
 }
 
-template <int QT, bool SYM, int NB = 4>
-int launch_rows(const TileParams& p, int64_t total_rows, cudaStream_t st) {
+template <int QT, bool SYM, int NB, bool ONE>
+void launch_rows1(const TileParams& p, int64_t total_rows, cudaStream_t st) {
     const int64_t cap = p.cols;
     auto grid = [&](int rpc) { return (unsigned)((total_rows + rpc - 1) / rpc); };
-    if (cap <= 2048) channel_fast_kernel<QT, SYM, 1, NB><<<grid(8), 256, 0, st>>>(p, total_rows);
-    else if (cap <= 4096) channel_fast_kernel<QT, SYM, 2, NB><<<grid(4), 256, 0, st>>>(p, total_rows);
-    else if (cap <= 8192) channel_fast_kernel<QT, SYM, 4, NB><<<grid(2), 256, 0, st>>>(p, total_rows);
-    else channel_fast_kernel<QT, SYM, 8, NB><<<grid(1), 256, 0, st>>>(p, total_rows);
+    if (cap <= 2048) channel_fast_kernel<QT, SYM, 1, NB, ONE><<<grid(8), 256, 0, st>>>(p, total_rows);
+    else if (cap <= 4096) channel_fast_kernel<QT, SYM, 2, NB, ONE><<<grid(4), 256, 0, st>>>(p, total_rows);
+    else if (cap <= 8192) channel_fast_kernel<QT, SYM, 4, NB, ONE><<<grid(2), 256, 0, st>>>(p, total_rows);
+    else channel_fast_kernel<QT, SYM, 8, NB, ONE><<<grid(1), 256, 0, st>>>(p, total_rows);
+}
+template <int QT, bool SYM, int NB = 4>
+int launch_rows(const TileParams& p, int64_t total_rows, cudaStream_t st) {
+    static const bool bracket = getenv("B200Q_CHANNEL_BRACKET") != nullptr;   // round-1 two-ended evaluation (A/B)
+    if (bracket) launch_rows1<QT, SYM, NB, false>(p, total_rows, st);
+    else launch_rows1<QT, SYM, NB, true>(p, total_rows, st);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }
