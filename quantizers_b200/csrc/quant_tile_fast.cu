@@ -43,7 +43,9 @@ __device__ __noinline__ uint2 fix_chunk_fp8(const uint4 raw, float s, bool add_z
     return make_uint2(o[0], o[1]);
 }
 
-template <bool ADD_ZP, bool FMA>
+// ONE (round 2): single evaluation of the quotient -- x and the block scale are both bf16, so x * rcp.approx(s) rounds to the reference's
+// T(x / s) (tests/test_exact_reciprocal.py; same argument as group_tma_kernel / channel_fast_kernel); unsafe scales keep the IEEE repair.
+template <bool ADD_ZP, bool FMA, bool ONE>
 // 4 CTAs/SM (64 registers): 0.80 -> 0.92 of the HBM roofline against 3 CTAs/SM at 75 registers -- the tile sits in registers
 // between the |max| and the conversion, so every extra resident CTA is 32 KB more in flight
 __global__ void __launch_bounds__(256, 4) block_fp8_fast_kernel(const TileParams p) {
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(256, 4) block_fp8_fast_kernel(const TileParams
     const uint32_t s_bits = __float_as_uint(s);
     if (threadIdx.x == 0) ((uint16_t*)p.scale)[(b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = (uint16_t)(s_bits >> 16);
     Bracket br;
-    br.init(s);
+    if (ONE) br.init1(s); else br.init(s);
     const bool unsafe = !scale_is_safe(s_bits);
 #pragma unroll
     for (int i = 0; i < NC; i++) {
@@ -85,9 +87,8 @@ __global__ void __launch_bounds__(256, 4) block_fp8_fast_kernel(const TileParams
             const f32x2 x = FMA ? bf16x2_to_f32x2_fma(w[k]) : bf16x2_to_f32x2(w[k]);
             float al, ah, bl, bh;
             unpack2(ADD_ZP ? mul2_plus0(x, br.lo) : mul2(x, br.lo), al, ah);
-            unpack2(ADD_ZP ? mul2_plus0(x, br.hi) : mul2(x, br.hi), bl, bh);
             const uint32_t v = cvt_bf16x2(ah, al);
-            diff |= v ^ cvt_bf16x2(bh, bl);
+            if (!ONE) { unpack2(ADD_ZP ? mul2_plus0(x, br.hi) : mul2(x, br.hi), bl, bh); diff |= v ^ cvt_bf16x2(bh, bl); }
             if (FMA) {  // ALU pipe at 72 % (ncu): unpack through FHFMA instead of LOP3 / IMAD.SHL
                 float vl, vh;
                 unpack2(bf16x2_to_f32x2_fma(v), vl, vh);
@@ -775,8 +776,12 @@ int launch_block_fp8_fast(const TileParams& p, int64_t batch, cudaStream_t st) {
     dim3 grid((unsigned)((p.cols + 127) / 128), (unsigned)((p.rows + 127) / 128), (unsigned)batch);
     if (grid.y > 65535 || grid.z > 65535) return B200Q_ENOSYS;
     static const bool fma = getenv("B200Q_FP8_BLOCK_LEGACY_ALU") == nullptr;  // FHFMA unpack: +1 % measured (ALU pipe at 72 %)
-    if (p.has_zp) { if (fma) block_fp8_fast_kernel<true, true><<<grid, 256, 0, st>>>(p); else block_fp8_fast_kernel<true, false><<<grid, 256, 0, st>>>(p); }
-    else { if (fma) block_fp8_fast_kernel<false, true><<<grid, 256, 0, st>>>(p); else block_fp8_fast_kernel<false, false><<<grid, 256, 0, st>>>(p); }
+    static const bool bracket = getenv("B200Q_FP8_BLOCK_BRACKET") != nullptr;  // round-1 two-ended quotient (A/B)
+#define B200Q_BLK(ZP_, FMA_) do { if (bracket) block_fp8_fast_kernel<ZP_, FMA_, false><<<grid, 256, 0, st>>>(p); \
+                                  else block_fp8_fast_kernel<ZP_, FMA_, true><<<grid, 256, 0, st>>>(p); } while (0)
+    if (p.has_zp) { if (fma) B200Q_BLK(true, true); else B200Q_BLK(true, false); }
+    else { if (fma) B200Q_BLK(false, true); else B200Q_BLK(false, false); }
+#undef B200Q_BLK
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
 }
