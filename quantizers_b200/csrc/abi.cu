@@ -130,6 +130,10 @@ int b200q_compress_fp8(const void* weight, int64_t batch, int64_t rows, int64_t 
         }
         return launch_block_fp8_compress(sc->dtype, p, batch, st);
     }
+    if (sc->dtype == B200Q_BF16 && fast_paths_enabled()) {
+        const int rc = launch_tensor_fp8_fast(p, batch, st);
+        if (rc != B200Q_ENOSYS) return rc;
+    }
     return launch_tensor_fp8_compress(sc->dtype, p, batch, st);
 }
 

@@ -34,6 +34,7 @@ int launch_awq_fq_grid_fast(const GroupParams& p, int n_ratios, cudaStream_t st)
 bool tma_paths_enabled();
 int launch_group_fast(int qt, const GroupParams& p, int64_t batch, cudaStream_t st);
 int launch_block_fp8_fast(const TileParams& p, int64_t batch, cudaStream_t st);
+int launch_tensor_fp8_fast(const TileParams& p, int64_t batch, cudaStream_t st);
 int launch_nvfp4_fast(const GroupParams& p, int64_t batch, cudaStream_t st);
 int launch_nvfp4_supplied(const GroupParams& p, int64_t batch, cudaStream_t st, int op = 0);  // caller's bf16 group scales + global scale; op 0 pack, 1 quantize (values), 2 fake_quantize
 int launch_nvfp4_fused(const GroupParams& p, int64_t batch, int span, float* gs_out, uint32_t* sync, cudaStream_t st,

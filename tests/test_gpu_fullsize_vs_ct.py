@@ -72,6 +72,8 @@ CASES = [
     ("fp8_g32", (1536, 3072)),
     # W8A8 weights (REF:scripts/quantization_multiple_modifiers.py:55: self_attn to W8A8): symmetric INT8 per channel, one-, two- and
     # four-warp row teams of channel_fast_kernel
+    # CT's "FP8" preset: one static scale per weight (two-pass bf16 fast path)
+    ("fp8_tensor", (4096, 2560)), ("fp8_tensor", (2624, 2048)), ("fp8_tensor", (37, 1000)),
     ("int8_channel_sym", (4096, 2560)), ("int8_channel_sym", (2560, 4096)), ("int8_channel_sym", (2560, 9728)), ("int8_channel_sym", (1000, 2056)),
 ]
 
